@@ -1,0 +1,197 @@
+/*
+ * lfb200.h -- C ABI of liblfb200.so: the B200-native (sm_100a) hot path of
+ * OceananigansLagrangianFilter.jl's offline filter PDEs.
+ *
+ * This is the drop-in boundary.  It replaces what the reference does between
+ * src/OfflineLagrangianFilter/run_offline_lagrangian_filter.jl:47 and :105, i.e. the
+ * `LagrangianFilter` model (lagrangian_filter.jl:23-180), the five method extensions Oceananigans'
+ * time stepper calls on it (rk3_substep! lagrangian_filter_rk3_substep.jl:11, cache_previous_tendencies!
+ * cache_lagrangian_filter_tendencies.jl:21, update_state! update_lagrangian_filter_state.jl:19,
+ * compute_tendencies! compute_lagrangian_filter_tendencies.jl:16, compute_flux_bc_tendencies! :99),
+ * the update_input_data! callback (src/Utils/lagrangian_filter_utils.jl:1036-1058) and the helpers
+ * that initialise / flip / combine the state (utils:1086-1137, 1232-1251, 898-1012;
+ * src/Utils/post_processing_utils.jl:45-170).  Every entry point cites the reference interface it
+ * stands in for.  The Julia-side `ccall` stubs are in INTEGRATION.md.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no exceptions cross the boundary.  Every function returns
+ *    LFB_OK (0) or a negative error code; lfb_last_error() returns the message of the last failure on
+ *    the calling thread.
+ *  - Host arrays are exactly Oceananigans' `parent(field)`: FP64 (or FP32 for the *_f32 variants),
+ *    column-major, x fastest, halos included; a field located on a Face of a Bounded axis carries one
+ *    extra entry on that axis (w: Nz+1 levels).  They are borrowed only for the duration of the call.
+ *  - The library owns all device memory.  One handle is used from one host thread at a time;
+ *    distinct handles are independent.  With several GPUs every rank (one process per GPU) owns one
+ *    handle holding its y-slab; see lfb_comm_init.
+ *  - There is no CPU fallback: creation fails with LFB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef LFB200_H
+#define LFB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LFB_VERSION 100           /* 0.1.0 */
+
+#define LFB_MAX_COEFFS 8          /* coefficient sets (a,b,c,d), i.e. Butterworth order up to 16 */
+#define LFB_MAX_VARS   8          /* variables to filter                                         */
+
+/* error codes */
+#define LFB_OK              0
+#define LFB_ERR_ARG        -1     /* invalid argument / configuration                            */
+#define LFB_ERR_CUDA       -2     /* CUDA runtime failure (no device, launch or memory error)    */
+#define LFB_ERR_STATE      -3     /* call sequence error (e.g. stepping without resident data)   */
+#define LFB_ERR_NO_DATA    -4     /* no resident snapshot brackets the requested time            */
+#define LFB_ERR_COMM       -5     /* NCCL failure                                                */
+
+/* grid topology per axis (Oceananigans Periodic / Bounded / Flat) */
+#define LFB_PERIODIC 0
+#define LFB_BOUNDED  1
+#define LFB_FLAT     2
+
+/* advection (OfflineFilterConfig.advection, OfflineLagrangianFilter.jl:139,246) */
+#define LFB_ADVECTION_NONE  0     /* advection = nothing: Eulerian filter through the same path  */
+#define LFB_ADVECTION_WENO5 1     /* WENO() default: WENO5-Z, buffers WENO3-Z and Centered2      */
+
+/* kernel selection (lfb_desc.kernel) */
+#define LFB_KERNEL_AUTO    0
+#define LFB_KERNEL_GENERIC 1      /* one thread per cell and coefficient pair, any topology      */
+#define LFB_KERNEL_ZMARCH  2      /* shared-memory x-y tiles marching in z, faces computed once  */
+
+/* field ids for snapshots */
+#define LFB_FIELD_U 0
+#define LFB_FIELD_V 1
+#define LFB_FIELD_W 2
+#define LFB_FIELD_VAR0 3          /* LFB_FIELD_VAR0 + q = q-th entry of var_names_to_filter      */
+
+/* output kinds of lfb_output (create_output_fields, utils:898-1012) */
+#define LFB_OUT_FILTERED_VAR 0    /* <var>_Lagrangian_filtered (or _Eulerian_filtered)           */
+#define LFB_OUT_XI           1    /* xi_<vel>                                                    */
+#define LFB_OUT_MEAN_VEL     2    /* <vel>_Lagrangian_filtered                                   */
+
+typedef struct lfb_handle lfb_handle;
+
+/* Everything the kernels need from OfflineFilterConfig (OfflineLagrangianFilter.jl:83-113) and the
+ * grid; validation of the user-facing options stays on the host side (:255-485). */
+typedef struct lfb_desc {
+    int32_t size[3];              /* Nx, Ny, Nz of THIS rank's slab                              */
+    int32_t halo[3];              /* Hx, Hy, Hz (0 on Flat axes; 3 for the default WENO)         */
+    int32_t topology[3];          /* LFB_PERIODIC / LFB_BOUNDED / LFB_FLAT of the GLOBAL grid    */
+    double  spacing[3];           /* regular spacings; 1.0 on Flat axes                          */
+    int32_t n_vars;               /* length(var_names_to_filter)                                 */
+    int32_t velocity_mask;        /* bit0 u, bit1 v, bit2 w present in velocity_names            */
+    int32_t n_coeffs;             /* filter_params.N_coeffs; 0 encodes the single exponential    */
+    double  a[LFB_MAX_COEFFS], b[LFB_MAX_COEFFS], c[LFB_MAX_COEFFS], d[LFB_MAX_COEFFS];
+    int32_t with_maps;            /* map_to_mean || compute_mean_velocities (utils:439,459)      */
+    int32_t advection;            /* LFB_ADVECTION_*                                             */
+    int32_t n_slots;              /* resident input snapshots (>= 2); InMemory(4) analogue       */
+    int32_t device;               /* CUDA device ordinal                                         */
+    int32_t strict;               /* 1: reference order of operations, no FMA contraction        */
+    int32_t kernel;               /* LFB_KERNEL_*                                                */
+    int32_t relaxation;           /* boundary_relaxation (OfflineLagrangianFilter.jl:108-111)    */
+    double  relax_timescale;
+    int32_t reserved[8];          /* must be zero                                                */
+} lfb_desc;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int         lfb_version(void);
+const char *lfb_last_error(void);
+/* replaces LagrangianFilter(grid; tracers, auxiliary_fields, forcing, advection), lagrangian_filter.jl:78-180 */
+int         lfb_create(const lfb_desc *desc, lfb_handle **out);
+int         lfb_destroy(lfb_handle *h);
+int         lfb_sync(lfb_handle *h);                      /* wait for all queued device work     */
+
+/* ---- tracer bookkeeping (create_filtered_vars, utils:423-470) -------------------------------- */
+int lfb_n_tracers(const lfb_handle *h);
+/* field: 0..n_vars-1 variables, then one map per present velocity in u,v,w order; pole: 0-based
+ * coefficient index; sine: 0 -> _C tracer, 1 -> _S tracer.  Returns the tracer index or <0. */
+int lfb_tracer_index(const lfb_handle *h, int field, int pole, int sine);
+/* number of FP64 elements of a centre-located / velocity parent array of this handle */
+int64_t lfb_parent_len(const lfb_handle *h, int field_id);
+
+/* ---- input series (load_data utils:201-215; update_input_data! utils:1036-1058;
+ *      create_input_data_on_disk utils:97-180) ------------------------------------------------- */
+/* Make `parent` the content of snapshot slot `slot` for `field_id`, tagged with the pass time
+ * `time` (t - T_start on the forward pass).  All fields of one slot must carry the same time.
+ * The copy runs on a side stream and overlaps with queued stage kernels that do not read `slot`. */
+int lfb_upload_snapshot(lfb_handle *h, int slot, int field_id, const double *parent, double time);
+int lfb_upload_snapshot_f32(lfb_handle *h, int slot, int field_id, const float *parent, double time);
+int lfb_invalidate_slot(lfb_handle *h, int slot);
+/* Re-tag a resident slot with a new pass time without touching its data. */
+int lfb_set_slot_time(lfb_handle *h, int slot, double time);
+/* direction = +1: forward pass.  direction = -1: backward pass: velocities are negated on the fly
+ * (utils:169-173).  Together with lfb_set_slot_time(slot, T_end - t) this replaces the reference's
+ * rewrite of the whole input file (utils:154-173): nothing is copied or re-uploaded. */
+int lfb_set_direction(lfb_handle *h, int direction);
+/* relaxation mask evaluated at cell centres (mask_func, utils:584-699); parent layout */
+int lfb_set_mask(lfb_handle *h, const double *parent);
+
+/* ---- state ----------------------------------------------------------------------------------- */
+/* initialise_filtered_vars_from_data, utils:1086-1137 (uses the snapshot at pass time 0) */
+int lfb_init_from_data(lfb_handle *h);
+/* change_sign_of_map_variables!, utils:1232-1251 */
+int lfb_negate_maps(lfb_handle *h);
+/* reset!(model.clock), run_offline_lagrangian_filter.jl:93 */
+int lfb_reset_clock(lfb_handle *h);
+double  lfb_time(const lfb_handle *h);
+int64_t lfb_iteration(const lfb_handle *h);
+/* parent(model.tracers[tracer]) with halos filled as update_state! leaves them */
+int lfb_get_tracer(lfb_handle *h, int tracer, double *parent);
+int lfb_set_tracer(lfb_handle *h, int tracer, const double *parent);
+/* tendency G^n of the CURRENT state at the current time (compute_tendencies!); diagnostic */
+int lfb_get_tendency(lfb_handle *h, int tracer, double *parent);
+
+/* ---- time stepping --------------------------------------------------------------------------- */
+/* One RK3 step of size dt = time_step!(model, dt): three fused stage kernels, each doing for every
+ * tracer the input time interpolation, WENO flux divergence, c div(U), forcing, the RK3 substep and
+ * the tendency caching.  The snapshots bracketing t, t+8dt/15 and t+2dt/3 must be resident. */
+int lfb_step(lfb_handle *h, double dt);
+/* Simulation time-step alignment (Oceananigans run!): steps with
+ * dt_n = min(dt, next multiple of each align interval - t, t_stop - t) until t_stop. */
+int lfb_run_until(lfb_handle *h, double t_stop, double dt, int n_align, const double *align_intervals);
+
+/* ---- outputs (create_output_fields utils:898-1012; written with halos like JLD2Writer) ------- */
+int lfb_output(lfb_handle *h, int kind, int field, double *parent);
+int lfb_output_f32(lfb_handle *h, int kind, int field, float *parent);
+/* sum_forward_backward_contributions!, post:45-170, for one output time on host arrays:
+ * out = fwd + sign * (w_hi*bwd_hi + (1-w_hi)*bwd_lo), computed on the device in FP64.
+ * sign = +1 for filtered vars and xi, -1 for mean velocities (post:151-164). */
+int lfb_combine(lfb_handle *h, int64_t n, const double *fwd, const double *bwd_lo, const double *bwd_hi,
+                double w_hi, double sign, double *out);
+
+/* ---- multi-GPU: y-slab decomposition, one process per GPU ------------------------------------- */
+/* NCCL unique id (128 bytes) created on rank 0 and broadcast by the host (torch.distributed / MPI). */
+int lfb_comm_unique_id(void *id128);
+/* Join the communicator.  Rank r owns rows [r*Ny/R, (r+1)*Ny/R) of the global grid; tracer y-halos
+ * are exchanged with ranks r-1 / r+1 once per RK3 stage (ncclSend/ncclRecv over NVLink) instead of
+ * being filled locally.  Stands in for Oceananigans' Distributed halo fill + compute_buffer_tendencies!
+ * (compute_lagrangian_filter_buffer_tendencies.jl:8-38). */
+int lfb_comm_init(lfb_handle *h, const void *id128, int rank, int nranks);
+
+/* ---- introspection ---------------------------------------------------------------------------- */
+/* kernels launched by this handle since creation (bench.py's gpu_launches) */
+int64_t lfb_kernel_launches(const lfb_handle *h);
+/* device time (ms) spent in RK3 stage kernels since the last call with reset != 0, measured with
+ * CUDA events on the compute stream, and the number of stage launches it covers */
+int lfb_stage_time_ms(lfb_handle *h, int reset, double *ms, int64_t *launches);
+/* CUDA-event stopwatch on the compute stream (the stream every stage kernel is launched on):
+ * lfb_timer_start records an event, lfb_timer_stop records a second one, waits for it and returns
+ * the device time between the two in milliseconds. */
+int lfb_timer_start(lfb_handle *h);
+int lfb_timer_stop(lfb_handle *h, double *ms);
+/* name of the stage kernel in use: "generic" | "generic-strict" | "zmarch" */
+const char *lfb_kernel_name(const lfb_handle *h);
+/* raw device pointers for zero-copy hosts (torch): what = 0 tracer (current), 1 tendency,
+ * 2 snapshot slot (idx = slot * 16 + field_id); internal padded layout, see lfb_layout */
+void *lfb_device_ptr(lfb_handle *h, int what, int idx);
+/* internal layout: element (i,j,k) (0-based interior) lives at x_offset + i + pitch*((Hy + j) + rows*(Hz + k)) */
+int lfb_layout(const lfb_handle *h, int64_t *x_offset, int64_t *pitch, int64_t *rows, int64_t *planes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFB200_H */

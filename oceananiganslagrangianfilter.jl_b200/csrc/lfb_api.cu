@@ -1,0 +1,877 @@
+// lfb_api.cu -- host side of liblfb200.so: the C ABI declared in include/lfb200.h.
+//
+// Owns device memory, streams and the RK3 / snapshot bookkeeping; all arithmetic on field data is
+// done by the kernels in lfb_generic.cu / lfb_zmarch.cu.  No CPU fallback exists: every entry point
+// that touches field data requires a CUDA device.
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "lfb_internal.h"
+
+// ---- kernel launchers (lfb_generic.cu, lfb_zmarch.cu) -------------------------------------------
+extern "C" {
+cudaError_t lfb_launch_stage_generic(const LfbStageParams *P, int strict, cudaStream_t stream);
+cudaError_t lfb_launch_stage_zmarch(const LfbStageParams *P, cudaStream_t stream);
+int         lfb_zmarch_supported(const LfbStageParams *P);
+cudaError_t lfb_launch_fill_halo_axis(double *base, int64_t field_stride, int n_fields, const LfbLayout *L,
+                                      int ax, int mode, cudaStream_t stream);
+cudaError_t lfb_launch_import(double *dst, const void *src, int is_f32, const LfbLayout *L, int ex, int ey, int ez,
+                              cudaStream_t stream);
+cudaError_t lfb_launch_export(void *dst, int is_f32, const double *src, const LfbLayout *L, int ex, int ey, int ez,
+                              cudaStream_t stream);
+cudaError_t lfb_launch_centre_velocity(double *dst, const double *vel, const LfbLayout *L, int ax, double sign,
+                                       cudaStream_t stream);
+cudaError_t lfb_launch_scale(double *dst, const double *src, double factor, int64_t n, cudaStream_t stream);
+cudaError_t lfb_launch_output(double *out, const LfbOutputParams *P, cudaStream_t stream);
+cudaError_t lfb_launch_combine(double *out, const double *fwd, const double *lo, const double *hi, double w,
+                               double sign, int64_t n, cudaStream_t stream);
+cudaError_t lfb_launch_pack_y(double *buf, double *base, int64_t field_stride, int n_fields, const LfbLayout *L,
+                              int side, int unpack, cudaStream_t stream);
+}
+
+// ---- error plumbing ------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(LFB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define NC(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess)                                                                     \
+            return fail(LFB_ERR_COMM, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
+#define N_FIELD_IDS (3 + LFB_MAX_VARS)
+
+struct lfb_handle {
+    lfb_desc   desc;
+    LfbLayout  L;
+    int        device;
+    int        n_maps, n_fields, n_items, n_tracers, sub;   // sub = tracers per item (1 or 2)
+    int        map_axis[3];
+    LfbItem    items[LFB_MAX_ITEMS];
+    int        single_exp, n_pairs;
+    // device storage
+    double    *U[2];
+    double    *G;
+    double    *scratch;                    // one field
+    double    *mask;
+    void      *staging;                    // dense parent array, device side
+    size_t     staging_bytes;
+    std::vector<double *> slot_field;      // [slot * N_FIELD_IDS + field_id]
+    std::vector<double>   slot_time;
+    std::vector<uint32_t> slot_valid;      // bit per field id
+    std::vector<cudaEvent_t> slot_ready;   // import finished (recorded on the copy stream)
+    std::vector<cudaEvent_t> slot_used;    // last stage kernel reading the slot (compute stream)
+    std::vector<int>      slot_pending;    // compute stream has not yet waited for slot_ready
+    int        cur;                        // index of the current U buffer
+    double     time;
+    int64_t    iteration;
+    int        direction;
+    cudaStream_t compute, copy;
+    cudaEvent_t  ev_tmp, ev_t0, ev_t1;
+    // statistics
+    int64_t    launches;
+    double     stage_ms;
+    int64_t    stage_launches;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;   // pending stage timings
+    int        use_zmarch;
+    // distributed y-slabs
+    ncclComm_t comm;
+    int        rank, nranks;
+    double    *send_lo, *send_hi, *recv_lo, *recv_hi;
+    size_t     halo_elems;
+};
+
+static inline int field_present(const lfb_handle *h, int field_id)
+{
+    if (field_id < 0) return 0;
+    if (field_id < 3) return (h->desc.velocity_mask >> field_id) & 1;
+    return field_id - 3 < h->desc.n_vars;
+}
+
+// interior extent of a field along each axis (N, or N+1 for a velocity on its own Bounded axis)
+static void parent_extents(const lfb_handle *h, int field_id, int e[3])
+{
+    for (int ax = 0; ax < 3; ++ax) {
+        int n = h->L.N[ax];
+        if (field_id == ax && h->L.topo[ax] == LFB_BOUNDED && !(ax == 1 && h->nranks > 1 && h->rank != h->nranks - 1)) n += 1;
+        e[ax] = n + 2 * h->L.H[ax];
+    }
+}
+
+extern "C" int lfb_version(void) { return LFB_VERSION; }
+extern "C" const char *lfb_last_error(void) { return g_err; }
+
+static void build_layout(lfb_handle *h)
+{
+    LfbLayout &L = h->L;
+    const lfb_desc &d = h->desc;
+    for (int ax = 0; ax < 3; ++ax) {
+        L.N[ax] = d.size[ax];
+        L.H[ax] = d.halo[ax];
+        L.topo[ax] = d.topology[ax];
+        L.NG[ax] = d.size[ax];
+        L.goff[ax] = 0;
+        L.connected_lo[ax] = L.connected_hi[ax] = 0;
+    }
+    L.xoff = L.H[0] > 0 ? LFB_XPAD : 0;
+    int need = L.xoff + L.N[0] + L.H[0] + 1;
+    L.pitch = (need + 15) / 16 * 16;
+    L.rows = L.N[1] + 2 * L.H[1] + 1;
+    L.planes = L.N[2] + 2 * L.H[2] + 1;
+    L.plane = (int64_t)L.pitch * L.rows;
+    L.len = L.plane * L.planes;
+    L.stride[0] = 1; L.stride[1] = L.pitch; L.stride[2] = L.plane;
+}
+
+extern "C" int lfb_create(const lfb_desc *desc, lfb_handle **out)
+{
+    if (!desc || !out) return fail(LFB_ERR_ARG, "null argument");
+    *out = nullptr;
+    for (int ax = 0; ax < 3; ++ax) {
+        if (desc->size[ax] < 1) return fail(LFB_ERR_ARG, "size[%d] = %d", ax, desc->size[ax]);
+        if (desc->topology[ax] < 0 || desc->topology[ax] > 2) return fail(LFB_ERR_ARG, "topology[%d] invalid", ax);
+        if (desc->topology[ax] == LFB_FLAT && (desc->size[ax] != 1 || desc->halo[ax] != 0))
+            return fail(LFB_ERR_ARG, "Flat axis %d must have size 1 and halo 0", ax);
+        if (desc->topology[ax] != LFB_FLAT && desc->advection == LFB_ADVECTION_WENO5 && desc->halo[ax] < 3)
+            return fail(LFB_ERR_ARG, "WENO5 needs halo >= 3 on axis %d (got %d)", ax, desc->halo[ax]);
+        if (desc->halo[ax] < 0 || desc->halo[ax] > 8) return fail(LFB_ERR_ARG, "halo[%d] out of range", ax);
+        if (!(desc->spacing[ax] > 0)) return fail(LFB_ERR_ARG, "spacing[%d] must be positive", ax);
+        if (desc->topology[ax] == LFB_PERIODIC && desc->size[ax] < desc->halo[ax])
+            return fail(LFB_ERR_ARG, "periodic axis %d shorter than its halo", ax);
+    }
+    if (desc->n_vars < 0 || desc->n_vars > LFB_MAX_VARS) return fail(LFB_ERR_ARG, "n_vars out of range");
+    if (desc->n_coeffs < 0 || desc->n_coeffs > LFB_MAX_COEFFS) return fail(LFB_ERR_ARG, "n_coeffs out of range");
+    if (desc->n_slots < 2 || desc->n_slots > 4096) return fail(LFB_ERR_ARG, "n_slots must be in [2, 4096]");
+    if (desc->advection != LFB_ADVECTION_NONE && desc->advection != LFB_ADVECTION_WENO5)
+        return fail(LFB_ERR_ARG, "unknown advection id %d", desc->advection);
+    if (desc->relaxation && !(desc->relax_timescale > 0)) return fail(LFB_ERR_ARG, "relax_timescale must be set");
+    for (int q = 0; q < 8; ++q) if (desc->reserved[q]) return fail(LFB_ERR_ARG, "reserved fields must be zero");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(LFB_ERR_CUDA, "no CUDA device available (%s); liblfb200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (desc->device < 0 || desc->device >= ndev) return fail(LFB_ERR_ARG, "device %d not in [0,%d)", desc->device, ndev);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, desc->device));
+    if (prop.major != 10)
+        return fail(LFB_ERR_CUDA, "device %d is sm_%d%d; liblfb200 is built for sm_100a only", desc->device, prop.major, prop.minor);
+    CU(cudaSetDevice(desc->device));
+
+    lfb_handle *h = new lfb_handle();
+    h->desc = *desc;
+    h->device = desc->device;
+    build_layout(h);
+    h->single_exp = desc->n_coeffs == 0;
+    h->n_pairs = h->single_exp ? 1 : desc->n_coeffs;
+    h->sub = h->single_exp ? 1 : 2;
+    h->n_maps = 0;
+    if (desc->with_maps)
+        for (int ax = 0; ax < 3; ++ax) if ((desc->velocity_mask >> ax) & 1) h->map_axis[h->n_maps++] = ax;
+    h->n_fields = desc->n_vars + h->n_maps;
+    h->n_items = h->n_fields * h->n_pairs;
+    if (h->n_items > LFB_MAX_ITEMS) { delete h; return fail(LFB_ERR_ARG, "too many tracers (%d items > %d)", h->n_items, LFB_MAX_ITEMS); }
+    h->n_tracers = h->n_items * h->sub;
+    for (int f = 0; f < h->n_fields; ++f)
+        for (int p = 0; p < h->n_pairs; ++p) {
+            LfbItem &it = h->items[f * h->n_pairs + p];
+            it.is_map = f >= desc->n_vars;
+            it.src = it.is_map ? h->map_axis[f - desc->n_vars] : f;
+            it.tracer_c = (f * h->n_pairs + p) * h->sub;
+            it.pad = 0;
+            it.c = desc->c[p];
+            it.d = h->single_exp ? 0.0 : desc->d[p];
+        }
+    const LfbLayout &L = h->L;
+    const size_t fbytes = (size_t)L.len * sizeof(double);
+    h->U[0] = h->U[1] = h->G = h->scratch = h->mask = nullptr;
+    h->staging = nullptr;
+    h->comm = nullptr; h->rank = 0; h->nranks = 1;
+    h->send_lo = h->send_hi = h->recv_lo = h->recv_hi = nullptr;
+    const int nt = h->n_tracers > 0 ? h->n_tracers : 1;
+    CU(cudaMalloc(&h->U[0], fbytes * nt));
+    CU(cudaMalloc(&h->U[1], fbytes * nt));
+    CU(cudaMalloc(&h->G, fbytes * nt));
+    CU(cudaMalloc(&h->scratch, fbytes));
+    CU(cudaMemset(h->U[0], 0, fbytes * nt));
+    CU(cudaMemset(h->U[1], 0, fbytes * nt));
+    CU(cudaMemset(h->G, 0, fbytes * nt));
+    CU(cudaMemset(h->scratch, 0, fbytes));
+    if (desc->relaxation) { CU(cudaMalloc(&h->mask, fbytes)); CU(cudaMemset(h->mask, 0, fbytes)); }
+    h->staging_bytes = fbytes;     // dense parent arrays are never larger than the padded layout
+    CU(cudaMalloc(&h->staging, h->staging_bytes));
+    const int ns = desc->n_slots;
+    h->slot_field.assign((size_t)ns * N_FIELD_IDS, nullptr);
+    h->slot_time.assign(ns, 0.0);
+    h->slot_valid.assign(ns, 0u);
+    h->slot_pending.assign(ns, 0);
+    h->slot_ready.resize(ns);
+    h->slot_used.resize(ns);
+    for (int s = 0; s < ns; ++s) {
+        CU(cudaEventCreateWithFlags(&h->slot_ready[s], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->slot_used[s], cudaEventDisableTiming));
+        for (int f = 0; f < N_FIELD_IDS; ++f)
+            if (field_present(h, f)) {
+                CU(cudaMalloc(&h->slot_field[(size_t)s * N_FIELD_IDS + f], fbytes));
+                CU(cudaMemset(h->slot_field[(size_t)s * N_FIELD_IDS + f], 0, fbytes));
+            }
+    }
+    CU(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_tmp, cudaEventDisableTiming));
+    CU(cudaEventCreate(&h->ev_t0));
+    CU(cudaEventCreate(&h->ev_t1));
+    h->cur = 0; h->time = 0; h->iteration = 0; h->direction = 1;
+    h->launches = 0; h->stage_ms = 0; h->stage_launches = 0;
+    h->use_zmarch = 0;
+    CU(cudaDeviceSynchronize());
+    *out = h;
+    return LFB_OK;
+}
+
+extern "C" int lfb_destroy(lfb_handle *h)
+{
+    if (!h) return LFB_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (h->comm) ncclCommDestroy(h->comm);
+    for (double *p : h->slot_field) if (p) cudaFree(p);
+    for (cudaEvent_t e : h->slot_ready) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->slot_used) cudaEventDestroy(e);
+    for (auto &pr : h->timing) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    cudaFree(h->U[0]); cudaFree(h->U[1]); cudaFree(h->G); cudaFree(h->scratch);
+    if (h->mask) cudaFree(h->mask);
+    cudaFree(h->staging);
+    if (h->send_lo) { cudaFree(h->send_lo); cudaFree(h->send_hi); cudaFree(h->recv_lo); cudaFree(h->recv_hi); }
+    cudaStreamDestroy(h->compute); cudaStreamDestroy(h->copy);
+    cudaEventDestroy(h->ev_tmp); cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1);
+    delete h;
+    return LFB_OK;
+}
+
+extern "C" int lfb_sync(lfb_handle *h)
+{
+    if (!h) return fail(LFB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->copy));
+    CU(cudaStreamSynchronize(h->compute));
+    return LFB_OK;
+}
+
+extern "C" int lfb_n_tracers(const lfb_handle *h) { return h ? h->n_tracers : LFB_ERR_ARG; }
+
+extern "C" int lfb_tracer_index(const lfb_handle *h, int field, int pole, int sine)
+{
+    if (!h || field < 0 || field >= h->n_fields || pole < 0 || pole >= h->n_pairs || sine < 0 || sine >= h->sub)
+        return fail(LFB_ERR_ARG, "no tracer (field %d, pole %d, sine %d)", field, pole, sine);
+    return (field * h->n_pairs + pole) * h->sub + sine;
+}
+
+extern "C" int64_t lfb_parent_len(const lfb_handle *h, int field_id)
+{
+    if (!h) return LFB_ERR_ARG;
+    int e[3];
+    parent_extents(h, field_id, e);
+    return (int64_t)e[0] * e[1] * e[2];
+}
+
+// ---- input series --------------------------------------------------------------------------------
+static int upload_impl(lfb_handle *h, int slot, int field_id, const void *parent, int is_f32, double time)
+{
+    if (!h || !parent) return fail(LFB_ERR_ARG, "null argument");
+    if (slot < 0 || slot >= h->desc.n_slots) return fail(LFB_ERR_ARG, "slot %d out of range", slot);
+    if (!field_present(h, field_id)) return fail(LFB_ERR_ARG, "field id %d is not part of this handle", field_id);
+    CU(cudaSetDevice(h->device));
+    int e[3];
+    parent_extents(h, field_id, e);
+    const size_t n = (size_t)e[0] * e[1] * e[2];
+    const size_t bytes = n * (is_f32 ? sizeof(float) : sizeof(double));
+    // the slot may still be read by stage kernels queued earlier
+    CU(cudaStreamWaitEvent(h->copy, h->slot_used[slot], 0));
+    CU(cudaMemcpyAsync(h->staging, parent, bytes, cudaMemcpyHostToDevice, h->copy));
+    CU(cudaEventRecord(h->ev_tmp, h->copy));
+    double *dst = h->slot_field[(size_t)slot * N_FIELD_IDS + field_id];
+    CU(lfb_launch_import(dst, h->staging, is_f32, &h->L, e[0], e[1], e[2], h->copy));
+    h->launches++;
+    CU(cudaEventRecord(h->slot_ready[slot], h->copy));
+    h->slot_pending[slot] = 1;
+    if (h->slot_valid[slot] && h->slot_time[slot] != time) h->slot_valid[slot] = 0;
+    h->slot_time[slot] = time;
+    h->slot_valid[slot] |= 1u << field_id;
+    // the host buffer is only borrowed: wait for the H2D copy (not for the import kernel)
+    CU(cudaEventSynchronize(h->ev_tmp));
+    return LFB_OK;
+}
+
+extern "C" int lfb_upload_snapshot(lfb_handle *h, int slot, int field_id, const double *parent, double time)
+{
+    return upload_impl(h, slot, field_id, parent, 0, time);
+}
+
+extern "C" int lfb_upload_snapshot_f32(lfb_handle *h, int slot, int field_id, const float *parent, double time)
+{
+    return upload_impl(h, slot, field_id, parent, 1, time);
+}
+
+extern "C" int lfb_invalidate_slot(lfb_handle *h, int slot)
+{
+    if (!h || slot < 0 || slot >= h->desc.n_slots) return fail(LFB_ERR_ARG, "slot out of range");
+    h->slot_valid[slot] = 0;
+    return LFB_OK;
+}
+
+extern "C" int lfb_set_slot_time(lfb_handle *h, int slot, double time)
+{
+    if (!h || slot < 0 || slot >= h->desc.n_slots) return fail(LFB_ERR_ARG, "slot out of range");
+    h->slot_time[slot] = time;
+    return LFB_OK;
+}
+
+extern "C" int lfb_set_direction(lfb_handle *h, int direction)
+{
+    if (!h || (direction != 1 && direction != -1)) return fail(LFB_ERR_ARG, "direction must be +1 or -1");
+    h->direction = direction;
+    return LFB_OK;
+}
+
+static uint32_t required_mask(const lfb_handle *h)
+{
+    uint32_t m = (uint32_t)h->desc.velocity_mask & 7u;
+    for (int q = 0; q < h->desc.n_vars; ++q) m |= 1u << (3 + q);
+    return m;
+}
+
+// slots bracketing pass time tau: s1 = latest slot with time <= tau, s2 = earliest slot with time > tau
+static int bracket(const lfb_handle *h, double tau, int *s1, int *s2, double *w1, double *w2, int *interp)
+{
+    const uint32_t need = required_mask(h);
+    int a = -1, b = -1;
+    for (int s = 0; s < h->desc.n_slots; ++s) {
+        if ((h->slot_valid[s] & need) != need) continue;
+        const double t = h->slot_time[s];
+        if (t <= tau) { if (a < 0 || t > h->slot_time[a]) a = s; }
+        else          { if (b < 0 || t < h->slot_time[b]) b = s; }
+    }
+    if (a < 0) return fail(LFB_ERR_NO_DATA, "no resident snapshot at or before pass time %.17g", tau);
+    *s1 = a;
+    if (h->slot_time[a] == tau) { *s2 = a; *w1 = 1; *w2 = 0; *interp = 0; return LFB_OK; }
+    if (b < 0) return fail(LFB_ERR_NO_DATA, "no resident snapshot after pass time %.17g", tau);
+    const double t1 = h->slot_time[a], t2 = h->slot_time[b];
+    const double n = (tau - t1) / (t2 - t1);
+    *s2 = b; *w2 = n; *w1 = 1 - n; *interp = 1;
+    return LFB_OK;
+}
+
+extern "C" int lfb_set_mask(lfb_handle *h, const double *parent)
+{
+    if (!h || !parent) return fail(LFB_ERR_ARG, "null argument");
+    if (!h->mask) return fail(LFB_ERR_STATE, "handle was created without relaxation");
+    CU(cudaSetDevice(h->device));
+    int e[3];
+    parent_extents(h, -1, e);
+    CU(cudaStreamSynchronize(h->copy));
+    CU(cudaMemcpyAsync(h->staging, parent, (size_t)e[0] * e[1] * e[2] * sizeof(double), cudaMemcpyHostToDevice, h->compute));
+    CU(lfb_launch_import(h->mask, h->staging, 0, &h->L, e[0], e[1], e[2], h->compute));
+    h->launches++;
+    CU(cudaStreamSynchronize(h->compute));
+    return LFB_OK;
+}
+
+// ---- halo handling -------------------------------------------------------------------------------
+// Periodic halos of the current tracer buffer (what the stencils read).  Bounded-axis halos are never
+// read by the stencils and are only produced for exported arrays.
+static int fill_periodic_halos(lfb_handle *h, double *base, int n_fields)
+{
+    for (int ax = 0; ax < 3; ++ax) {
+        if (h->L.topo[ax] != LFB_PERIODIC) continue;
+        if (ax == 1 && h->nranks > 1) continue;     // exchanged with the neighbour ranks instead
+        CU(lfb_launch_fill_halo_axis(base, h->L.len, n_fields, &h->L, ax, 0, h->compute));
+        h->launches++;
+    }
+    return LFB_OK;
+}
+
+static int fill_all_halos(lfb_handle *h, double *base, int n_fields)
+{
+    for (int ax = 0; ax < 3; ++ax) {
+        if (h->L.topo[ax] == LFB_FLAT || h->L.H[ax] == 0) continue;
+        if (ax == 1 && h->nranks > 1) continue;
+        CU(lfb_launch_fill_halo_axis(base, h->L.len, n_fields, &h->L, ax, h->L.topo[ax] == LFB_PERIODIC ? 0 : 1, h->compute));
+        h->launches++;
+    }
+    return LFB_OK;
+}
+
+// y-halo exchange between neighbouring slabs: pack the H edge rows of every tracer, ncclSend/Recv
+// them to ranks r-1 / r+1 (periodic wrap when the global y axis is Periodic), unpack into the halos.
+static int exchange_y(lfb_handle *h, double *base, int n_fields)
+{
+    if (h->nranks <= 1 || h->L.H[1] == 0) return LFB_OK;
+    const bool periodic = h->L.topo[1] == LFB_PERIODIC;
+    const int lo = h->rank > 0 ? h->rank - 1 : (periodic ? h->nranks - 1 : -1);
+    const int hi = h->rank < h->nranks - 1 ? h->rank + 1 : (periodic ? 0 : -1);
+    const size_t per_field = (size_t)(h->L.N[0] + 2 * h->L.H[0]) * h->L.H[1] * (h->L.N[2] + 2 * h->L.H[2]);
+    const size_t count = per_field * n_fields;
+    if (lo >= 0) { CU(lfb_launch_pack_y(h->send_lo, base, h->L.len, n_fields, &h->L, 0, 0, h->compute)); h->launches++; }
+    if (hi >= 0) { CU(lfb_launch_pack_y(h->send_hi, base, h->L.len, n_fields, &h->L, 1, 0, h->compute)); h->launches++; }
+    NC(ncclGroupStart());
+    if (lo >= 0) { NC(ncclSend(h->send_lo, count, ncclDouble, lo, h->comm, h->compute)); NC(ncclRecv(h->recv_lo, count, ncclDouble, lo, h->comm, h->compute)); }
+    if (hi >= 0) { NC(ncclSend(h->send_hi, count, ncclDouble, hi, h->comm, h->compute)); NC(ncclRecv(h->recv_hi, count, ncclDouble, hi, h->comm, h->compute)); }
+    NC(ncclGroupEnd());
+    if (lo >= 0) { CU(lfb_launch_pack_y(h->recv_lo, base, h->L.len, n_fields, &h->L, 0, 1, h->compute)); h->launches++; }
+    if (hi >= 0) { CU(lfb_launch_pack_y(h->recv_hi, base, h->L.len, n_fields, &h->L, 1, 1, h->compute)); h->launches++; }
+    return LFB_OK;
+}
+
+static int refresh_halos(lfb_handle *h, double *base, int n_fields)
+{
+    int rc = fill_periodic_halos(h, base, n_fields);
+    if (rc) return rc;
+    return exchange_y(h, base, n_fields);
+}
+
+// ---- state ---------------------------------------------------------------------------------------
+extern "C" int lfb_init_from_data(lfb_handle *h)
+{
+    if (!h) return fail(LFB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    int s1, s2, interp; double w1, w2;
+    int rc = bracket(h, 0.0, &s1, &s2, &w1, &w2, &interp);
+    if (rc) return rc;
+    if (interp) return fail(LFB_ERR_NO_DATA, "initialisation needs a resident snapshot at pass time 0");
+    CU(cudaStreamWaitEvent(h->compute, h->slot_ready[s1], 0));
+    h->slot_pending[s1] = 0;
+    const LfbLayout &L = h->L;
+    const double sign = h->direction < 0 ? -1.0 : 1.0;
+    for (int f = 0; f < h->n_fields; ++f) {
+        const bool is_map = f >= h->desc.n_vars;
+        const double *src;
+        if (!is_map) src = h->slot_field[(size_t)s1 * N_FIELD_IDS + 3 + f];
+        else {
+            const int ax = h->map_axis[f - h->desc.n_vars];
+            CU(cudaMemsetAsync(h->scratch, 0, (size_t)L.len * sizeof(double), h->compute));
+            CU(lfb_launch_centre_velocity(h->scratch, h->slot_field[(size_t)s1 * N_FIELD_IDS + ax], &L, ax, sign, h->compute));
+            h->launches++;
+            rc = fill_all_halos(h, h->scratch, 1);
+            if (rc) return rc;
+            rc = exchange_y(h, h->scratch, 1);
+            if (rc) return rc;
+            src = h->scratch;
+        }
+        for (int p = 0; p < h->n_pairs; ++p) {
+            const double c = h->desc.c[p], d = h->single_exp ? 0.0 : h->desc.d[p];
+            double fC, fS = 0;
+            if (h->single_exp) fC = is_map ? (-1 / (c * c)) : 1 / c;
+            else if (!is_map) { fC = c / (c * c + d * d); fS = d / (c * c + d * d); }
+            else { const double n2 = c * c + d * d; fC = (d * d - c * c) / (n2 * n2); fS = -2 * c * d / (n2 * n2); }
+            const int tc = (f * h->n_pairs + p) * h->sub;
+            for (int b = 0; b < 2; ++b) {
+                CU(lfb_launch_scale(h->U[b] + (int64_t)tc * L.len, src, fC, L.len, h->compute));
+                h->launches++;
+                if (!h->single_exp) {
+                    CU(lfb_launch_scale(h->U[b] + (int64_t)(tc + 1) * L.len, src, fS, L.len, h->compute));
+                    h->launches++;
+                }
+            }
+        }
+    }
+    h->cur = 0; h->time = 0; h->iteration = 0;
+    return LFB_OK;
+}
+
+extern "C" int lfb_negate_maps(lfb_handle *h)
+{
+    if (!h) return fail(LFB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    const LfbLayout &L = h->L;
+    for (int f = h->desc.n_vars; f < h->n_fields; ++f)
+        for (int p = 0; p < h->n_pairs; ++p)
+            for (int s = 0; s < h->sub; ++s)
+                for (int b = 0; b < 2; ++b) {
+                    double *U = h->U[b] + (int64_t)((f * h->n_pairs + p) * h->sub + s) * L.len;
+                    CU(lfb_launch_scale(U, U, -1.0, L.len, h->compute));
+                    h->launches++;
+                }
+    return LFB_OK;
+}
+
+extern "C" int lfb_reset_clock(lfb_handle *h)
+{
+    if (!h) return fail(LFB_ERR_ARG, "null handle");
+    h->time = 0; h->iteration = 0;
+    return LFB_OK;
+}
+
+extern "C" double lfb_time(const lfb_handle *h) { return h ? h->time : NAN; }
+extern "C" int64_t lfb_iteration(const lfb_handle *h) { return h ? h->iteration : -1; }
+
+static int download(lfb_handle *h, const double *src, void *parent, int is_f32, int field_id)
+{
+    int e[3];
+    parent_extents(h, field_id, e);
+    const size_t n = (size_t)e[0] * e[1] * e[2];
+    CU(cudaStreamSynchronize(h->copy));      // staging is shared with uploads
+    CU(lfb_launch_export(h->staging, is_f32, src, &h->L, e[0], e[1], e[2], h->compute));
+    h->launches++;
+    CU(cudaMemcpyAsync(parent, h->staging, n * (is_f32 ? sizeof(float) : sizeof(double)), cudaMemcpyDeviceToHost, h->compute));
+    CU(cudaStreamSynchronize(h->compute));
+    return LFB_OK;
+}
+
+extern "C" int lfb_get_tracer(lfb_handle *h, int tracer, double *parent)
+{
+    if (!h || !parent) return fail(LFB_ERR_ARG, "null argument");
+    if (tracer < 0 || tracer >= h->n_tracers) return fail(LFB_ERR_ARG, "tracer %d out of range", tracer);
+    CU(cudaSetDevice(h->device));
+    double *U = h->U[h->cur] + (int64_t)tracer * h->L.len;
+    int rc = fill_all_halos(h, U, 1);
+    if (rc) return rc;
+    rc = exchange_y(h, U, 1);
+    if (rc) return rc;
+    return download(h, U, parent, 0, -1);
+}
+
+extern "C" int lfb_set_tracer(lfb_handle *h, int tracer, const double *parent)
+{
+    if (!h || !parent) return fail(LFB_ERR_ARG, "null argument");
+    if (tracer < 0 || tracer >= h->n_tracers) return fail(LFB_ERR_ARG, "tracer %d out of range", tracer);
+    CU(cudaSetDevice(h->device));
+    int e[3];
+    parent_extents(h, -1, e);
+    CU(cudaStreamSynchronize(h->copy));
+    CU(cudaMemcpyAsync(h->staging, parent, (size_t)e[0] * e[1] * e[2] * sizeof(double), cudaMemcpyHostToDevice, h->compute));
+    for (int b = 0; b < 2; ++b) {
+        CU(lfb_launch_import(h->U[b] + (int64_t)tracer * h->L.len, h->staging, 0, &h->L, e[0], e[1], e[2], h->compute));
+        h->launches++;
+    }
+    CU(cudaStreamSynchronize(h->compute));
+    return LFB_OK;
+}
+
+// ---- time stepping -------------------------------------------------------------------------------
+static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, double zeta, int first, int store_G, int update)
+{
+    LfbStageParams P;
+    memset(&P, 0, sizeof(P));
+    P.L = h->L;
+    P.U_old = h->U[h->cur];
+    P.U_new = h->U[1 - h->cur];
+    P.G = h->G;
+    P.n_items = h->n_items;
+    P.single_exp = h->single_exp;
+    P.advect = h->desc.advection != LFB_ADVECTION_NONE;
+    P.relax = h->desc.relaxation;
+    memcpy(P.items, h->items, sizeof(LfbItem) * h->n_items);
+    int s1, s2, interp; double w1, w2;
+    int rc = bracket(h, tau, &s1, &s2, &w1, &w2, &interp);
+    if (rc) return rc;
+    for (int s : {s1, s2})
+        if (h->slot_pending[s]) { CU(cudaStreamWaitEvent(h->compute, h->slot_ready[s], 0)); h->slot_pending[s] = 0; }
+    for (int ax = 0; ax < 3; ++ax) {
+        P.vel_present[ax] = (h->desc.velocity_mask >> ax) & 1;
+        P.vel1[ax] = h->slot_field[(size_t)s1 * N_FIELD_IDS + ax];
+        P.vel2[ax] = h->slot_field[(size_t)s2 * N_FIELD_IDS + ax];
+        P.area[ax] = 1.0;
+    }
+    for (int q = 0; q < h->desc.n_vars; ++q) {
+        P.var1[q] = h->slot_field[(size_t)s1 * N_FIELD_IDS + 3 + q];
+        P.var2[q] = h->slot_field[(size_t)s2 * N_FIELD_IDS + 3 + q];
+    }
+    P.mask = h->mask;
+    P.interp = interp; P.w1 = w1; P.w2 = w2;
+    P.vel_sign = h->direction < 0 ? -1.0 : 1.0;
+    const double dx = h->desc.spacing[0], dy = h->desc.spacing[1], dz = h->desc.spacing[2];
+    P.area[0] = dy * dz; P.area[1] = dx * dz; P.area[2] = dx * dy; P.volume = dx * dy * dz;
+    P.relax_timescale = h->desc.relax_timescale;
+    P.dt = dt; P.gamma = gamma; P.zeta = zeta;
+    P.first_stage = first; P.store_G = store_G; P.update = update;
+    P.j0 = 0; P.j1 = h->L.N[1];
+
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, h->compute));
+    if (h->use_zmarch && update) CU(lfb_launch_stage_zmarch(&P, h->compute));
+    else                         CU(lfb_launch_stage_generic(&P, h->desc.strict, h->compute));
+    CU(cudaEventRecord(e1, h->compute));
+    h->timing.push_back({e0, e1});
+    h->launches++;
+    CU(cudaEventRecord(h->slot_used[s1], h->compute));
+    if (s2 != s1) CU(cudaEventRecord(h->slot_used[s2], h->compute));
+    return LFB_OK;
+}
+
+static int drain_timings(lfb_handle *h, bool wait)
+{
+    size_t done = 0;
+    for (auto &pr : h->timing) {
+        if (!wait && cudaEventQuery(pr.second) != cudaSuccess) break;
+        if (wait) CU(cudaEventSynchronize(pr.second));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        h->stage_ms += ms;
+        h->stage_launches++;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+        ++done;
+    }
+    h->timing.erase(h->timing.begin(), h->timing.begin() + done);
+    return LFB_OK;
+}
+
+extern "C" int lfb_step(lfb_handle *h, double dt)
+{
+    if (!h) return fail(LFB_ERR_ARG, "null handle");
+    if (!(dt > 0)) return fail(LFB_ERR_ARG, "dt must be positive");
+    CU(cudaSetDevice(h->device));
+    // Oceananigans RungeKutta3 (Le & Moin 1991) coefficients and stage times
+    const double g1 = 8.0 / 15, g2 = 5.0 / 12, g3 = 3.0 / 4, z2 = -17.0 / 60, z3 = -5.0 / 12;
+    const double t0 = h->time, t1 = t0 + dt;
+    const double tau1 = t0 + g1 * dt;
+    const double tau2 = tau1 + (g2 + z2) * dt;
+    const double taus[3] = {t0, tau1, tau2};
+    const double gam[3] = {g1, g2, g3}, zet[3] = {0.0, z2, z3};
+    if (h->timing.size() > 64) drain_timings(h, false);
+    for (int s = 0; s < 3; ++s) {
+        int rc = refresh_halos(h, h->U[h->cur], h->n_tracers);
+        if (rc) return rc;
+        rc = launch_stage(h, taus[s], dt, gam[s], zet[s], s == 0, s < 2, 1);
+        if (rc) return rc;
+        h->cur ^= 1;
+    }
+    h->time = t1;
+    h->iteration += 1;
+    return LFB_OK;
+}
+
+extern "C" int lfb_run_until(lfb_handle *h, double t_stop, double dt, int n_align, const double *align_intervals)
+{
+    if (!h) return fail(LFB_ERR_ARG, "null handle");
+    if (!(dt > 0)) return fail(LFB_ERR_ARG, "dt must be positive");
+    if (n_align < 0 || (n_align > 0 && !align_intervals)) return fail(LFB_ERR_ARG, "bad align intervals");
+    while (h->time < t_stop) {
+        const double t = h->time;
+        double step = dt, target = t + dt;
+        bool snapped = false;
+        auto consider = [&](double when) {
+            const double cand = when - t;
+            if (cand < step) { step = cand; target = when; snapped = true; }
+        };
+        for (int q = 0; q < n_align; ++q) {
+            const double iv = align_intervals[q];
+            if (!(iv > 0)) return fail(LFB_ERR_ARG, "align interval must be positive");
+            consider((floor(t / iv) + 1) * iv);
+        }
+        consider(t_stop);
+        if (!(step > 0)) return fail(LFB_ERR_STATE, "time step alignment produced dt = %g at t = %.17g", step, t);
+        int rc = lfb_step(h, step);
+        if (rc) return rc;
+        // land exactly on the aligned time when t + (when - t) rounds one ulp off
+        if (snapped && fabs(h->time - target) <= 4 * fabs(target) * 2.220446049250313e-16) h->time = target;
+    }
+    return LFB_OK;
+}
+
+extern "C" int lfb_get_tendency(lfb_handle *h, int tracer, double *parent)
+{
+    if (!h || !parent) return fail(LFB_ERR_ARG, "null argument");
+    if (tracer < 0 || tracer >= h->n_tracers) return fail(LFB_ERR_ARG, "tracer %d out of range", tracer);
+    CU(cudaSetDevice(h->device));
+    int rc = refresh_halos(h, h->U[h->cur], h->n_tracers);
+    if (rc) return rc;
+    rc = launch_stage(h, h->time, 0.0, 0.0, 0.0, 1, 1, 0);
+    if (rc) return rc;
+    return download(h, h->G + (int64_t)tracer * h->L.len, parent, 0, -1);
+}
+
+// ---- outputs -------------------------------------------------------------------------------------
+static int output_impl(lfb_handle *h, int kind, int field, void *parent, int is_f32)
+{
+    if (!h || !parent) return fail(LFB_ERR_ARG, "null argument");
+    CU(cudaSetDevice(h->device));
+    int fld;
+    if (kind == LFB_OUT_FILTERED_VAR) {
+        if (field < 0 || field >= h->desc.n_vars) return fail(LFB_ERR_ARG, "variable %d out of range", field);
+        fld = field;
+    } else if (kind == LFB_OUT_XI || kind == LFB_OUT_MEAN_VEL) {
+        if (field < 0 || field >= h->n_maps) return fail(LFB_ERR_ARG, "map %d out of range", field);
+        fld = h->desc.n_vars + field;
+    } else return fail(LFB_ERR_ARG, "unknown output kind %d", kind);
+    LfbOutputParams P;
+    memset(&P, 0, sizeof(P));
+    P.L = h->L;
+    P.U = h->U[h->cur];
+    P.n_terms = h->n_pairs;
+    P.single_exp = h->single_exp;
+    for (int p = 0; p < h->n_pairs; ++p) {
+        const double a = h->desc.a[p], b = h->desc.b[p], c = h->desc.c[p], d = h->desc.d[p];
+        P.tracer_c[p] = (fld * h->n_pairs + p) * h->sub;
+        if (kind == LFB_OUT_MEAN_VEL) {
+            if (h->single_exp) { P.wc[p] = -a * c; P.ws[p] = 0; }
+            else { P.wc[p] = -a * c + b * d; P.ws[p] = -a * d - b * c; }
+        } else { P.wc[p] = a; P.ws[p] = h->single_exp ? 0 : b; }
+    }
+    CU(cudaMemsetAsync(h->scratch, 0, (size_t)h->L.len * sizeof(double), h->compute));
+    CU(lfb_launch_output(h->scratch, &P, h->compute));
+    h->launches++;
+    int rc = fill_all_halos(h, h->scratch, 1);
+    if (rc) return rc;
+    rc = exchange_y(h, h->scratch, 1);
+    if (rc) return rc;
+    return download(h, h->scratch, parent, is_f32, -1);
+}
+
+extern "C" int lfb_output(lfb_handle *h, int kind, int field, double *parent) { return output_impl(h, kind, field, parent, 0); }
+extern "C" int lfb_output_f32(lfb_handle *h, int kind, int field, float *parent) { return output_impl(h, kind, field, parent, 1); }
+
+extern "C" int lfb_combine(lfb_handle *h, int64_t n, const double *fwd, const double *bwd_lo, const double *bwd_hi,
+                           double w_hi, double sign, double *out)
+{
+    if (!h || !fwd || !bwd_lo || !out || n <= 0) return fail(LFB_ERR_ARG, "bad argument");
+    if (w_hi != 0.0 && !bwd_hi) return fail(LFB_ERR_ARG, "bwd_hi required when w_hi != 0");
+    CU(cudaSetDevice(h->device));
+    // chunk through the scratch/staging buffers: [fwd | lo | hi] thirds of staging, result in scratch
+    const int64_t cap = (int64_t)(h->staging_bytes / sizeof(double)) / 3;
+    if (cap <= 0) return fail(LFB_ERR_STATE, "staging buffer too small");
+    CU(cudaStreamSynchronize(h->copy));
+    double *d_f = (double *)h->staging, *d_lo = d_f + cap, *d_hi = d_lo + cap;
+    for (int64_t off = 0; off < n; off += cap) {
+        const int64_t m = n - off < cap ? n - off : cap;
+        CU(cudaMemcpyAsync(d_f, fwd + off, m * sizeof(double), cudaMemcpyHostToDevice, h->compute));
+        CU(cudaMemcpyAsync(d_lo, bwd_lo + off, m * sizeof(double), cudaMemcpyHostToDevice, h->compute));
+        if (w_hi != 0.0) CU(cudaMemcpyAsync(d_hi, bwd_hi + off, m * sizeof(double), cudaMemcpyHostToDevice, h->compute));
+        CU(lfb_launch_combine(h->scratch, d_f, d_lo, d_hi, w_hi, sign, m, h->compute));
+        h->launches++;
+        CU(cudaMemcpyAsync(out + off, h->scratch, m * sizeof(double), cudaMemcpyDeviceToHost, h->compute));
+        CU(cudaStreamSynchronize(h->compute));
+    }
+    // scratch doubles as the zero-initialised work field of outputs: nothing to restore, it is
+    // memset before every use
+    return LFB_OK;
+}
+
+// ---- multi-GPU -----------------------------------------------------------------------------------
+extern "C" int lfb_comm_unique_id(void *id128)
+{
+    if (!id128) return fail(LFB_ERR_ARG, "null argument");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+    ncclUniqueId id;
+    NC(ncclGetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return LFB_OK;
+}
+
+extern "C" int lfb_comm_init(lfb_handle *h, const void *id128, int rank, int nranks)
+{
+    if (!h || !id128) return fail(LFB_ERR_ARG, "null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(LFB_ERR_ARG, "bad rank %d / %d", rank, nranks);
+    if (h->comm) return fail(LFB_ERR_STATE, "communicator already initialised");
+    if (h->L.topo[1] == LFB_FLAT) return fail(LFB_ERR_ARG, "y-slab decomposition needs a non-Flat y axis");
+    if (nranks > 1 && h->L.N[1] < h->L.H[1]) return fail(LFB_ERR_ARG, "slab thinner than the halo");
+    CU(cudaSetDevice(h->device));
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    NC(ncclCommInitRank(&h->comm, nranks, id, rank));
+    h->rank = rank; h->nranks = nranks;
+    // global indexing of this slab: equal slabs, rank-major (the host guarantees Ny_global = R * Ny_local)
+    h->L.NG[1] = h->L.N[1] * nranks;
+    h->L.goff[1] = h->L.N[1] * rank;
+    h->L.connected_lo[1] = rank > 0 || h->L.topo[1] == LFB_PERIODIC;
+    h->L.connected_hi[1] = rank < nranks - 1 || h->L.topo[1] == LFB_PERIODIC;
+    const size_t per_field = (size_t)(h->L.N[0] + 2 * h->L.H[0]) * h->L.H[1] * (h->L.N[2] + 2 * h->L.H[2]);
+    h->halo_elems = per_field * (h->n_tracers > 0 ? h->n_tracers : 1);
+    CU(cudaMalloc(&h->send_lo, h->halo_elems * sizeof(double)));
+    CU(cudaMalloc(&h->send_hi, h->halo_elems * sizeof(double)));
+    CU(cudaMalloc(&h->recv_lo, h->halo_elems * sizeof(double)));
+    CU(cudaMalloc(&h->recv_hi, h->halo_elems * sizeof(double)));
+    return LFB_OK;
+}
+
+// ---- introspection -------------------------------------------------------------------------------
+extern "C" int64_t lfb_kernel_launches(const lfb_handle *h) { return h ? h->launches : -1; }
+
+extern "C" int lfb_stage_time_ms(lfb_handle *h, int reset, double *ms, int64_t *launches)
+{
+    if (!h) return fail(LFB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    int rc = drain_timings(h, true);
+    if (rc) return rc;
+    if (ms) *ms = h->stage_ms;
+    if (launches) *launches = h->stage_launches;
+    if (reset) { h->stage_ms = 0; h->stage_launches = 0; }
+    return LFB_OK;
+}
+
+extern "C" int lfb_timer_start(lfb_handle *h)
+{
+    if (!h) return fail(LFB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev_t0, h->compute));
+    return LFB_OK;
+}
+
+extern "C" int lfb_timer_stop(lfb_handle *h, double *ms)
+{
+    if (!h || !ms) return fail(LFB_ERR_ARG, "null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->ev_t1, h->compute));
+    CU(cudaEventSynchronize(h->ev_t1));
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, h->ev_t0, h->ev_t1));
+    *ms = f;
+    return LFB_OK;
+}
+
+extern "C" const char *lfb_kernel_name(const lfb_handle *h)
+{
+    if (!h) return "";
+    if (h->use_zmarch) return "zmarch";
+    return h->desc.strict ? "generic-strict" : "generic";
+}
+
+extern "C" void *lfb_device_ptr(lfb_handle *h, int what, int idx)
+{
+    if (!h) return nullptr;
+    if (what == 0 && idx >= 0 && idx < h->n_tracers) return h->U[h->cur] + (int64_t)idx * h->L.len;
+    if (what == 1 && idx >= 0 && idx < h->n_tracers) return h->G + (int64_t)idx * h->L.len;
+    if (what == 2) {
+        const int slot = idx / 16, f = idx % 16;
+        if (slot >= 0 && slot < h->desc.n_slots && f < N_FIELD_IDS) return h->slot_field[(size_t)slot * N_FIELD_IDS + f];
+    }
+    return nullptr;
+}
+
+extern "C" int lfb_layout(const lfb_handle *h, int64_t *x_offset, int64_t *pitch, int64_t *rows, int64_t *planes)
+{
+    if (!h) return fail(LFB_ERR_ARG, "null handle");
+    if (x_offset) *x_offset = h->L.xoff;
+    if (pitch) *pitch = h->L.pitch;
+    if (rows) *rows = h->L.rows;
+    if (planes) *planes = h->L.planes;
+    return LFB_OK;
+}

@@ -1,0 +1,87 @@
+// lfb_internal.h -- shared host/device definitions of liblfb200 (not part of the public ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lfb200.h"
+
+#define LFB_MAX_ITEMS 64   // (variables + maps) x coefficient sets handled by one stage launch
+#define LFB_XPAD 16        // doubles in front of interior column 0: 128-byte aligned interior rows
+
+// Device memory layout shared by every field of a handle (centre- and face-located alike):
+// element (i,j,k), 0-based interior indices that may run into halos, lives at
+//     xoff + i + pitch * ((Hy + j) + rows * (Hz + k))
+// pitch is a multiple of 16 doubles and xoff = 16 (0 on a Flat x axis), so interior rows start on
+// 128-byte boundaries and a warp reading 32 consecutive cells touches exactly two cache lines.
+// rows/planes carry one spare entry for Face fields on Bounded axes (w: Nz+1 levels).
+struct LfbLayout {
+    int     N[3];        // local interior cells
+    int     H[3];        // halo widths
+    int     topo[3];     // global topology
+    int     xoff;        // column of interior i = 0
+    int     pitch;       // row pitch in elements
+    int     rows;        // Ny + 2Hy + 1
+    int     planes;      // Nz + 2Hz + 1
+    int64_t plane;       // pitch * rows
+    int64_t len;         // pitch * rows * planes
+    int64_t stride[3];   // 1, pitch, plane
+    // distributed y-slabs
+    int     NG[3];       // global interior cells
+    int     goff[3];     // global index of local cell 0
+    int     connected_lo[3], connected_hi[3];   // halo on that side is owned by a neighbour rank
+
+    __host__ __device__ inline int64_t at(int i, int j, int k) const {
+        return (int64_t)(xoff + i) + (int64_t)pitch * ((int64_t)(H[1] + j) + (int64_t)rows * (int64_t)(H[2] + k));
+    }
+};
+
+// one (field, coefficient set) work item: a cosine tracer and (unless single exponential) its sine partner
+struct LfbItem {
+    int    is_map;      // 0: filtered variable forced by the original data; 1: xi map forced by a velocity
+    int    src;         // variable index, or velocity axis for maps
+    int    tracer_c;    // tracer slot of the _C tracer; the _S tracer is tracer_c + 1
+    int    pad;
+    double c, d;        // filter coefficients of this set (d = 0 for the single exponential)
+};
+
+struct LfbStageParams {
+    LfbLayout L;
+    // tracer storage: U[buf][tracer], G[tracer]: contiguous blocks of L.len doubles
+    const double *U_old;
+    double       *U_new;
+    double       *G;          // read as G^- (if use_prev) and overwritten with G^n (if store_G)
+    int     n_items;
+    int     single_exp;
+    int     advect;
+    int     relax;
+    LfbItem items[LFB_MAX_ITEMS];
+    // inputs: two bracketing snapshots per field and their weights psi = s2*w2 + s1*w1
+    const double *vel1[3], *vel2[3];
+    const double *var1[LFB_MAX_VARS], *var2[LFB_MAX_VARS];
+    const double *mask;
+    int     vel_present[3];
+    int     interp;           // 0: w2 == 0, use snapshot 1 as is
+    double  w1, w2;           // (1 - n~), n~
+    double  vel_sign;         // -1 on the backward pass
+    // geometry
+    double  area[3], volume;
+    double  relax_timescale;
+    // RK3 substep: U_new = U_old + dt * (gamma * G + zeta * G^-)
+    double  dt, gamma, zeta;
+    int     first_stage;      // zeta = nothing: U += (dt * gamma) * G
+    int     store_G;          // write G^n for the next stage
+    int     update;           // 0: tendencies only (lfb_get_tendency)
+    // sub-range of the local grid this launch covers (boundary strips / interior when overlapping
+    // the halo exchange): cells j in [j0, j1)
+    int     j0, j1;
+};
+
+// Output combinations (create_output_fields, utils:898-1012): out = sum_i wc[i] U[tc[i]] + ws[i] U[tc[i]+1]
+struct LfbOutputParams {
+    LfbLayout L;
+    const double *U;
+    int    n_terms, single_exp;
+    int    tracer_c[LFB_MAX_COEFFS];
+    double wc[LFB_MAX_COEFFS], ws[LFB_MAX_COEFFS];
+};

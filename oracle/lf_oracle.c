@@ -479,7 +479,7 @@ static void rk3_substep(lfo_state *S, double dt, double gamma, double zeta, int 
         #pragma omp parallel for collapse(2) schedule(static)
         for (int k = 0; k < P->N[2]; ++k) for (int j = 0; j < P->N[1]; ++j) for (int i = 0; i < P->N[0]; ++i) {
             long q = fidx(U, P, i, j, k);
-            if (first) U->p[q] += dt * (gamma * G->p[q]);
+            if (first) U->p[q] += dt * gamma * G->p[q];      /* Oceananigans: convert(FT, dt) * gamma1 * G1 */
             else       U->p[q] += dt * (gamma * G->p[q] + zeta * Gm->p[q]);
         }
     }
