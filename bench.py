@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the filter-PDE hot path (BASELINE.json metric: filter cell-updates/s, tracer x cell / s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size NX NY NZ]
+
+One "step" = one full RK3 time step (3 fused stage launches) of every filter tracer on the synthetic
+3-D 1024x1024x128 FP64 grid (Periodic, Periodic, Bounded), N=2 Butterworth, filtered variables (T, b),
+velocities (u, v, w) => 10 tracers (BASELINE.json configs[4]).  With N > 1
+(torchrun, one rank per GPU) the same grid is split into N y-slabs with an NCCL halo exchange per
+stage: strong scaling, `value` = whole-job cell-updates / max-over-ranks device time.
+
+  value      stepping only, inputs resident in HBM, CUDA events on the library's compute stream
+  e2e        the same metric through the host API with HOST buffers: snapshot uploads from pinned host
+             memory (Float32, as on disk), steps, and the Float32 output download every output time
+  roofline   dominant kernel (the fused stage kernel): algorithmic bytes / mean launch duration vs the
+             measured HBM peak in MEASURED_PEAKS.json
+  cpu_baseline / --impl reference: the CPU restatement of the reference numerics (oracle/) on a bounded
+             sample of the same workload, all host threads (Julia + Oceananigans are not installed, so
+             the reference itself cannot run; kind = "port")
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "filter cell-updates/s"
+UNIT = "tracer*cell/s"
+VAR_NAMES, VEL_NAMES = ("T", "b"), ("u", "v", "w")
+N_TRACERS, N_INPUTS = 10, 5
+T_S = 1.0                      # snapshot spacing
+DT = T_S / 8                   # filter time step
+N_SNAP = 5
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="lfb200")
+    ap.add_argument("--size", type=int, nargs=3, default=[1024, 1024, 128])
+    ap.add_argument("--kernel", default="auto")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-size", type=int, nargs=3, default=[128, 128, 64])
+    return ap.parse_args()
+
+
+def make_grid(size):
+    import lfb200
+    return lfb200.RectilinearGrid(size=tuple(size), extent=tuple(float(s) for s in size),
+                                  topology=("Periodic", "Periodic", "Bounded"))
+
+
+def filter_params():
+    import lfb200
+    return lfb200.set_offline_BW2_filter_params(N=2, freq_c=2 * np.pi / (4 * T_S))
+
+
+def algorithmic_bytes_per_cell_step():
+    """8 (10 n_T + 6 n_in) bytes per cell per RK3 step."""
+    return 8 * (10 * N_TRACERS + 6 * N_INPUTS)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_rate(size, steps, warmup):
+    """cell-updates/s of the CPU restatement (oracle/lf_oracle.c, OpenMP over all host threads) on a
+    `size` sample of the workload with the same filter, tracers and synthetic fields."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lf_oracle as lo
+    from lfb200.synthetic import make_series
+    g = make_grid(size)
+    times = [0.0, T_S, 2 * T_S]
+    fields = make_series(g, times, var_names=VAR_NAMES, velocity_names=VEL_NAMES, T_period=4 * T_S)
+    fp = filter_params()
+    o = lo.Oracle(g.N, g.H, g.topology, g.spacing, len(VAR_NAMES), "".join(VEL_NAMES), fp, True, True)
+    o.load_series(times, {k: [a.astype(np.float64) for a in fields[k]] for k in VEL_NAMES},
+                  [[a.astype(np.float64) for a in fields[v]] for v in VAR_NAMES], 0.0, 2 * T_S, backward=False)
+    o.init_from_data()
+    for _ in range(warmup):
+        o.step(DT)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.step(DT)
+    dt = time.perf_counter() - t0
+    o.close()
+    cells = size[0] * size[1] * size[2]
+    return cells * N_TRACERS * steps / dt, dt / steps * 1e3
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    size = args.cpu_size
+    rate, ms = cpu_port_rate(size, args.steps, args.warmup)
+    sample = (f"{size[0]}x{size[1]}x{size[2]} sub-grid of the workload, {args.steps} RK3 steps after {args.warmup} warm-up, "
+              f"OpenMP over {cores} host threads; CPU restatement of the reference numerics (Julia/Oceananigans absent)")
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    nx, ny, nz = args.size
+    return {"workload": f"synthetic 3D {nx}x{ny}x{nz} FP64 (Periodic,Periodic,Bounded), N=2 Butterworth offline filter, "
+                        f"vars (T,b) + maps (u,v,w) = {N_TRACERS} tracers, WENO5-Z + RK3, dt = T_s/8",
+            "grid": [nx, ny, nz], "tracers": N_TRACERS, "inputs": N_INPUTS, "snapshots": N_SNAP,
+            "decomposition": f"{world} y-slab(s)", "l2": "inputs (>= 25 GB of fields per GPU at full size) exceed the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    import lfb200
+    from lfb200.model import LagrangianFilter
+    from lfb200.synthetic import make_snapshot
+    from lfb200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: lfb200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    gglobal = make_grid(args.size)
+    g = gglobal.slab(rank, world)
+    fp = filter_params()
+    n_slots = N_SNAP
+    m = LagrangianFilter(g, var_names_to_filter=VAR_NAMES, velocity_names=VEL_NAMES, filter_params=fp, n_slots=n_slots,
+                         device=local, kernel=args.kernel)
+    if world > 1:
+        uid = [LagrangianFilter.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        m.comm_init(uid[0], rank, world)
+
+    # ---- synthetic series generated on the GPU, kept on the host as pinned Float32 (the on-disk precision)
+    times = [n * T_S for n in range(N_SNAP)]
+    names = list(VEL_NAMES) + list(VAR_NAMES)
+    host = {}
+    for s, t in enumerate(times):
+        snap = make_snapshot(g, t, 4 * T_S, var_names=VAR_NAMES, velocity_names=VEL_NAMES, xp=torch,
+                             device=torch.device("cuda", local), dtype=np.float32)
+        for name in names:
+            pinned = torch.empty(snap[name].shape, dtype=torch.float32, pin_memory=True)
+            pinned.copy_(snap[name])
+            host[(name, s)] = pinned.numpy().T          # Fortran (ex, ey, ez) view of the pinned buffer
+        del snap
+    torch.cuda.synchronize()
+
+    def upload(slot, s):
+        nbytes = 0
+        for name in names:
+            m.upload_snapshot(slot, name, host[(name, s)], times[s])
+            nbytes += host[(name, s)].nbytes
+        return nbytes
+
+    for s in range(N_SNAP):
+        upload(s, s)
+    m.init_from_data()
+    m.sync()
+
+    def barrier():
+        m.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        m.sync()
+
+    cells_global = args.size[0] * args.size[1] * args.size[2]
+    cells_local = g.Nx * g.Ny * g.Nz
+    K, W = args.steps, args.warmup
+    max_steps = int((times[-1] - 0.0) / DT)
+    if K + W > max_steps:
+        raise SystemExit(f"--steps + --warmup must be <= {max_steps} (the synthetic series covers {times[-1]} T_s)")
+
+    # ---- value: stepping only, inputs resident ------------------------------------------------------
+    for _ in range(W):
+        m.step(DT)
+    barrier()
+    m.stage_time_ms(reset=True)
+    launches0 = m.kernel_launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    m.timer_start()
+    for _ in range(K):
+        m.step(DT)
+    ms = m.timer_stop()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = m.kernel_launches - launches0
+    stage_ms, stage_n = m.stage_time_ms(reset=True)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = cells_global * N_TRACERS * K / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers, uploads and output downloads inside the timed region --------------------
+    e2e = None
+    if not args.no_e2e:
+        m.reset_clock()
+        m.init_from_data()
+        for s in range(n_slots):
+            m.invalidate_slot(s)
+        barrier()
+        out_bufs = {}
+        t0 = time.perf_counter()
+        h2d = d2h = 0
+        h2d += upload(0, 0)
+        h2d += upload(1, 1)
+        next_snap = 2
+        steps_per_snap = int(round(T_S / DT))
+        for n in range(K):
+            t_next = (n + 1) * DT
+            if next_snap < N_SNAP and t_next > times[next_snap - 1] and next_snap - 1 <= int(t_next / T_S):
+                h2d += upload(next_snap % n_slots, next_snap)
+                next_snap += 1
+            m.step(DT)
+            if (n + 1) % steps_per_snap == 0 or n == K - 1:          # output time (T_out = T_s) / end of run
+                for q in range(len(VAR_NAMES)):
+                    d2h += m.output(_lib.OUT_FILTERED_VAR, q, np.float32).nbytes
+                for mi in range(len(VEL_NAMES)):
+                    d2h += m.output(_lib.OUT_XI, mi, np.float32).nbytes
+                    d2h += m.output(_lib.OUT_MEAN_VEL, mi, np.float32).nbytes
+        barrier()
+        wall = time.perf_counter() - t0
+        t_w = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_w, op=dist.ReduceOp.MAX)
+        e2e = {"value": cells_global * N_TRACERS * K / float(t_w.item()), "unit": UNIT,
+               "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+               "note": "Float32 snapshot uploads from pinned host memory + Float32 output downloads every T_out, "
+                       "wall clock between device syncs, max over ranks"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        which = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        stage_avg_ms = stage_ms / max(stage_n, 1)
+        bytes_per_launch = cells_local * algorithmic_bytes_per_cell_step() / 3.0
+        achieved = bytes_per_launch / (stage_avg_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": m.kernel_name, "launch_ms": stage_avg_ms, "peak_source": which,
+                    "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "note": "FP64 WENO5-Z is FP64-pipe bound before it is HBM bound; see DESIGN.md"}
+        cpu = None
+        if not args.no_cpu and world == 1:
+            rate, cms = cpu_port_rate(args.cpu_size, 2, 1)
+            cs = args.cpu_size
+            cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"{cs[0]}x{cs[1]}x{cs[2]} sub-grid of the workload, 2 RK3 steps after 1 warm-up, OpenMP over "
+                             f"{os.cpu_count()} host threads ({cms:.0f} ms/step)"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
