@@ -147,6 +147,24 @@ static void build_layout(lfb_handle *h)
     L.stride[0] = 1; L.stride[1] = L.pitch; L.stride[2] = L.plane;
 }
 
+// stage kernel selection: the z-marching kernel when the grid / options allow it, else the generic one
+static int select_kernel(lfb_handle *h)
+{
+    LfbStageParams P;
+    memset(&P, 0, sizeof(P));
+    P.L = h->L;
+    P.advect = h->desc.advection != LFB_ADVECTION_NONE;
+    P.relax = h->desc.relaxation;
+    for (int ax = 0; ax < 3; ++ax) P.vel_present[ax] = (h->desc.velocity_mask >> ax) & 1;
+    P.j0 = 0; P.j1 = h->L.N[1];
+    const int ok = lfb_zmarch_supported(&P) && !h->desc.strict;
+    if (h->desc.kernel == LFB_KERNEL_ZMARCH && !ok)
+        return fail(LFB_ERR_ARG, "the z-marching kernel needs a (Periodic|slab, Periodic|slab, Bounded) grid with Nx %% 32 == 0, "
+                                 "Ny %% 8 == 0, Nz >= 8, u,v,w all present, WENO advection, no relaxation and strict = 0");
+    h->use_zmarch = (h->desc.kernel != LFB_KERNEL_GENERIC) && ok;
+    return LFB_OK;
+}
+
 extern "C" int lfb_create(const lfb_desc *desc, lfb_handle **out)
 {
     if (!desc || !out) return fail(LFB_ERR_ARG, "null argument");
@@ -250,6 +268,8 @@ extern "C" int lfb_create(const lfb_desc *desc, lfb_handle **out)
     h->launches = 0; h->stage_ms = 0; h->stage_launches = 0;
     h->use_zmarch = 0;
     CU(cudaDeviceSynchronize());
+    int rc = select_kernel(h);
+    if (rc) { lfb_destroy(h); return rc; }
     *out = h;
     return LFB_OK;
 }
@@ -809,7 +829,7 @@ extern "C" int lfb_comm_init(lfb_handle *h, const void *id128, int rank, int nra
     CU(cudaMalloc(&h->send_hi, h->halo_elems * sizeof(double)));
     CU(cudaMalloc(&h->recv_lo, h->halo_elems * sizeof(double)));
     CU(cudaMalloc(&h->recv_hi, h->halo_elems * sizeof(double)));
-    return LFB_OK;
+    return select_kernel(h);
 }
 
 // ---- introspection -------------------------------------------------------------------------------
