@@ -21,6 +21,7 @@ extern "C" {
 cudaError_t lfb_launch_stage_generic(const LfbStageParams *P, int strict, cudaStream_t stream);
 cudaError_t lfb_launch_stage_zmarch(const LfbStageParams *P, cudaStream_t stream);
 int         lfb_zmarch_supported(const LfbStageParams *P);
+cudaError_t lfb_launch_interp_inputs(const LfbInterpParams *P, cudaStream_t stream);
 cudaError_t lfb_launch_fill_halo_axis(double *base, int64_t field_stride, int n_fields, const LfbLayout *L,
                                       int ax, int mode, cudaStream_t stream);
 cudaError_t lfb_launch_import(double *dst, const void *src, int is_f32, const LfbLayout *L, int ex, int ey, int ez,
@@ -78,6 +79,7 @@ struct lfb_handle {
     double    *G;
     double    *scratch;                    // one field
     double    *mask;
+    double    *cur_in[N_FIELD_IDS];           // inputs at the current stage time (update_input_data!)
     void      *staging;                    // dense parent array, device side
     size_t     staging_bytes;
     std::vector<double *> slot_field;      // [slot * N_FIELD_IDS + field_id]
@@ -241,6 +243,10 @@ extern "C" int lfb_create(const lfb_desc *desc, lfb_handle **out)
     CU(cudaMemset(h->G, 0, fbytes * nt));
     CU(cudaMemset(h->scratch, 0, fbytes));
     if (desc->relaxation) { CU(cudaMalloc(&h->mask, fbytes)); CU(cudaMemset(h->mask, 0, fbytes)); }
+    for (int f = 0; f < N_FIELD_IDS; ++f) {
+        h->cur_in[f] = nullptr;
+        if (field_present(h, f)) { CU(cudaMalloc(&h->cur_in[f], fbytes)); CU(cudaMemset(h->cur_in[f], 0, fbytes)); }
+    }
     h->staging_bytes = fbytes;     // dense parent arrays are never larger than the padded layout
     CU(cudaMalloc(&h->staging, h->staging_bytes));
     const int ns = desc->n_slots;
@@ -286,6 +292,7 @@ extern "C" int lfb_destroy(lfb_handle *h)
     for (auto &pr : h->timing) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaFree(h->U[0]); cudaFree(h->U[1]); cudaFree(h->G); cudaFree(h->scratch);
     if (h->mask) cudaFree(h->mask);
+    for (int f = 0; f < N_FIELD_IDS; ++f) if (h->cur_in[f]) cudaFree(h->cur_in[f]);
     cudaFree(h->staging);
     if (h->send_lo) { cudaFree(h->send_lo); cudaFree(h->send_hi); cudaFree(h->recv_lo); cudaFree(h->recv_hi); }
     cudaStreamDestroy(h->compute); cudaStreamDestroy(h->copy);
@@ -612,19 +619,29 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
     if (rc) return rc;
     for (int s : {s1, s2})
         if (h->slot_pending[s]) { CU(cudaStreamWaitEvent(h->compute, h->slot_ready[s], 0)); h->slot_pending[s] = 0; }
-    for (int ax = 0; ax < 3; ++ax) {
-        P.vel_present[ax] = (h->desc.velocity_mask >> ax) & 1;
-        P.vel1[ax] = h->slot_field[(size_t)s1 * N_FIELD_IDS + ax];
-        P.vel2[ax] = h->slot_field[(size_t)s2 * N_FIELD_IDS + ax];
-        P.area[ax] = 1.0;
+    // update_input_data!: inputs at the stage time (aliased to the slot when no arithmetic is needed)
+    {
+        LfbInterpParams I;
+        memset(&I, 0, sizeof(I));
+        I.len = h->L.len; I.interp = interp; I.w1 = w1; I.w2 = w2;
+        const bool backward = h->direction < 0;
+        for (int f = 0; f < N_FIELD_IDS; ++f) {
+            if (!field_present(h, f)) continue;
+            const double *a = h->slot_field[(size_t)s1 * N_FIELD_IDS + f];
+            const double *b = h->slot_field[(size_t)s2 * N_FIELD_IDS + f];
+            const bool neg = backward && f < 3;
+            const double *use = a;
+            if (interp || neg) {
+                const int q = I.n_fields++;
+                I.s1[q] = a; I.s2[q] = b; I.dst[q] = h->cur_in[f]; I.negate[q] = neg;
+                use = h->cur_in[f];
+            }
+            if (f < 3) P.vel[f] = use; else P.var[f - 3] = use;
+        }
+        if (I.n_fields) { CU(lfb_launch_interp_inputs(&I, h->compute)); h->launches++; }
     }
-    for (int q = 0; q < h->desc.n_vars; ++q) {
-        P.var1[q] = h->slot_field[(size_t)s1 * N_FIELD_IDS + 3 + q];
-        P.var2[q] = h->slot_field[(size_t)s2 * N_FIELD_IDS + 3 + q];
-    }
+    for (int ax = 0; ax < 3; ++ax) P.vel_present[ax] = (h->desc.velocity_mask >> ax) & 1;
     P.mask = h->mask;
-    P.interp = interp; P.w1 = w1; P.w2 = w2;
-    P.vel_sign = h->direction < 0 ? -1.0 : 1.0;
     const double dx = h->desc.spacing[0], dy = h->desc.spacing[1], dz = h->desc.spacing[2];
     P.area[0] = dy * dz; P.area[1] = dx * dz; P.area[2] = dx * dy; P.volume = dx * dy * dz;
     P.relax_timescale = h->desc.relax_timescale;

@@ -19,14 +19,6 @@
 // U is ping-ponged (the stencil reads neighbours of U_old).  Each thread owns one cell, loads the six
 // face velocities once and loops over the (field, coefficient set) items.
 // ------------------------------------------------------------------------------------------------
-template <class T>
-__device__ __forceinline__ T interp_input(const double *__restrict__ s1, const double *__restrict__ s2, int64_t idx,
-                                          int interp, T w1, T w2)
-{
-    if (!interp) return T(s1[idx]);
-    return T(s2[idx]) * w2 + T(s1[idx]) * w1;      // psi2 * n~ + psi1 * (1 - n~)
-}
-
 template <class T, bool STRICT>
 __global__ void __launch_bounds__(128) lfb_stage_generic(const __grid_constant__ LfbStageParams P)
 {
@@ -37,7 +29,6 @@ __global__ void __launch_bounds__(128) lfb_stage_generic(const __grid_constant__
     if (i >= L.N[0] || j >= P.j1) return;
     const int ijk[3] = {i, j, k};
     const int64_t idx = L.at(i, j, k);
-    const T w1(P.w1), w2(P.w2);
 
     // face velocities (low / high face of this cell per axis) and centred velocities for the maps
     T q_lo[3], q_hi[3], q_c[3];
@@ -46,11 +37,9 @@ __global__ void __launch_bounds__(128) lfb_stage_generic(const __grid_constant__
     for (int ax = 0; ax < 3; ++ax) {
         q_lo[ax] = q_hi[ax] = q_c[ax] = T(0.0);
         if (!P.vel_present[ax]) continue;
-        T lo = interp_input<T>(P.vel1[ax], P.vel2[ax], idx, P.interp, w1, w2);
-        if (P.vel_sign < 0) lo = -lo;
+        const T lo(P.vel[ax][idx]);
         if (L.topo[ax] == LFB_FLAT) { q_c[ax] = lo; continue; }
-        T hi = interp_input<T>(P.vel1[ax], P.vel2[ax], idx + L.stride[ax], P.interp, w1, w2);
-        if (P.vel_sign < 0) hi = -hi;
+        const T hi(P.vel[ax][idx + L.stride[ax]]);
         q_lo[ax] = lo; q_hi[ax] = hi;
         q_c[ax] = (lo + hi) / T(2.0);
         if (P.advect) div_u = div_u + (T(P.area[ax]) * hi - T(P.area[ax]) * lo);
@@ -68,7 +57,7 @@ __global__ void __launch_bounds__(128) lfb_stage_generic(const __grid_constant__
         const T gS = P.single_exp ? T(0.0) : T(Us[idx]);
         T src;
         if (item.is_map) src = q_c[item.src];
-        else src = interp_input<T>(P.var1[item.src], P.var2[item.src], idx, P.interp, w1, w2);
+        else src = T(P.var[item.src][idx]);
 
         for (int sub = 0; sub < n_sub; ++sub) {
             const double *U = sub ? Us : Uc;
@@ -127,6 +116,40 @@ extern "C" cudaError_t lfb_launch_stage_generic(const LfbStageParams *P, int str
     dim3 grid((L.N[0] + block.x - 1) / block.x, P->j1 - P->j0, L.N[2]);
     if (strict) lfb_stage_generic<sd, true><<<grid, block, 0, stream>>>(*P);
     else        lfb_stage_generic<double, false><<<grid, block, 0, stream>>>(*P);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// update_input_data! (utils:1036-1058): fields at the stage time from the two bracketing snapshots,
+// psi2 * n~ + psi1 * (1 - n~), individually rounded like the reference's broadcast; velocities are
+// negated on the backward pass (utils:169-173).  One launch for all input fields.
+// ------------------------------------------------------------------------------------------------
+__global__ void lfb_interp_inputs(const __grid_constant__ LfbInterpParams P)
+{
+    const int f = blockIdx.y;
+    const double *__restrict__ s1 = P.s1[f], *__restrict__ s2 = P.s2[f];
+    double *__restrict__ dst = P.dst[f];
+    const bool neg = P.negate[f] != 0;
+    int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 2;
+    for (; q < P.len; q += stride) {           // len is a multiple of 16: two elements per thread, 16-byte accesses
+        const double2 a = *reinterpret_cast<const double2 *>(s1 + q);
+        double2 r = a;
+        if (P.interp) {
+            const double2 b = *reinterpret_cast<const double2 *>(s2 + q);
+            r.x = __dadd_rn(__dmul_rn(b.x, P.w2), __dmul_rn(a.x, P.w1));
+            r.y = __dadd_rn(__dmul_rn(b.y, P.w2), __dmul_rn(a.y, P.w1));
+        }
+        if (neg) { r.x = -r.x; r.y = -r.y; }
+        *reinterpret_cast<double2 *>(dst + q) = r;
+    }
+}
+
+extern "C" cudaError_t lfb_launch_interp_inputs(const LfbInterpParams *P, cudaStream_t stream)
+{
+    if (P->n_fields == 0) return cudaSuccess;
+    dim3 block(256, 1, 1), grid(148 * 8, P->n_fields, 1);
+    lfb_interp_inputs<<<grid, block, 0, stream>>>(*P);
     return cudaGetLastError();
 }
 

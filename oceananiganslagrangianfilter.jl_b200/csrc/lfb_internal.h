@@ -56,14 +56,13 @@ struct LfbStageParams {
     int     advect;
     int     relax;
     LfbItem items[LFB_MAX_ITEMS];
-    // inputs: two bracketing snapshots per field and their weights psi = s2*w2 + s1*w1
-    const double *vel1[3], *vel2[3];
-    const double *var1[LFB_MAX_VARS], *var2[LFB_MAX_VARS];
+    // inputs at the stage time: u, v, w and the original variables, already interpolated in time (and
+    // negated on the backward pass) by lfb_interp_inputs, or aliased to a snapshot slot when the stage
+    // time sits on a snapshot
+    const double *vel[3];
+    const double *var[LFB_MAX_VARS];
     const double *mask;
     int     vel_present[3];
-    int     interp;           // 0: w2 == 0, use snapshot 1 as is
-    double  w1, w2;           // (1 - n~), n~
-    double  vel_sign;         // -1 on the backward pass
     // geometry
     double  area[3], volume;
     double  relax_timescale;
@@ -84,4 +83,15 @@ struct LfbOutputParams {
     int    n_terms, single_exp;
     int    tracer_c[LFB_MAX_COEFFS];
     double wc[LFB_MAX_COEFFS], ws[LFB_MAX_COEFFS];
+};
+
+// update_input_data! (utils:1036-1058): cur = s2 * w2 + s1 * w1 for a batch of fields, optionally negated
+struct LfbInterpParams {
+    int           n_fields;
+    int64_t       len;
+    const double *s1[3 + LFB_MAX_VARS], *s2[3 + LFB_MAX_VARS];
+    double       *dst[3 + LFB_MAX_VARS];
+    int           negate[3 + LFB_MAX_VARS];
+    int           interp;      // 0: copy s1 (only used when a negation is needed)
+    double        w1, w2;
 };
