@@ -46,9 +46,53 @@ __device__ __forceinline__ void cp_async8(unsigned smem_dst, const double *gmem_
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// WENO3-Z increment from dn = e - n, do_ = n - o (buffer scheme next to a wall)
+__device__ __forceinline__ double weno3z_inc(double do_, double dn)
+{
+    const double eps = LFB_WENO_EPS;
+    const double b0 = dn * dn, b1 = do_ * do_;
+    const double tau = fabs(b0 - b1);
+    const double r0 = tau / (b0 + eps), r1 = tau / (b1 + eps);
+    const double a0 = (2.0 / 3.0) * (1.0 + r0 * r0), a1 = (1.0 / 3.0) * (1.0 + r1 * r1);
+    return (a0 * (0.5 * dn) + a1 * (0.5 * do_)) / (a0 + a1);
+}
+
+// shared memory carve-up (doubles).  Everything that is double-buffered along the march lives in one
+// per-buffer block, so a single uniform offset (k & 1) * BUF selects the buffer for all arrays.
+template <int NSUB>
+struct ZmSmem {
+    static constexpr int C_SUB = ZM_CH * ZM_CW;                 // one tracer plane with halo
+    static constexpr int FX_SUB = ZM_TY * (ZM_TX + 1);
+    static constexpr int FY_SUB = (ZM_TY + 1) * ZM_TX;
+    static constexpr int NMAIN = NSUB * ZM_MAIN;
+    static constexpr int OFF_C = 0;                             // C[NSUB][CH][CW]
+    static constexpr int OFF_FX = OFF_C + NSUB * C_SUB;         // Fx[NSUB][TY][TX+1]
+    static constexpr int OFF_FY = OFF_FX + NSUB * FX_SUB;       // Fy[NSUB][TY+1][TX]
+    static constexpr int OFF_QX = OFF_FY + NSUB * FY_SUB;       // Qx[TY][TX+1]   face velocities u
+    static constexpr int OFF_QY = OFF_QX + FX_SUB;              // Qy[TY+1][TX]   face velocities v
+    static constexpr int OFF_IN = OFF_QY + FY_SUB;              // In[5][NMAIN]   per-thread inputs u,v,w,G-,f of the plane
+    static constexpr int BUF = (OFF_IN + 5 * NMAIN + 15) / 16 * 16;
+    static constexpr int BYTES = 2 * BUF * 8;
+};
+
+__device__ __forceinline__ void block_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+// num / den for den > 0 in the normal range: reciprocal seed + two Newton steps + one residual correction
+// (about 1 ulp; no special-case branch, unlike the IEEE division sequence)
+__device__ __forceinline__ double div_pos(double num, double den)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    double e = fma(-den, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-den, r, 1.0);
+    r = fma(r, e, r);
+    const double q = num * r;
+    return fma(fma(-den, q, num), r, q);
+}
+
 // Z weights and candidate increments from the smoothness indicators; returns (face value - n).
-__device__ __forceinline__ double weno5z_from_betas(double b0, double b1, double b2, double dp, double do_, double dn,
-                                                    double de)
+__device__ __forceinline__ double zm_from_betas(double b0, double b1, double b2, double dp, double do_, double dn, double de)
 {
     const double eps = LFB_WENO_EPS;
     const double x0 = fma(2.0 / 3.0, dn, (-1.0 / 6.0) * de);
@@ -63,58 +107,46 @@ __device__ __forceinline__ double weno5z_from_betas(double b0, double b1, double
     const double A2 = (G2 + tt) * (G0 * G1);
     const double den = fma(3.0, A0, fma(6.0, A1, A2));
     const double num = fma(3.0, A0 * x0, fma(6.0, A1 * x1, A2 * x2));
-    return num / den;
+    return div_pos(num, den);
 }
 
-// WENO5-Z increment with the curvature terms Q_s = 13/4 s_s^2 supplied (z direction)
-__device__ __forceinline__ double weno5z_inc_q(double dp, double do_, double dn, double de, double Q2, double Q1, double Q0)
+// WENO5-Z increment from the four first differences of the upwind-ordered stencil
+__device__ __forceinline__ double zm_inc(double dp, double do_, double dn, double de)
+{
+    const double s0 = de - dn, s1 = dn - do_, s2 = do_ - dp;
+    const double t0 = fma(-3.0, dn, de), t1 = dn + do_, t2 = fma(3.0, do_, -dp);
+    const double b0 = fma(3.25 * s0, s0, (0.75 * t0) * t0);
+    const double b1 = fma(3.25 * s1, s1, (0.75 * t1) * t1);
+    const double b2 = fma(3.25 * s2, s2, (0.75 * t2) * t2);
+    return zm_from_betas(b0, b1, b2, dp, do_, dn, de);
+}
+
+// ... with the curvature terms Q_s = 13/4 s_s^2 supplied (z direction, register window)
+__device__ __forceinline__ double zm_inc_q(double dp, double do_, double dn, double de, double Q2, double Q1, double Q0)
 {
     const double t0 = fma(-3.0, dn, de), t1 = dn + do_, t2 = fma(3.0, do_, -dp);
     const double b0 = fma(0.75 * t0, t0, Q0);
     const double b1 = fma(0.75 * t1, t1, Q1);
     const double b2 = fma(0.75 * t2, t2, Q2);
-    return weno5z_from_betas(b0, b1, b2, dp, do_, dn, de);
-}
-
-// WENO3-Z increment from dn = e - n, do_ = n - o (buffer scheme next to a wall)
-__device__ __forceinline__ double weno3z_inc(double do_, double dn)
-{
-    const double eps = LFB_WENO_EPS;
-    const double b0 = dn * dn, b1 = do_ * do_;
-    const double tau = fabs(b0 - b1);
-    const double r0 = tau / (b0 + eps), r1 = tau / (b1 + eps);
-    const double a0 = (2.0 / 3.0) * (1.0 + r0 * r0), a1 = (1.0 / 3.0) * (1.0 + r1 * r1);
-    return (a0 * (0.5 * dn) + a1 * (0.5 * do_)) / (a0 + a1);
+    return zm_from_betas(b0, b1, b2, dp, do_, dn, de);
 }
 
 // Upwind WENO5-Z face value from a line of the shared tile: `a` is the 32-bit address of the cell on the
-// high side of the face (cell m), `s` the byte stride along the axis, cm its value, q the face velocity.
-__device__ __forceinline__ double face_from_tile(unsigned a, int s, double cm, double q)
+// high side of the face (cell m), S the byte stride along the axis, cm its value, q the face velocity.
+// The increment is odd in the differences, so the right-biased value is n - inc(mirrored differences)
+// and no operand has to be negated.
+template <int S>
+__device__ __forceinline__ double zm_face_from_tile(unsigned a, double cm, double q)
 {
     const bool left = q > 0.0;
-    const double m1 = lds(a - s), m2 = lds(a - 2 * s), p1 = lds(a + s);
-    const double far = lds(left ? a - 3 * s : a + 2 * s);
-    const double n = left ? m1 : cm;
-    const double e = left ? cm : m1;
-    const double o = left ? m2 : p1;
-    const double f = left ? p1 : m2;
-    return n + weno5z_increment(o - far, n - o, e - n, f - e);
+    const double m1 = lds(a - S), m2 = lds(a - 2 * S), p1 = lds(a + S);
+    const double far = lds(left ? a - 3 * S : a + 2 * S);
+    // left : p,o,n,e,f = far,m2,m1,cm,p1      right: p,o,n,e,f = far,p1,cm,m1,m2 (mirrored)
+    const double d_lo = m1 - m2, d_mid = cm - m1, d_hi = p1 - cm;            // differences in storage order
+    const double d_far = left ? m2 - far : far - p1;
+    const double inc = zm_inc(d_far, left ? d_lo : d_hi, d_mid, left ? d_hi : d_lo);
+    return left ? m1 + inc : cm - inc;
 }
-
-// shared memory carve-up (doubles); NSUB tracers per block
-template <int NSUB>
-struct ZmSmem {
-    static constexpr int C_SUB = ZM_CH * ZM_CW;                 // one tracer plane with halo
-    static constexpr int C_BUF = NSUB * C_SUB;
-    static constexpr int FX_SUB = ZM_TY * (ZM_TX + 1);
-    static constexpr int FY_SUB = (ZM_TY + 1) * ZM_TX;
-    static constexpr int OFF_C = 0;                             // C[2][NSUB][CH][CW]
-    static constexpr int OFF_FX = OFF_C + 2 * C_BUF;            // Fx[2][NSUB][TY][TX+1]
-    static constexpr int OFF_FY = OFF_FX + 2 * NSUB * FX_SUB;   // Fy[2][NSUB][TY+1][TX]
-    static constexpr int OFF_QX = OFF_FY + 2 * NSUB * FY_SUB;   // Qx[2][TY][TX+1]
-    static constexpr int OFF_QY = OFF_QX + 2 * FX_SUB;          // Qy[2][TY+1][TX]
-    static constexpr int TOTAL = OFF_QY + 2 * FY_SUB;
-};
 
 template <int NSUB>
 __global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_zmarch(const __grid_constant__ LfbStageParams P)
@@ -122,6 +154,7 @@ __global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_z
     using SM = ZmSmem<NSUB>;
     extern __shared__ __align__(16) double zm_smem[];
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(zm_smem);
+    constexpr unsigned BUF_B = 8u * SM::BUF;
     const LfbLayout &L = P.L;
     const int tid = threadIdx.x;
     const int item_id = blockIdx.x % P.n_items;
@@ -132,45 +165,67 @@ __global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_z
     const int Nz = L.N[2];
     const int64_t plane = L.plane;
 
-    // ---- roles ----------------------------------------------------------------------------------
-    const bool is_main = tid < NSUB * ZM_MAIN;
-    int sub, tx, ty;
-    int hkind = 0;                               // helpers: 1 = extra y face (north edge), 2 = extra x face (east edge)
-    if (is_main) {
-        tx = tid % ZM_TX; ty = (tid / ZM_TX) % ZM_TY; sub = tid / ZM_MAIN;
-    } else {
-        const int hl = tid - NSUB * ZM_MAIN;
-        if (hl < NSUB * 32) { hkind = 1; sub = hl / 32; tx = hl % 32; ty = ZM_TY; }
+    if (tid >= SM::NMAIN) {
+        // ================= helper warps: the extra faces on the north / east edge of the tile =================
+        const int hl = tid - SM::NMAIN;
+        int sub, tx, ty, kind;                   // kind 1: y face at row j0+TY, 2: x face at column i0+TX, 0: idle lane
+        if (hl < NSUB * 32) { kind = 1; sub = hl / 32; tx = hl % 32; ty = ZM_TY; }
         else {
             const int xl = hl - NSUB * 32;
-            if (xl < NSUB * ZM_TY) { hkind = 2; sub = xl / ZM_TY; ty = xl % ZM_TY; tx = ZM_TX; }
-            else { hkind = 0; sub = 0; tx = 0; ty = 0; }
+            if (xl < NSUB * ZM_TY) { kind = 2; sub = xl / ZM_TY; ty = xl % ZM_TY; tx = ZM_TX; }
+            else { kind = 0; sub = 0; tx = 0; ty = 0; }
         }
+        const unsigned aC = sbase + 8u * (SM::OFF_C + sub * SM::C_SUB + (ty + 3) * ZM_CW + tx + 3);
+        const unsigned aF = kind == 1 ? sbase + 8u * (SM::OFF_FY + sub * SM::FY_SUB + ty * ZM_TX + tx)
+                                      : sbase + 8u * (SM::OFF_FX + sub * SM::FX_SUB + ty * (ZM_TX + 1) + tx);
+        const unsigned aQ = kind == 1 ? sbase + 8u * (SM::OFF_QY + ty * ZM_TX + tx)
+                                      : sbase + 8u * (SM::OFF_QX + ty * (ZM_TX + 1) + tx);
+        const double *__restrict__ vel = (kind == 1 ? P.vel[1] : P.vel[0]) + L.at(i0 + tx, j0 + ty, 0);
+        const double area = kind == 1 ? P.area[1] : P.area[0];
+        double q = kind ? vel[0] : 0.0;
+        block_barrier();                                            // prologue barrier of the main warps
+        for (int k = 0; k < Nz; ++k) {
+            const unsigned boff = (k & 1) * BUF_B;
+            if (kind) {
+                const double cm = lds(aC + boff);
+                const double cf = kind == 1 ? zm_face_from_tile<8 * ZM_CW>(aC + boff, cm, q)
+                                            : zm_face_from_tile<8>(aC + boff, cm, q);
+                sts(aF + boff, (area * q) * cf);
+                if (sub == 0) sts(aQ + boff, q);
+                vel += plane;
+                if (k + 1 < Nz) q = vel[0];
+            }
+            block_barrier();
+        }
+        return;
     }
-    const bool do_x = is_main || hkind == 2, do_y = is_main || hkind == 1;
-    // per-thread shared addresses (bytes)
+
+    // ================= main warps: one cell column of one tracer per thread =================
+    const int tx = tid % ZM_TX, ty = (tid / ZM_TX) % ZM_TY, sub = tid / ZM_MAIN;
     const unsigned aC = sbase + 8u * (SM::OFF_C + sub * SM::C_SUB + (ty + 3) * ZM_CW + tx + 3);
     const unsigned aFx = sbase + 8u * (SM::OFF_FX + sub * SM::FX_SUB + ty * (ZM_TX + 1) + tx);
     const unsigned aFy = sbase + 8u * (SM::OFF_FY + sub * SM::FY_SUB + ty * ZM_TX + tx);
     const unsigned aQx = sbase + 8u * (SM::OFF_QX + ty * (ZM_TX + 1) + tx);
     const unsigned aQy = sbase + 8u * (SM::OFF_QY + ty * ZM_TX + tx);
-    constexpr unsigned C_BUF_B = 8u * SM::C_BUF, FX_BUF_B = 8u * NSUB * SM::FX_SUB, FY_BUF_B = 8u * NSUB * SM::FY_SUB;
-    constexpr unsigned QX_BUF_B = 8u * SM::FX_SUB, QY_BUF_B = 8u * SM::FY_SUB;
+    const unsigned aIn = sbase + 8u * (SM::OFF_IN + tid);
+    constexpr unsigned IN_F = 8u * SM::NMAIN;                        // stride between the input fields of a thread
     const int partner_off = (NSUB == 2) ? (sub ? -8 * SM::C_SUB : 8 * SM::C_SUB) : 0;
 
-    // element offsets of this thread's column: `off` into layout-shaped arrays, `toff` into the tracer stacks
-    int64_t off = L.at(i0 + tx, j0 + ty, 0);
-    int64_t toff = (int64_t)(item.tracer_c + sub) * L.len + off;
-    const double *__restrict__ Uold = P.U_old;
-    const double *__restrict__ velu = P.vel[0], *__restrict__ velv = P.vel[1], *__restrict__ velw = P.vel[2];
-    const double *__restrict__ varp = item.is_map ? nullptr : P.var[item.src];
-    const bool need_var = is_main && !item.is_map && sub == 0;
+    // global pointers of this thread's column (advanced by one plane per iteration)
+    const int64_t off0 = L.at(i0 + tx, j0 + ty, 0);
+    const int64_t tbase = (int64_t)(item.tracer_c + sub) * L.len;
+    const double *__restrict__ pU = P.U_old + tbase + off0;
+    double *__restrict__ pUn = P.U_new + tbase + off0;
+    double *__restrict__ pG = P.G + tbase + off0;
+    const double *__restrict__ pu = P.vel[0] + off0, *__restrict__ pv = P.vel[1] + off0, *__restrict__ pw = P.vel[2] + off0;
+    const bool need_var = !item.is_map && sub == 0;
+    const double *__restrict__ pf = need_var ? P.var[item.src] + off0 : nullptr;
     const bool use_G = !P.first_stage;
 
-    // halo duties of the tile (main threads only): up to two elements per thread
+    // halo duties of the tile: up to two elements per thread
     unsigned h_s0 = 0, h_s1 = 0;                 // shared byte address in buffer 0 (0 = none)
-    int64_t h_g0 = 0, h_g1 = 0;                  // element offset in the tracer stack, plane 0
-    if (is_main) {
+    const double *h_g0 = nullptr, *h_g1 = nullptr;
+    {
         const int t = tid % ZM_MAIN;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -182,81 +237,71 @@ __global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_z
             else if (e < 6 * ZM_CW + 6 * ZM_TY) { row = 3 + (e - 6 * ZM_CW - 3 * ZM_TY) / 3; cc = ZM_TX + 3 + (e - 6 * ZM_CW - 3 * ZM_TY) % 3; }
             if (row >= 0) {
                 const unsigned sa = sbase + 8u * (SM::OFF_C + sub * SM::C_SUB + row * ZM_CW + cc);
-                const int64_t ga = (int64_t)(item.tracer_c + sub) * L.len + L.at(i0 - 3 + cc, j0 - 3 + row, 0);
+                const double *ga = P.U_old + tbase + L.at(i0 - 3 + cc, j0 - 3 + row, 0);
                 if (r == 0) { h_s0 = sa; h_g0 = ga; } else { h_s1 = sa; h_g1 = ga; }
             }
         }
     }
 
-    // ---- prologue: z window of the column, plane-0 tile, inputs of plane 0 --------------------------
-    double d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0;     // d[k-2..k+2], d[m] = c[m+1] - c[m]
-    double Qa = 0, Qb = 0, Qc = 0, Qd = 0;             // Q[k-1..k+2]
-    double ck = 0, ck1 = 0, ck2 = 0, ck3 = 0, ck4 = 0; // c[k..k+4]
-    double Fb = 0, wb = 0;
-    double cu = 0, cv = 0, cw = 0, cG = 0, cf = 0;     // inputs of the current plane
-    if (is_main) {
-        const double cm2 = Uold[toff - 2 * plane], cm1 = Uold[toff - plane];
-        ck = Uold[toff]; ck1 = Uold[toff + plane]; ck2 = Uold[toff + 2 * plane];
-        ck3 = Uold[toff + 3 * plane]; ck4 = Uold[toff + 4 * plane];
+    // ---- prologue: z window of the column, plane-0 tile and inputs ------------------------------------
+    double d0, d1, d2, d3, d4;                   // d[k-2..k+2], d[m] = c[m+1] - c[m]
+    double Qa, Qb, Qc, Qd;                       // Q[k-1..k+2], Q[m] = 13/4 (d[m] - d[m-1])^2
+    double ck, ck1, ck2, ck3, ck4;               // c[k..k+4]
+    double Fb, wb;
+    {
+        const double cm2 = pU[-2 * plane], cm1 = pU[-plane];
+        ck = pU[0]; ck1 = pU[plane]; ck2 = pU[2 * plane]; ck3 = pU[3 * plane]; ck4 = pU[4 * plane];
         d0 = cm1 - cm2; d1 = ck - cm1; d2 = ck1 - ck; d3 = ck2 - ck1; d4 = ck3 - ck2;
         double s;
         s = d1 - d0; Qa = 3.25 * s * s;
         s = d2 - d1; Qb = 3.25 * s * s;
         s = d3 - d2; Qc = 3.25 * s * s;
         s = d4 - d3; Qd = 3.25 * s * s;
-        wb = velw[off];
+        wb = pw[0];
         Fb = (P.area[2] * wb) * ck;                     // wall face m = 1: Centered2 on the mirrored halo
         sts(aC, ck);
-        if (h_s0) sts(h_s0, Uold[h_g0]);
-        if (h_s1) sts(h_s1, Uold[h_g1]);
-        cw = velw[off + plane];
-        if (use_G) cG = P.G[toff];
-        if (need_var) cf = varp[off];
+        if (h_s0) cp_async8(h_s0, h_g0);
+        if (h_s1) cp_async8(h_s1, h_g1);
+        cp_async8(aIn, pu);
+        cp_async8(aIn + IN_F, pv);
+        cp_async8(aIn + 2 * IN_F, pw + plane);
+        if (use_G) cp_async8(aIn + 3 * IN_F, pG);
+        if (need_var) cp_async8(aIn + 4 * IN_F, pf);
+        cp_async_wait_all();
     }
-    if (do_x) cu = velu[off];
-    if (do_y) cv = velv[off];
-    __syncthreads();
+    block_barrier();
 
     for (int k = 0; k < Nz; ++k) {
-        const unsigned b = k & 1;
-        const bool more = k + 1 < Nz;
-        // ---- next plane: tile interior + halo, raw inputs (consumed after the barrier / next iteration) ----
-        double nu = 0, nv = 0, nw = 0, nG = 0, nf = 0;
-        if (more) {
-            if (is_main) {
-                sts(aC + (b ^ 1) * C_BUF_B, ck1);
-                if (h_s0) cp_async8(h_s0 + (b ^ 1) * C_BUF_B, Uold + h_g0 + plane);
-                if (h_s1) cp_async8(h_s1 + (b ^ 1) * C_BUF_B, Uold + h_g1 + plane);
-                nw = velw[off + 2 * plane];
-                if (use_G) nG = P.G[toff + plane];
-                if (need_var) nf = varp[off + plane];
-            }
-            if (do_x) nu = velu[off + plane];
-            if (do_y) nv = velv[off + plane];
+        const unsigned boff = (k & 1) * BUF_B, noff = BUF_B - boff;
+        // ---- plane k+1 -> the other buffer: own value, halo and per-thread inputs, all asynchronous ----
+        if (k + 1 < Nz) {
+            sts(aC + noff, ck1);
+            if (h_s0) cp_async8(h_s0 + noff, h_g0 + plane);
+            if (h_s1) cp_async8(h_s1 + noff, h_g1 + plane);
+            cp_async8(aIn + noff, pu + plane);
+            cp_async8(aIn + noff + IN_F, pv + plane);
+            cp_async8(aIn + noff + 2 * IN_F, pw + 2 * plane);
+            if (use_G) cp_async8(aIn + noff + 3 * IN_F, pG + plane);
+            if (need_var) cp_async8(aIn + noff + 4 * IN_F, pf + plane);
         }
         // ---- faces of plane k ------------------------------------------------------------------
-        const unsigned aCb = aC + b * C_BUF_B;
-        double Fw = 0, Fs = 0, Ft = 0, other = 0;
-        if (is_main && NSUB == 2) other = lds(aCb + partner_off);
-        const double cmid = is_main ? ck : lds(aCb);
-        if (do_x) {                                      // west face of (i, j)  [helpers: east edge of the tile]
-            Fw = (P.area[0] * cu) * face_from_tile(aCb, 8, cmid, cu);
-            sts(aFx + b * FX_BUF_B, Fw);
-            if (sub == 0) sts(aQx + b * QX_BUF_B, cu);
-        }
-        if (do_y) {                                      // south face of (i, j) [helpers: north edge of the tile]
-            Fs = (P.area[1] * cv) * face_from_tile(aCb, 8 * ZM_CW, cmid, cv);
-            sts(aFy + b * FY_BUF_B, Fs);
-            if (sub == 0) sts(aQy + b * QY_BUF_B, cv);
-        }
-        if (is_main) {                                   // top face of cell k: 1-based face index m = k + 2
+        const unsigned aCb = aC + boff;
+        const double cu = lds(aIn + boff), cv = lds(aIn + boff + IN_F), cw = lds(aIn + boff + 2 * IN_F);
+        double other = 0.0;
+        if (NSUB == 2) other = lds(aCb + partner_off);
+        const double Fw = (P.area[0] * cu) * zm_face_from_tile<8>(aCb, ck, cu);
+        sts(aFx + boff, Fw);
+        if (sub == 0) sts(aQx + boff, cu);
+        const double Fs = (P.area[1] * cv) * zm_face_from_tile<8 * ZM_CW>(aCb, ck, cv);
+        sts(aFy + boff, Fs);
+        if (sub == 0) sts(aQy + boff, cv);
+        double ct;
+        {                                                // top face of cell k: 1-based face index m = k + 2
             const int m = k + 2;
             const bool left = cw > 0.0;
-            double ct;
             if (m >= 4 && m <= Nz - 2) {
-                // the increment is odd in the differences: right-biased = minus the mirrored evaluation
-                const double inc = weno5z_inc_q(left ? d0 : d4, left ? d1 : d3, d2, left ? d3 : d1,
-                                                left ? Qa : Qd, left ? Qb : Qc, left ? Qc : Qb);
+                const double inc = zm_inc_q(left ? d0 : d4, left ? d1 : d3, d2, left ? d3 : d1,
+                                            left ? Qa : Qd, left ? Qb : Qc, left ? Qc : Qb);
                 ct = left ? ck + inc : ck1 - inc;
             } else if (m == Nz + 1) {
                 ct = ck;                                  // top wall
@@ -266,15 +311,15 @@ __global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_z
             } else {
                 ct = (ck + ck1) / 2.0;                    // m = 2, Nz: Centered2
             }
-            Ft = (P.area[2] * cw) * ct;
         }
+        const double Ft = (P.area[2] * cw) * ct;
         cp_async_wait_all();
-        __syncthreads();
+        block_barrier();
 
         // ---- tendency, RK3 substep, advance the window ---------------------------------------------
-        if (is_main) {
-            const double Fe = lds(aFx + b * FX_BUF_B + 8), Fn = lds(aFy + b * FY_BUF_B + 8 * ZM_TX);
-            const double ue = lds(aQx + b * QX_BUF_B + 8), vn = lds(aQy + b * QY_BUF_B + 8 * ZM_TX);
+        {
+            const double Fe = lds(aFx + boff + 8), Fn = lds(aFy + boff + 8 * ZM_TX);
+            const double ue = lds(aQx + boff + 8), vn = lds(aQy + boff + 8 * ZM_TX);
             const double inv_vol = 1.0 / P.volume;
             double div_flux = (Fe - Fw);
             div_flux = div_flux + (Fn - Fs);
@@ -288,8 +333,9 @@ __global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_z
             double gC, gS;
             if (NSUB == 2) { gC = sub ? other : ck; gS = sub ? ck : other; }
             else { gC = ck; gS = 0.0; }
-            double src = cf;
+            double src;
             if (item.is_map) src = item.src == 0 ? (cu + ue) / 2.0 : (item.src == 1 ? (cv + vn) / 2.0 : (wb + cw) / 2.0);
+            else src = need_var ? lds(aIn + boff + 4 * IN_F) : 0.0;
             const double n2 = c * c + d * d;
             double forcing;
             if (NSUB == 1)      forcing = item.is_map ? (-c / n2 * src) + (-c * gC) : (-c * gC) + src;
@@ -298,21 +344,20 @@ __global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_z
             const double Gn = (-div_flux + ck * div_u) + forcing;
             double unew;
             if (P.first_stage) unew = ck + P.dt * P.gamma * Gn;
-            else               unew = ck + P.dt * (P.gamma * Gn + P.zeta * cG);
-            P.U_new[toff] = unew;
-            if (P.store_G) P.G[toff] = Gn;
+            else               unew = ck + P.dt * (P.gamma * Gn + P.zeta * lds(aIn + boff + 3 * IN_F));
+            pUn[0] = unew;
+            if (P.store_G) pG[0] = Gn;
             // advance the window to cell k+1
             Fb = Ft; wb = cw;
-            double c5 = 0;
-            if (k + 5 <= Nz + 2) c5 = Uold[toff + 5 * plane];
             const double dnew = ck4 - ck3;                // d[k+3]
             const double s = dnew - d4;
             d0 = d1; d1 = d2; d2 = d3; d3 = d4; d4 = dnew;
             Qa = Qb; Qb = Qc; Qc = Qd; Qd = 3.25 * s * s;
-            ck = ck1; ck1 = ck2; ck2 = ck3; ck3 = ck4; ck4 = c5;
+            ck = ck1; ck1 = ck2; ck2 = ck3; ck3 = ck4;
+            if (k + 5 <= Nz + 2) ck4 = pU[5 * plane];     // consumed one iteration later
         }
-        cu = nu; cv = nv; cw = nw; cG = nG; cf = nf;
-        off += plane; toff += plane;
+        pU += plane; pUn += plane; pG += plane; pu += plane; pv += plane; pw += plane;
+        if (need_var) pf += plane;
         h_g0 += plane; h_g1 += plane;
     }
 }
@@ -337,11 +382,11 @@ extern "C" cudaError_t lfb_launch_stage_zmarch(const LfbStageParams *P, cudaStre
     dim3 grid(P->n_items * ytiles, L.N[0] / ZM_TX, 1);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(lfb_stage_zmarch<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * ZmSmem<1>::TOTAL));
-        cudaFuncSetAttribute(lfb_stage_zmarch<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * ZmSmem<2>::TOTAL));
+        cudaFuncSetAttribute(lfb_stage_zmarch<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZmSmem<1>::BYTES);
+        cudaFuncSetAttribute(lfb_stage_zmarch<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZmSmem<2>::BYTES);
         configured = true;
     }
-    if (P->single_exp) lfb_stage_zmarch<1><<<grid, 1 * ZM_MAIN + 32 + 32, 8 * ZmSmem<1>::TOTAL, stream>>>(*P);
-    else               lfb_stage_zmarch<2><<<grid, 2 * ZM_MAIN + 64 + 32, 8 * ZmSmem<2>::TOTAL, stream>>>(*P);
+    if (P->single_exp) lfb_stage_zmarch<1><<<grid, 1 * ZM_MAIN + 32 + 32, ZmSmem<1>::BYTES, stream>>>(*P);
+    else               lfb_stage_zmarch<2><<<grid, 2 * ZM_MAIN + 64 + 32, ZmSmem<2>::BYTES, stream>>>(*P);
     return cudaGetLastError();
 }
