@@ -27,10 +27,7 @@
 #include "lfb_math.cuh"
 
 #define ZM_TX 32
-#define ZM_TY 8
-#define ZM_MAIN (ZM_TX * ZM_TY)
 #define ZM_CW (ZM_TX + 6)
-#define ZM_CH (ZM_TY + 6)
 
 // ---- shared memory through 32-bit shared-window addresses -----------------------------------------
 __device__ __forceinline__ double lds(unsigned a)
@@ -57,22 +54,24 @@ __device__ __forceinline__ double weno3z_inc(double do_, double dn)
     return (a0 * (0.5 * dn) + a1 * (0.5 * do_)) / (a0 + a1);
 }
 
-// shared memory carve-up (doubles).  Everything that is double-buffered along the march lives in one
-// per-buffer block, so a single uniform offset (k & 1) * BUF selects the buffer for all arrays.
-template <int NSUB>
+// shared memory carve-up (doubles).  Every per-cell array (tracer tile, x/y fluxes, x/y face velocities)
+// uses the geometry of the haloed tile (ZM_CH rows of ZM_CW), so one per-thread offset addresses them
+// all; everything that is double-buffered along the march lives in one per-buffer block, so a single
+// uniform offset (k & 1) * BUF selects the buffer.
+template <int NSUB, int TY>
 struct ZmSmem {
-    static constexpr int C_SUB = ZM_CH * ZM_CW;                 // one tracer plane with halo
-    static constexpr int FX_SUB = ZM_TY * (ZM_TX + 1);
-    static constexpr int FY_SUB = (ZM_TY + 1) * ZM_TX;
-    static constexpr int NMAIN = NSUB * ZM_MAIN;
-    static constexpr int OFF_C = 0;                             // C[NSUB][CH][CW]
-    static constexpr int OFF_FX = OFF_C + NSUB * C_SUB;         // Fx[NSUB][TY][TX+1]
-    static constexpr int OFF_FY = OFF_FX + NSUB * FX_SUB;       // Fy[NSUB][TY+1][TX]
-    static constexpr int OFF_QX = OFF_FY + NSUB * FY_SUB;       // Qx[TY][TX+1]   face velocities u
-    static constexpr int OFF_QY = OFF_QX + FX_SUB;              // Qy[TY+1][TX]   face velocities v
-    static constexpr int OFF_IN = OFF_QY + FY_SUB;              // In[5][NMAIN]   per-thread inputs u,v,w,G-,f of the plane
-    static constexpr int BUF = (OFF_IN + 5 * NMAIN + 15) / 16 * 16;
+    static constexpr int CH = TY + 6;
+    static constexpr int TILE = CH * ZM_CW;                     // one haloed plane
+    static constexpr int NMAIN = NSUB * ZM_TX * TY;
+    static constexpr int OFF_C = 0;                             // C [NSUB][TILE]  tracer values
+    static constexpr int OFF_FX = OFF_C + NSUB * TILE;          // Fx[NSUB][TILE]  west-face fluxes
+    static constexpr int OFF_FY = OFF_FX + NSUB * TILE;         // Fy[NSUB][TILE]  south-face fluxes
+    static constexpr int OFF_QX = OFF_FY + NSUB * TILE;         // Qx[TILE]        u at west faces
+    static constexpr int OFF_QY = OFF_QX + TILE;                // Qy[TILE]        v at south faces
+    static constexpr int OFF_IN = OFF_QY + TILE;                // In[6][NMAIN]    per-thread inputs u,v,w,G-,f,c[k+5]
+    static constexpr int BUF = (OFF_IN + 6 * NMAIN + 15) / 16 * 16;
     static constexpr int BYTES = 2 * BUF * 8;
+    static constexpr int THREADS = NMAIN + NSUB * 32 + 32;
 };
 
 __device__ __forceinline__ void block_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
@@ -148,48 +147,50 @@ __device__ __forceinline__ double zm_face_from_tile(unsigned a, double cm, doubl
     return left ? m1 + inc : cm - inc;
 }
 
-template <int NSUB>
-__global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_zmarch(const __grid_constant__ LfbStageParams P)
+template <int NSUB, int TY>
+__global__ void __launch_bounds__(ZmSmem<NSUB, TY>::THREADS, 1) lfb_stage_zmarch(const __grid_constant__ LfbStageParams P)
 {
-    using SM = ZmSmem<NSUB>;
+    using SM = ZmSmem<NSUB, TY>;
     extern __shared__ __align__(16) double zm_smem[];
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(zm_smem);
     constexpr unsigned BUF_B = 8u * SM::BUF;
+    constexpr int ROW_B = 8 * ZM_CW;                                  // byte stride between tile rows
+    constexpr unsigned oC = 8u * SM::OFF_C, oFX = 8u * SM::OFF_FX, oFY = 8u * SM::OFF_FY, oQX = 8u * SM::OFF_QX,
+                       oQY = 8u * SM::OFF_QY;
     const LfbLayout &L = P.L;
     const int tid = threadIdx.x;
     const int item_id = blockIdx.x % P.n_items;
     const int ytile = blockIdx.x / P.n_items;
     const int i0 = blockIdx.y * ZM_TX;
-    const int j0 = P.j0 + ytile * ZM_TY;
+    const int j0 = P.j0 + ytile * TY;
     const LfbItem item = P.items[item_id];
     const int Nz = L.N[2];
     const int64_t plane = L.plane;
+    const int jmax = L.N[1] + L.H[1];                                 // last row that exists in the arrays
 
     if (tid >= SM::NMAIN) {
         // ================= helper warps: the extra faces on the north / east edge of the tile =================
         const int hl = tid - SM::NMAIN;
         int sub, tx, ty, kind;                   // kind 1: y face at row j0+TY, 2: x face at column i0+TX, 0: idle lane
-        if (hl < NSUB * 32) { kind = 1; sub = hl / 32; tx = hl % 32; ty = ZM_TY; }
+        if (hl < NSUB * 32) { kind = 1; sub = hl / 32; tx = hl % 32; ty = TY; }
         else {
             const int xl = hl - NSUB * 32;
-            if (xl < NSUB * ZM_TY) { kind = 2; sub = xl / ZM_TY; ty = xl % ZM_TY; tx = ZM_TX; }
+            if (xl < NSUB * TY) { kind = 2; sub = xl / TY; ty = xl % TY; tx = ZM_TX; }
             else { kind = 0; sub = 0; tx = 0; ty = 0; }
         }
-        const unsigned aC = sbase + 8u * (SM::OFF_C + sub * SM::C_SUB + (ty + 3) * ZM_CW + tx + 3);
-        const unsigned aF = kind == 1 ? sbase + 8u * (SM::OFF_FY + sub * SM::FY_SUB + ty * ZM_TX + tx)
-                                      : sbase + 8u * (SM::OFF_FX + sub * SM::FX_SUB + ty * (ZM_TX + 1) + tx);
-        const unsigned aQ = kind == 1 ? sbase + 8u * (SM::OFF_QY + ty * ZM_TX + tx)
-                                      : sbase + 8u * (SM::OFF_QX + ty * (ZM_TX + 1) + tx);
-        const double *__restrict__ vel = (kind == 1 ? P.vel[1] : P.vel[0]) + L.at(i0 + tx, j0 + ty, 0);
+        const unsigned aT = sbase + 8u * (sub * SM::TILE + (ty + 3) * ZM_CW + tx + 3);
+        const unsigned aF = aT + (kind == 1 ? oFY : oFX);
+        const unsigned aQ = sbase + 8u * ((ty + 3) * ZM_CW + tx + 3) + (kind == 1 ? oQY : oQX);
+        const double *__restrict__ vel = (kind == 1 ? P.vel[1] : P.vel[0]) + L.at(i0 + tx, min(j0 + ty, jmax), 0);
         const double area = kind == 1 ? P.area[1] : P.area[0];
         double q = kind ? vel[0] : 0.0;
         block_barrier();                                            // prologue barrier of the main warps
         for (int k = 0; k < Nz; ++k) {
             const unsigned boff = (k & 1) * BUF_B;
             if (kind) {
-                const double cm = lds(aC + boff);
-                const double cf = kind == 1 ? zm_face_from_tile<8 * ZM_CW>(aC + boff, cm, q)
-                                            : zm_face_from_tile<8>(aC + boff, cm, q);
+                const double cm = lds(aT + oC + boff);
+                const double cf = kind == 1 ? zm_face_from_tile<ROW_B>(aT + oC + boff, cm, q)
+                                            : zm_face_from_tile<8>(aT + oC + boff, cm, q);
                 sts(aF + boff, (area * q) * cf);
                 if (sub == 0) sts(aQ + boff, q);
                 vel += plane;
@@ -201,18 +202,16 @@ __global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_z
     }
 
     // ================= main warps: one cell column of one tracer per thread =================
-    const int tx = tid % ZM_TX, ty = (tid / ZM_TX) % ZM_TY, sub = tid / ZM_MAIN;
-    const unsigned aC = sbase + 8u * (SM::OFF_C + sub * SM::C_SUB + (ty + 3) * ZM_CW + tx + 3);
-    const unsigned aFx = sbase + 8u * (SM::OFF_FX + sub * SM::FX_SUB + ty * (ZM_TX + 1) + tx);
-    const unsigned aFy = sbase + 8u * (SM::OFF_FY + sub * SM::FY_SUB + ty * ZM_TX + tx);
-    const unsigned aQx = sbase + 8u * (SM::OFF_QX + ty * (ZM_TX + 1) + tx);
-    const unsigned aQy = sbase + 8u * (SM::OFF_QY + ty * ZM_TX + tx);
+    const int tx = tid % ZM_TX, ty = (tid / ZM_TX) % TY, sub = tid / (ZM_TX * TY);
+    const unsigned aT = sbase + 8u * (sub * SM::TILE + (ty + 3) * ZM_CW + tx + 3);       // tracer-indexed arrays
+    const unsigned aV = sbase + 8u * ((ty + 3) * ZM_CW + tx + 3);                        // velocity arrays
     const unsigned aIn = sbase + 8u * (SM::OFF_IN + tid);
     constexpr unsigned IN_F = 8u * SM::NMAIN;                        // stride between the input fields of a thread
-    const int partner_off = (NSUB == 2) ? (sub ? -8 * SM::C_SUB : 8 * SM::C_SUB) : 0;
+    const int partner_off = (NSUB == 2) ? (sub ? -8 * SM::TILE : 8 * SM::TILE) : 0;
+    const bool active = j0 + ty < P.j1;                              // partial tiles at the end of the y range
 
     // global pointers of this thread's column (advanced by one plane per iteration)
-    const int64_t off0 = L.at(i0 + tx, j0 + ty, 0);
+    const int64_t off0 = L.at(i0 + tx, min(j0 + ty, jmax), 0);
     const int64_t tbase = (int64_t)(item.tracer_c + sub) * L.len;
     const double *__restrict__ pU = P.U_old + tbase + off0;
     double *__restrict__ pUn = P.U_new + tbase + off0;
@@ -226,22 +225,24 @@ __global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_z
     unsigned h_s0 = 0, h_s1 = 0;                 // shared byte address in buffer 0 (0 = none)
     const double *h_g0 = nullptr, *h_g1 = nullptr;
     {
-        const int t = tid % ZM_MAIN;
+        constexpr int NT = ZM_TX * TY;
+        const int t = tid % NT;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
-            const int e = t + r * ZM_MAIN;
+            const int e = t + r * NT;
             int row = -1, cc = 0;
             if (e < 3 * ZM_CW) { row = e / ZM_CW; cc = e % ZM_CW; }
-            else if (e < 6 * ZM_CW) { row = ZM_TY + 3 + (e - 3 * ZM_CW) / ZM_CW; cc = (e - 3 * ZM_CW) % ZM_CW; }
-            else if (e < 6 * ZM_CW + 3 * ZM_TY) { row = 3 + (e - 6 * ZM_CW) / 3; cc = (e - 6 * ZM_CW) % 3; }
-            else if (e < 6 * ZM_CW + 6 * ZM_TY) { row = 3 + (e - 6 * ZM_CW - 3 * ZM_TY) / 3; cc = ZM_TX + 3 + (e - 6 * ZM_CW - 3 * ZM_TY) % 3; }
+            else if (e < 6 * ZM_CW) { row = TY + 3 + (e - 3 * ZM_CW) / ZM_CW; cc = (e - 3 * ZM_CW) % ZM_CW; }
+            else if (e < 6 * ZM_CW + 3 * TY) { row = 3 + (e - 6 * ZM_CW) / 3; cc = (e - 6 * ZM_CW) % 3; }
+            else if (e < 6 * ZM_CW + 6 * TY) { row = 3 + (e - 6 * ZM_CW - 3 * TY) / 3; cc = ZM_TX + 3 + (e - 6 * ZM_CW - 3 * TY) % 3; }
             if (row >= 0) {
-                const unsigned sa = sbase + 8u * (SM::OFF_C + sub * SM::C_SUB + row * ZM_CW + cc);
-                const double *ga = P.U_old + tbase + L.at(i0 - 3 + cc, j0 - 3 + row, 0);
+                const unsigned sa = sbase + oC + 8u * (sub * SM::TILE + row * ZM_CW + cc);
+                const double *ga = P.U_old + tbase + L.at(i0 - 3 + cc, min(j0 - 3 + row, jmax), 0);
                 if (r == 0) { h_s0 = sa; h_g0 = ga; } else { h_s1 = sa; h_g1 = ga; }
             }
         }
     }
+    static_assert(6 * ZM_CW + 6 * TY <= 2 * ZM_TX * TY, "tile halo does not fit two duties per thread");
 
     // ---- prologue: z window of the column, plane-0 tile and inputs ------------------------------------
     double d0, d1, d2, d3, d4;                   // d[k-2..k+2], d[m] = c[m+1] - c[m]
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_z
         s = d4 - d3; Qd = 3.25 * s * s;
         wb = pw[0];
         Fb = (P.area[2] * wb) * ck;                     // wall face m = 1: Centered2 on the mirrored halo
-        sts(aC, ck);
+        sts(aT + oC, ck);
         if (h_s0) cp_async8(h_s0, h_g0);
         if (h_s1) cp_async8(h_s1, h_g1);
         cp_async8(aIn, pu);
@@ -267,6 +268,7 @@ __global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_z
         cp_async8(aIn + 2 * IN_F, pw + plane);
         if (use_G) cp_async8(aIn + 3 * IN_F, pG);
         if (need_var) cp_async8(aIn + 4 * IN_F, pf);
+        cp_async8(aIn + 5 * IN_F, pU + 5 * plane);
         cp_async_wait_all();
     }
     block_barrier();
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_z
         const unsigned boff = (k & 1) * BUF_B, noff = BUF_B - boff;
         // ---- plane k+1 -> the other buffer: own value, halo and per-thread inputs, all asynchronous ----
         if (k + 1 < Nz) {
-            sts(aC + noff, ck1);
+            sts(aT + oC + noff, ck1);
             if (h_s0) cp_async8(h_s0 + noff, h_g0 + plane);
             if (h_s1) cp_async8(h_s1 + noff, h_g1 + plane);
             cp_async8(aIn + noff, pu + plane);
@@ -283,18 +285,19 @@ __global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_z
             cp_async8(aIn + noff + 2 * IN_F, pw + 2 * plane);
             if (use_G) cp_async8(aIn + noff + 3 * IN_F, pG + plane);
             if (need_var) cp_async8(aIn + noff + 4 * IN_F, pf + plane);
+            if (k + 6 <= Nz + 2) cp_async8(aIn + noff + 5 * IN_F, pU + 6 * plane);
         }
         // ---- faces of plane k ------------------------------------------------------------------
-        const unsigned aCb = aC + boff;
+        const unsigned aCb = aT + oC + boff;
         const double cu = lds(aIn + boff), cv = lds(aIn + boff + IN_F), cw = lds(aIn + boff + 2 * IN_F);
         double other = 0.0;
         if (NSUB == 2) other = lds(aCb + partner_off);
         const double Fw = (P.area[0] * cu) * zm_face_from_tile<8>(aCb, ck, cu);
-        sts(aFx + boff, Fw);
-        if (sub == 0) sts(aQx + boff, cu);
-        const double Fs = (P.area[1] * cv) * zm_face_from_tile<8 * ZM_CW>(aCb, ck, cv);
-        sts(aFy + boff, Fs);
-        if (sub == 0) sts(aQy + boff, cv);
+        sts(aT + oFX + boff, Fw);
+        if (sub == 0) sts(aV + oQX + boff, cu);
+        const double Fs = (P.area[1] * cv) * zm_face_from_tile<ROW_B>(aCb, ck, cv);
+        sts(aT + oFY + boff, Fs);
+        if (sub == 0) sts(aV + oQY + boff, cv);
         double ct;
         {                                                // top face of cell k: 1-based face index m = k + 2
             const int m = k + 2;
@@ -318,8 +321,8 @@ __global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_z
 
         // ---- tendency, RK3 substep, advance the window ---------------------------------------------
         {
-            const double Fe = lds(aFx + boff + 8), Fn = lds(aFy + boff + 8 * ZM_TX);
-            const double ue = lds(aQx + boff + 8), vn = lds(aQy + boff + 8 * ZM_TX);
+            const double Fe = lds(aT + oFX + boff + 8), Fn = lds(aT + oFY + boff + ROW_B);
+            const double ue = lds(aV + oQX + boff + 8), vn = lds(aV + oQY + boff + ROW_B);
             const double inv_vol = 1.0 / P.volume;
             double div_flux = (Fe - Fw);
             div_flux = div_flux + (Fn - Fs);
@@ -345,8 +348,10 @@ __global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_z
             double unew;
             if (P.first_stage) unew = ck + P.dt * P.gamma * Gn;
             else               unew = ck + P.dt * (P.gamma * Gn + P.zeta * lds(aIn + boff + 3 * IN_F));
-            pUn[0] = unew;
-            if (P.store_G) pG[0] = Gn;
+            if (active) {
+                pUn[0] = unew;
+                if (P.store_G) pG[0] = Gn;
+            }
             // advance the window to cell k+1
             Fb = Ft; wb = cw;
             const double dnew = ck4 - ck3;                // d[k+3]
@@ -354,13 +359,17 @@ __global__ void __launch_bounds__(NSUB *ZM_MAIN + NSUB * 32 + 32, 1) lfb_stage_z
             d0 = d1; d1 = d2; d2 = d3; d3 = d4; d4 = dnew;
             Qa = Qb; Qb = Qc; Qc = Qd; Qd = 3.25 * s * s;
             ck = ck1; ck1 = ck2; ck2 = ck3; ck3 = ck4;
-            if (k + 5 <= Nz + 2) ck4 = pU[5 * plane];     // consumed one iteration later
+            ck4 = lds(aIn + boff + 5 * IN_F);             // c[k+5], staged one plane ago
         }
         pU += plane; pUn += plane; pG += plane; pu += plane; pv += plane; pw += plane;
         if (need_var) pf += plane;
         h_g0 += plane; h_g1 += plane;
     }
 }
+
+#ifndef ZM_TY
+#define ZM_TY 6          // tile height: 6 rows -> 480 threads per block, 136 registers per thread available
+#endif
 
 extern "C" int lfb_zmarch_supported(const LfbStageParams *P)
 {
@@ -369,24 +378,29 @@ extern "C" int lfb_zmarch_supported(const LfbStageParams *P)
     if (L.topo[0] != LFB_PERIODIC || L.topo[2] != LFB_BOUNDED) return 0;
     if (L.topo[1] != LFB_PERIODIC && !(L.connected_lo[1] && L.connected_hi[1])) return 0;
     if (!(P->vel_present[0] && P->vel_present[1] && P->vel_present[2])) return 0;
-    if (L.N[0] % ZM_TX || (P->j1 - P->j0) % ZM_TY || L.N[2] < 8) return 0;
+    if (L.N[0] % ZM_TX || L.N[1] < 4 || L.N[2] < 8) return 0;
     if (L.H[0] < 3 || L.H[1] < 3 || L.H[2] < 3) return 0;
     return 1;
 }
 
-extern "C" cudaError_t lfb_launch_stage_zmarch(const LfbStageParams *P, cudaStream_t stream)
+template <int NSUB, int TY>
+static cudaError_t zm_launch(const LfbStageParams *P, cudaStream_t stream)
 {
-    const LfbLayout &L = P->L;
-    if (P->j1 <= P->j0) return cudaSuccess;
-    const int ytiles = (P->j1 - P->j0) / ZM_TY;
-    dim3 grid(P->n_items * ytiles, L.N[0] / ZM_TX, 1);
+    using SM = ZmSmem<NSUB, TY>;
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(lfb_stage_zmarch<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZmSmem<1>::BYTES);
-        cudaFuncSetAttribute(lfb_stage_zmarch<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZmSmem<2>::BYTES);
+        cudaError_t e = cudaFuncSetAttribute(lfb_stage_zmarch<NSUB, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES);
+        if (e != cudaSuccess) return e;
         configured = true;
     }
-    if (P->single_exp) lfb_stage_zmarch<1><<<grid, 1 * ZM_MAIN + 32 + 32, ZmSmem<1>::BYTES, stream>>>(*P);
-    else               lfb_stage_zmarch<2><<<grid, 2 * ZM_MAIN + 64 + 32, ZmSmem<2>::BYTES, stream>>>(*P);
+    const int ytiles = (P->j1 - P->j0 + TY - 1) / TY;
+    dim3 grid(P->n_items * ytiles, P->L.N[0] / ZM_TX, 1);
+    lfb_stage_zmarch<NSUB, TY><<<grid, SM::THREADS, SM::BYTES, stream>>>(*P);
     return cudaGetLastError();
+}
+
+extern "C" cudaError_t lfb_launch_stage_zmarch(const LfbStageParams *P, cudaStream_t stream)
+{
+    if (P->j1 <= P->j0) return cudaSuccess;
+    return P->single_exp ? zm_launch<1, ZM_TY>(P, stream) : zm_launch<2, ZM_TY>(P, stream);
 }
