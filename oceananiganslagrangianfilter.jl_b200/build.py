@@ -21,6 +21,7 @@ HEADERS = ["lfb_internal.h", "lfb_math.cuh", os.path.join(ROOT, "include", "lfb2
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off", "-ccbin", "/usr/bin/g++"]
+CFLAGS += os.environ.get("LFB_NVCC_FLAGS", "").split()      # experiments, e.g. LFB_NVCC_FLAGS=-DZM_TY=7
 
 
 def _stale(target, deps):

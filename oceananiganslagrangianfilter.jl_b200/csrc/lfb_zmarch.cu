@@ -76,8 +76,8 @@ struct ZmSmem {
 
 __device__ __forceinline__ void block_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
 
-// num / den for den > 0 in the normal range: reciprocal seed + two Newton steps + one residual correction
-// (about 1 ulp; no special-case branch, unlike the IEEE division sequence)
+// num / den for den > 0 in the normal range: reciprocal seed + two Newton steps (a couple of ulp, far inside
+// the 1e-12 parity budget; no special-case branch, unlike the IEEE division sequence)
 __device__ __forceinline__ double div_pos(double num, double den)
 {
     double r;
@@ -86,8 +86,7 @@ __device__ __forceinline__ double div_pos(double num, double den)
     r = fma(r, e, r);
     e = fma(-den, r, 1.0);
     r = fma(r, e, r);
-    const double q = num * r;
-    return fma(fma(-den, q, num), r, q);
+    return num * r;
 }
 
 // Z weights and candidate increments from the smoothness indicators; returns (face value - n).
@@ -130,21 +129,37 @@ __device__ __forceinline__ double zm_inc_q(double dp, double do_, double dn, dou
     return zm_from_betas(b0, b1, b2, dp, do_, dn, de);
 }
 
-// Upwind WENO5-Z face value from a line of the shared tile: `a` is the 32-bit address of the cell on the
-// high side of the face (cell m), S the byte stride along the axis, cm its value, q the face velocity.
-// The increment is odd in the differences, so the right-biased value is n - inc(mirrored differences)
-// and no operand has to be negated.
+// A line of the shared tile around a face: `a` is the 32-bit address of the cell on the high side of the
+// face (cell m), S the byte stride along the axis.  Loads are issued first (for both in-plane faces) so the
+// arithmetic of the two faces can overlap.
+struct ZmLine { double m1, m2, p1, far; };
+
+template <int S>
+__device__ __forceinline__ ZmLine zm_load_line(unsigned a, bool left)
+{
+    ZmLine l;
+    l.m1 = lds(a - S); l.m2 = lds(a - 2 * S); l.p1 = lds(a + S);
+    l.far = lds(left ? a - 3 * S : a + 2 * S);
+    return l;
+}
+
+// Upwind WENO5-Z face value.  The increment is odd in the differences, so the right-biased value is
+// n - inc(mirrored differences) and no operand has to be negated.
+//   left : p,o,n,e,f = far,m2,m1,cm,p1      right: p,o,n,e,f = far,p1,cm,m1,m2 (mirrored)
+__device__ __forceinline__ double zm_face(const ZmLine &l, double cm, bool left)
+{
+    const double d_lo = l.m1 - l.m2, d_mid = cm - l.m1, d_hi = l.p1 - cm;      // differences in storage order
+    const double d_far = left ? l.m2 - l.far : l.far - l.p1;
+    const double inc = zm_inc(d_far, left ? d_lo : d_hi, d_mid, left ? d_hi : d_lo);
+    return left ? l.m1 + inc : cm - inc;
+}
+
 template <int S>
 __device__ __forceinline__ double zm_face_from_tile(unsigned a, double cm, double q)
 {
     const bool left = q > 0.0;
-    const double m1 = lds(a - S), m2 = lds(a - 2 * S), p1 = lds(a + S);
-    const double far = lds(left ? a - 3 * S : a + 2 * S);
-    // left : p,o,n,e,f = far,m2,m1,cm,p1      right: p,o,n,e,f = far,p1,cm,m1,m2 (mirrored)
-    const double d_lo = m1 - m2, d_mid = cm - m1, d_hi = p1 - cm;            // differences in storage order
-    const double d_far = left ? m2 - far : far - p1;
-    const double inc = zm_inc(d_far, left ? d_lo : d_hi, d_mid, left ? d_hi : d_lo);
-    return left ? m1 + inc : cm - inc;
+    const ZmLine l = zm_load_line<S>(a, left);
+    return zm_face(l, cm, left);
 }
 
 template <int NSUB, int TY>
@@ -220,6 +235,18 @@ __global__ void __launch_bounds__(ZmSmem<NSUB, TY>::THREADS, 1) lfb_stage_zmarch
     const bool need_var = !item.is_map && sub == 0;
     const double *__restrict__ pf = need_var ? P.var[item.src] + off0 : nullptr;
     const bool use_G = !P.first_stage;
+    // forcing = k_src * src + (k_own * own + k_oth * partner)   (create_forcing, utils:731-865)
+    double k_src, k_own, k_oth;
+    {
+        const double c = item.c, d = item.d, n2 = c * c + d * d;
+        k_own = -c;
+        k_oth = NSUB == 1 ? 0.0 : (sub == 0 ? -d : d);
+        if (item.is_map) k_src = (NSUB == 2 && sub == 1) ? -d / n2 : -c / n2;
+        else             k_src = sub == 0 ? 1.0 : 0.0;
+    }
+    const int map_axis = item.is_map ? item.src : -1;
+    const double inv_vol = 1.0 / P.volume;
+    const double dtg = P.dt * P.gamma, dtz = P.dt * P.zeta;
 
     // halo duties of the tile: up to two elements per thread
     unsigned h_s0 = 0, h_s1 = 0;                 // shared byte address in buffer 0 (0 = none)
@@ -292,12 +319,14 @@ __global__ void __launch_bounds__(ZmSmem<NSUB, TY>::THREADS, 1) lfb_stage_zmarch
         const double cu = lds(aIn + boff), cv = lds(aIn + boff + IN_F), cw = lds(aIn + boff + 2 * IN_F);
         double other = 0.0;
         if (NSUB == 2) other = lds(aCb + partner_off);
-        const double Fw = (P.area[0] * cu) * zm_face_from_tile<8>(aCb, ck, cu);
+        const bool left_x = cu > 0.0, left_y = cv > 0.0;
+        const ZmLine lx = zm_load_line<8>(aCb, left_x);
+        const ZmLine ly = zm_load_line<ROW_B>(aCb, left_y);
+        const double Fw = (P.area[0] * cu) * zm_face(lx, ck, left_x);
+        const double Fs = (P.area[1] * cv) * zm_face(ly, ck, left_y);
         sts(aT + oFX + boff, Fw);
-        if (sub == 0) sts(aV + oQX + boff, cu);
-        const double Fs = (P.area[1] * cv) * zm_face_from_tile<ROW_B>(aCb, ck, cv);
         sts(aT + oFY + boff, Fs);
-        if (sub == 0) sts(aV + oQY + boff, cv);
+        if (sub == 0) { sts(aV + oQX + boff, cu); sts(aV + oQY + boff, cv); }
         double ct;
         {                                                // top face of cell k: 1-based face index m = k + 2
             const int m = k + 2;
@@ -312,7 +341,7 @@ __global__ void __launch_bounds__(ZmSmem<NSUB, TY>::THREADS, 1) lfb_stage_zmarch
                 const double inc = weno3z_inc(left ? d1 : d3, d2);
                 ct = left ? ck + inc : ck1 - inc;
             } else {
-                ct = (ck + ck1) / 2.0;                    // m = 2, Nz: Centered2
+                ct = 0.5 * (ck + ck1);                    // m = 2, Nz: Centered2
             }
         }
         const double Ft = (P.area[2] * cw) * ct;
@@ -323,7 +352,6 @@ __global__ void __launch_bounds__(ZmSmem<NSUB, TY>::THREADS, 1) lfb_stage_zmarch
         {
             const double Fe = lds(aT + oFX + boff + 8), Fn = lds(aT + oFY + boff + ROW_B);
             const double ue = lds(aV + oQX + boff + 8), vn = lds(aV + oQY + boff + ROW_B);
-            const double inv_vol = 1.0 / P.volume;
             double div_flux = (Fe - Fw);
             div_flux = div_flux + (Fn - Fs);
             div_flux = div_flux + (Ft - Fb);
@@ -332,22 +360,14 @@ __global__ void __launch_bounds__(ZmSmem<NSUB, TY>::THREADS, 1) lfb_stage_zmarch
             div_u = div_u + (P.area[1] * vn - P.area[1] * cv);
             div_u = div_u + (P.area[2] * cw - P.area[2] * wb);
             div_u *= inv_vol;
-            const double c = item.c, d = item.d;
-            double gC, gS;
-            if (NSUB == 2) { gC = sub ? other : ck; gS = sub ? ck : other; }
-            else { gC = ck; gS = 0.0; }
             double src;
-            if (item.is_map) src = item.src == 0 ? (cu + ue) / 2.0 : (item.src == 1 ? (cv + vn) / 2.0 : (wb + cw) / 2.0);
+            if (map_axis >= 0) src = map_axis == 0 ? 0.5 * (cu + ue) : (map_axis == 1 ? 0.5 * (cv + vn) : 0.5 * (wb + cw));
             else src = need_var ? lds(aIn + boff + 4 * IN_F) : 0.0;
-            const double n2 = c * c + d * d;
-            double forcing;
-            if (NSUB == 1)      forcing = item.is_map ? (-c / n2 * src) + (-c * gC) : (-c * gC) + src;
-            else if (sub == 0)  forcing = item.is_map ? (-c / n2 * src) + (-c * gC - d * gS) : (-c * gC - d * gS) + src;
-            else                forcing = item.is_map ? (-d / n2 * src) + (-c * gS + d * gC) : (-c * gS + d * gC);
-            const double Gn = (-div_flux + ck * div_u) + forcing;
+            const double forcing = fma(k_src, src, fma(k_own, ck, k_oth * other));
+            const double Gn = fma(ck, div_u, -div_flux) + forcing;
             double unew;
-            if (P.first_stage) unew = ck + P.dt * P.gamma * Gn;
-            else               unew = ck + P.dt * (P.gamma * Gn + P.zeta * lds(aIn + boff + 3 * IN_F));
+            if (P.first_stage) unew = fma(dtg, Gn, ck);
+            else               unew = fma(dtg, Gn, fma(dtz, lds(aIn + boff + 3 * IN_F), ck));
             if (active) {
                 pUn[0] = unew;
                 if (P.store_G) pG[0] = Gn;
