@@ -100,7 +100,10 @@ struct lfb_handle {
     int64_t    stage_launches;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;   // pending stage timings
     int        use_zmarch;
+    int        halos_valid;                // halos of U[cur] are up to date (kept so by the stage kernels)
     // distributed y-slabs
+    cudaStream_t comm_stream;
+    cudaEvent_t  ev_strips, ev_halo;
     ncclComm_t comm;
     int        rank, nranks;
     double    *send_lo, *send_hi, *recv_lo, *recv_hi;
@@ -138,6 +141,8 @@ static void build_layout(lfb_handle *h)
         L.NG[ax] = d.size[ax];
         L.goff[ax] = 0;
         L.connected_lo[ax] = L.connected_hi[ax] = 0;
+        // periodic images are written by the stage kernels when every cell has at most one image per axis
+        L.fuse_halo[ax] = d.topology[ax] == LFB_PERIODIC && d.halo[ax] > 0 && d.size[ax] >= 2 * d.halo[ax];
     }
     L.xoff = L.H[0] > 0 ? LFB_XPAD : 0;
     int need = L.xoff + L.N[0] + L.H[0] + 1;
@@ -231,7 +236,7 @@ extern "C" int lfb_create(const lfb_desc *desc, lfb_handle **out)
     const size_t fbytes = (size_t)L.len * sizeof(double);
     h->U[0] = h->U[1] = h->G = h->scratch = h->mask = nullptr;
     h->staging = nullptr;
-    h->comm = nullptr; h->rank = 0; h->nranks = 1;
+    h->comm = nullptr; h->rank = 0; h->nranks = 1; h->comm_stream = nullptr; h->halos_valid = 0;
     h->send_lo = h->send_hi = h->recv_lo = h->recv_hi = nullptr;
     const int nt = h->n_tracers > 0 ? h->n_tracers : 1;
     CU(cudaMalloc(&h->U[0], fbytes * nt));
@@ -286,6 +291,7 @@ extern "C" int lfb_destroy(lfb_handle *h)
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->comm) ncclCommDestroy(h->comm);
+    if (h->comm_stream) { cudaStreamDestroy(h->comm_stream); cudaEventDestroy(h->ev_strips); cudaEventDestroy(h->ev_halo); }
     for (double *p : h->slot_field) if (p) cudaFree(p);
     for (cudaEvent_t e : h->slot_ready) cudaEventDestroy(e);
     for (cudaEvent_t e : h->slot_used) cudaEventDestroy(e);
@@ -431,12 +437,15 @@ extern "C" int lfb_set_mask(lfb_handle *h, const double *parent)
 
 // ---- halo handling -------------------------------------------------------------------------------
 // Periodic halos of the current tracer buffer (what the stencils read).  Bounded-axis halos are never
-// read by the stencils and are only produced for exported arrays.
-static int fill_periodic_halos(lfb_handle *h, double *base, int n_fields)
+// read by the stencils and are only produced for exported arrays.  Axes whose images
+// the stage kernels write themselves (LfbLayout::fuse_halo) only need this after the state was set from
+// outside (force = 1).
+static int fill_periodic_halos(lfb_handle *h, double *base, int n_fields, int force)
 {
     for (int ax = 0; ax < 3; ++ax) {
         if (h->L.topo[ax] != LFB_PERIODIC) continue;
         if (ax == 1 && h->nranks > 1) continue;     // exchanged with the neighbour ranks instead
+        if (h->L.fuse_halo[ax] && !force) continue;
         CU(lfb_launch_fill_halo_axis(base, h->L.len, n_fields, &h->L, ax, 0, h->compute));
         h->launches++;
     }
@@ -456,30 +465,39 @@ static int fill_all_halos(lfb_handle *h, double *base, int n_fields)
 
 // y-halo exchange between neighbouring slabs: pack the H edge rows of every tracer, ncclSend/Recv
 // them to ranks r-1 / r+1 (periodic wrap when the global y axis is Periodic), unpack into the halos.
-static int exchange_y(lfb_handle *h, double *base, int n_fields)
+static int exchange_y(lfb_handle *h, double *base, int n_fields, cudaStream_t st = nullptr)
 {
+    if (!st) st = h->compute;
     if (h->nranks <= 1 || h->L.H[1] == 0) return LFB_OK;
     const bool periodic = h->L.topo[1] == LFB_PERIODIC;
     const int lo = h->rank > 0 ? h->rank - 1 : (periodic ? h->nranks - 1 : -1);
     const int hi = h->rank < h->nranks - 1 ? h->rank + 1 : (periodic ? 0 : -1);
     const size_t per_field = (size_t)(h->L.N[0] + 2 * h->L.H[0]) * h->L.H[1] * (h->L.N[2] + 2 * h->L.H[2]);
     const size_t count = per_field * n_fields;
-    if (lo >= 0) { CU(lfb_launch_pack_y(h->send_lo, base, h->L.len, n_fields, &h->L, 0, 0, h->compute)); h->launches++; }
-    if (hi >= 0) { CU(lfb_launch_pack_y(h->send_hi, base, h->L.len, n_fields, &h->L, 1, 0, h->compute)); h->launches++; }
+    if (lo >= 0) { CU(lfb_launch_pack_y(h->send_lo, base, h->L.len, n_fields, &h->L, 0, 0, st)); h->launches++; }
+    if (hi >= 0) { CU(lfb_launch_pack_y(h->send_hi, base, h->L.len, n_fields, &h->L, 1, 0, st)); h->launches++; }
+    // sends first (low edge, high edge), then receives (high halo, low halo): with two ranks on a periodic
+    // axis both neighbours are the same peer and NCCL matches operations per peer in program order
     NC(ncclGroupStart());
-    if (lo >= 0) { NC(ncclSend(h->send_lo, count, ncclDouble, lo, h->comm, h->compute)); NC(ncclRecv(h->recv_lo, count, ncclDouble, lo, h->comm, h->compute)); }
-    if (hi >= 0) { NC(ncclSend(h->send_hi, count, ncclDouble, hi, h->comm, h->compute)); NC(ncclRecv(h->recv_hi, count, ncclDouble, hi, h->comm, h->compute)); }
+    if (lo >= 0) NC(ncclSend(h->send_lo, count, ncclDouble, lo, h->comm, st));
+    if (hi >= 0) NC(ncclSend(h->send_hi, count, ncclDouble, hi, h->comm, st));
+    if (hi >= 0) NC(ncclRecv(h->recv_hi, count, ncclDouble, hi, h->comm, st));
+    if (lo >= 0) NC(ncclRecv(h->recv_lo, count, ncclDouble, lo, h->comm, st));
     NC(ncclGroupEnd());
-    if (lo >= 0) { CU(lfb_launch_pack_y(h->recv_lo, base, h->L.len, n_fields, &h->L, 0, 1, h->compute)); h->launches++; }
-    if (hi >= 0) { CU(lfb_launch_pack_y(h->recv_hi, base, h->L.len, n_fields, &h->L, 1, 1, h->compute)); h->launches++; }
+    if (lo >= 0) { CU(lfb_launch_pack_y(h->recv_lo, base, h->L.len, n_fields, &h->L, 0, 1, st)); h->launches++; }
+    if (hi >= 0) { CU(lfb_launch_pack_y(h->recv_hi, base, h->L.len, n_fields, &h->L, 1, 1, st)); h->launches++; }
     return LFB_OK;
 }
 
+// Make the halos of U[cur] valid before a stage reads them.
 static int refresh_halos(lfb_handle *h, double *base, int n_fields)
 {
-    int rc = fill_periodic_halos(h, base, n_fields);
+    const int force = !h->halos_valid;
+    int rc = fill_periodic_halos(h, base, n_fields, force);
     if (rc) return rc;
-    return exchange_y(h, base, n_fields);
+    if (h->nranks > 1 && force) { rc = exchange_y(h, base, n_fields); if (rc) return rc; }
+    h->halos_valid = 1;
+    return LFB_OK;
 }
 
 // ---- state ---------------------------------------------------------------------------------------
@@ -528,6 +546,7 @@ extern "C" int lfb_init_from_data(lfb_handle *h)
         }
     }
     h->cur = 0; h->time = 0; h->iteration = 0;
+    h->halos_valid = 0;
     return LFB_OK;
 }
 
@@ -597,6 +616,7 @@ extern "C" int lfb_set_tracer(lfb_handle *h, int tracer, const double *parent)
         h->launches++;
     }
     CU(cudaStreamSynchronize(h->compute));
+    h->halos_valid = 0;
     return LFB_OK;
 }
 
@@ -653,11 +673,39 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, h->compute));
-    if (h->use_zmarch && update) CU(lfb_launch_stage_zmarch(&P, h->compute));
-    else                         CU(lfb_launch_stage_generic(&P, h->desc.strict, h->compute));
+    const int Ny = h->L.N[1];
+    const int strip = h->use_zmarch ? 6 : h->L.H[1];      // rows per edge strip: one z-march tile row / the halo width
+    const bool overlap = update && h->nranks > 1 && Ny >= 4 * strip;
+    auto launch = [&](int j0, int j1) -> int {
+        P.j0 = j0; P.j1 = j1;
+        if (h->use_zmarch && update) CU(lfb_launch_stage_zmarch(&P, h->compute));
+        else                         CU(lfb_launch_stage_generic(&P, h->desc.strict, h->compute));
+        h->launches++;
+        return LFB_OK;
+    };
+    if (!overlap) {
+        rc = launch(0, Ny);
+        if (rc) return rc;
+        if (update && h->nranks > 1) { rc = exchange_y(h, P.U_new, h->n_tracers); if (rc) return rc; }
+    } else {
+        // slab decomposition: edge strips first, then their halo exchange on the communication stream
+        // while the interior is computed (stands in for Oceananigans' async halo fill +
+        // compute_buffer_tendencies!, compute_lagrangian_filter_buffer_tendencies.jl:8-38)
+        rc = launch(0, strip);
+        if (rc) return rc;
+        rc = launch(Ny - strip, Ny);
+        if (rc) return rc;
+        CU(cudaEventRecord(h->ev_strips, h->compute));
+        CU(cudaStreamWaitEvent(h->comm_stream, h->ev_strips, 0));
+        rc = exchange_y(h, P.U_new, h->n_tracers, h->comm_stream);
+        if (rc) return rc;
+        CU(cudaEventRecord(h->ev_halo, h->comm_stream));
+        rc = launch(strip, Ny - strip);
+        if (rc) return rc;
+        CU(cudaStreamWaitEvent(h->compute, h->ev_halo, 0));   // the next stage reads the received halo rows
+    }
     CU(cudaEventRecord(e1, h->compute));
     h->timing.push_back({e0, e1});
-    h->launches++;
     CU(cudaEventRecord(h->slot_used[s1], h->compute));
     if (s2 != s1) CU(cudaEventRecord(h->slot_used[s2], h->compute));
     return LFB_OK;
@@ -699,7 +747,7 @@ extern "C" int lfb_step(lfb_handle *h, double dt)
         if (rc) return rc;
         rc = launch_stage(h, taus[s], dt, gam[s], zet[s], s == 0, s < 2, 1);
         if (rc) return rc;
-        h->cur ^= 1;
+        h->cur ^= 1;          // the stage kernels (and the slab exchange) leave the halos of the new state valid
     }
     h->time = t1;
     h->iteration += 1;
@@ -840,6 +888,18 @@ extern "C" int lfb_comm_init(lfb_handle *h, const void *id128, int rank, int nra
     h->L.goff[1] = h->L.N[1] * rank;
     h->L.connected_lo[1] = rank > 0 || h->L.topo[1] == LFB_PERIODIC;
     h->L.connected_hi[1] = rank < nranks - 1 || h->L.topo[1] == LFB_PERIODIC;
+    if (nranks > 1) {
+        h->L.fuse_halo[1] = 0;                        // y halos come from the neighbour ranks
+        for (int ax = 0; ax < 3; ax += 2)
+            if (h->L.topo[ax] == LFB_PERIODIC && !h->L.fuse_halo[ax])
+                return fail(LFB_ERR_ARG, "slab decomposition needs periodic axes at least twice as long as their halo");
+        int lo_prio = 0, hi_prio = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        CU(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, hi_prio));
+        CU(cudaEventCreateWithFlags(&h->ev_strips, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+    }
+    h->halos_valid = 0;
     const size_t per_field = (size_t)(h->L.N[0] + 2 * h->L.H[0]) * h->L.H[1] * (h->L.N[2] + 2 * h->L.H[2]);
     h->halo_elems = per_field * (h->n_tracers > 0 ? h->n_tracers : 1);
     CU(cudaMalloc(&h->send_lo, h->halo_elems * sizeof(double)));

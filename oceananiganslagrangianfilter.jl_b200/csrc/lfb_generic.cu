@@ -46,6 +46,18 @@ __global__ void __launch_bounds__(128) lfb_stage_generic(const __grid_constant__
     }
     div_u = div_u / T(P.volume);
 
+    // periodic images of this cell in the halo: per axis an offset (0 = none); all 2^n - 1 combinations are written
+    int64_t wrap[3] = {0, 0, 0};
+    int wrap_mask = 0;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        if (!L.fuse_halo[ax]) continue;
+        if (ijk[ax] < L.H[ax]) wrap[ax] = (int64_t)L.N[ax] * L.stride[ax];
+        else if (ijk[ax] >= L.N[ax] - L.H[ax]) wrap[ax] = -(int64_t)L.N[ax] * L.stride[ax];
+        if (wrap[ax]) wrap_mask |= 1 << ax;
+    }
+    const bool nwrap = wrap_mask != 0;
+
     const int n_sub = P.single_exp ? 1 : 2;
     for (int it = 0; it < P.n_items; ++it) {
         const LfbItem item = P.items[it];
@@ -102,6 +114,18 @@ __global__ void __launch_bounds__(128) lfb_stage_generic(const __grid_constant__
                 if (P.first_stage) unew = cval + T(P.dt) * T(P.gamma) * Gn;
                 else               unew = cval + T(P.dt) * (T(P.gamma) * Gn + T(P.zeta) * T(P.G[tix]));
                 P.U_new[tix] = val(unew);
+                // periodic halo images of the new state (tracer halo fill of update_state!, fused)
+                if (nwrap) {
+                    double *base = P.U_new + tix;
+                    for (int w = 1; w < 8; ++w) {
+                        if ((w & wrap_mask) != w) continue;
+                        int64_t o = 0;
+                        if (w & 1) o += wrap[0];
+                        if (w & 2) o += wrap[1];
+                        if (w & 4) o += wrap[2];
+                        base[o] = val(unew);
+                    }
+                }
             }
             if (P.store_G) P.G[tix] = val(Gn);
         }

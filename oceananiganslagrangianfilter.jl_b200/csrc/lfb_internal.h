@@ -30,6 +30,7 @@ struct LfbLayout {
     int     NG[3];       // global interior cells
     int     goff[3];     // global index of local cell 0
     int     connected_lo[3], connected_hi[3];   // halo on that side is owned by a neighbour rank
+    int     fuse_halo[3];                       // stage kernels write the periodic halo images of this axis themselves
 
     __host__ __device__ inline int64_t at(int i, int j, int k) const {
         return (int64_t)(xoff + i) + (int64_t)pitch * ((int64_t)(H[1] + j) + (int64_t)rows * (int64_t)(H[2] + k));

@@ -235,6 +235,16 @@ __global__ void __launch_bounds__(ZmSmem<NSUB, TY>::THREADS, 1) lfb_stage_zmarch
     const bool need_var = !item.is_map && sub == 0;
     const double *__restrict__ pf = need_var ? P.var[item.src] + off0 : nullptr;
     const bool use_G = !P.first_stage;
+    // offsets of this column's periodic images in the halo (0 = none); y only when the y halo is not owned by a
+    // neighbour rank
+    int64_t xwrap = 0, ywrap = 0;
+    {
+        const int i = i0 + tx, j = j0 + ty;
+        if (L.fuse_halo[0]) { if (i < L.H[0]) xwrap = L.N[0]; else if (i >= L.N[0] - L.H[0]) xwrap = -L.N[0]; }
+        if (L.fuse_halo[1]) {
+            if (j < L.H[1]) ywrap = (int64_t)L.N[1] * L.pitch; else if (j >= L.N[1] - L.H[1]) ywrap = -(int64_t)L.N[1] * L.pitch;
+        }
+    }
     // forcing = k_src * src + (k_own * own + k_oth * partner)   (create_forcing, utils:731-865)
     double k_src, k_own, k_oth;
     {
@@ -300,6 +310,9 @@ __global__ void __launch_bounds__(ZmSmem<NSUB, TY>::THREADS, 1) lfb_stage_zmarch
     }
     block_barrier();
 
+#ifdef ZM_UNROLL
+#pragma unroll ZM_UNROLL
+#endif
     for (int k = 0; k < Nz; ++k) {
         const unsigned boff = (k & 1) * BUF_B, noff = BUF_B - boff;
         // ---- plane k+1 -> the other buffer: own value, halo and per-thread inputs, all asynchronous ----
@@ -370,6 +383,9 @@ __global__ void __launch_bounds__(ZmSmem<NSUB, TY>::THREADS, 1) lfb_stage_zmarch
             else               unew = fma(dtg, Gn, fma(dtz, lds(aIn + boff + 3 * IN_F), ck));
             if (active) {
                 pUn[0] = unew;
+                // periodic halo images of the new state (the tracer halo fill of update_state!, fused)
+                if (xwrap) pUn[xwrap] = unew;
+                if (ywrap) { pUn[ywrap] = unew; if (xwrap) pUn[xwrap + ywrap] = unew; }
                 if (P.store_G) pG[0] = Gn;
             }
             // advance the window to cell k+1

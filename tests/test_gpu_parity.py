@@ -294,3 +294,19 @@ def test_zmarch_matches_generic_on_larger_grid():
         m.close()
     for a, b in zip(res["generic"], res["zmarch"]):
         assert rel_l2(b, a) < TOL_STEP
+
+
+def test_multi_gpu_slabs_match_single_gpu():
+    """y-slab decomposition with NCCL halo exchange (tests/mgpu_check.py under torchrun) when the box has >= 2 GPUs."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", "29517", "tests/mgpu_check.py"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MISMATCH" not in r.stdout
