@@ -197,7 +197,7 @@ def main():
     host = {}
     for s, t in enumerate(times):
         snap = make_snapshot(g, t, 4 * T_S, var_names=VAR_NAMES, velocity_names=VEL_NAMES, xp=torch,
-                             device=torch.device("cuda", local), dtype=np.float32)
+                             device=torch.device("cuda", local), dtype=np.float32, global_grid=gglobal)
         for name in names:
             pinned = torch.empty(snap[name].shape, dtype=torch.float32, pin_memory=True)
             pinned.copy_(snap[name])

@@ -102,8 +102,11 @@ class RectilinearGrid:
         return tuple(self.N[ax] + 2 * self.H[ax] for ax in range(3))
 
     def face_shape(self, axis: int):
+        """Parent shape of a field on the faces of `axis`: one extra entry on a Bounded axis (on a y-slab only
+        the last rank holds the wall face)."""
         s = list(self.center_shape())
-        if self.topology[axis] == Bounded:
+        rank, nranks = getattr(self, "_slab", (0, 1))
+        if self.topology[axis] == Bounded and not (axis == 1 and rank != nranks - 1):
             s[axis] += 1
         return tuple(s)
 
@@ -129,4 +132,5 @@ class RectilinearGrid:
         o = list(self.origin)
         o[1] = self.origin[1] + dy * ny * rank
         object.__setattr__(g, "origin", tuple(o))
+        object.__setattr__(g, "_slab", (rank, nranks))
         return g

@@ -27,13 +27,14 @@ def _coords(grid: RectilinearGrid, axis: int, face: bool) -> np.ndarray:
 
 def make_snapshot(grid: RectilinearGrid, t: float, T_period: float, var_names: Sequence[str] = ("T", "b"),
                   velocity_names: Sequence[str] = ("u", "v", "w"), amplitude: float = 1.0, xp=np, device=None,
-                  dtype=np.float32) -> Dict[str, "np.ndarray"]:
+                  dtype=np.float32, global_grid: RectilinearGrid = None) -> Dict[str, "np.ndarray"]:
     """All fields of one snapshot at time t.  With xp=torch the arrays are torch tensors on `device`
     of shape (ez, ey, ex) (C order), i.e. the same memory as a Fortran (ex, ey, ez) parent array."""
     is_torch = xp is not np
     two_pi = 2 * math.pi
-    Lx, Ly, Lz = grid.Lx, grid.Ly, grid.Lz
-    ox, oy, oz = grid.origin
+    ref = global_grid or grid           # a y-slab evaluates the GLOBAL analytic fields on its own rows
+    Lx, Ly, Lz = ref.Lx, ref.Ly, ref.Lz
+    ox, oy, oz = ref.origin
     ph = two_pi * t / T_period
 
     def ax(axis, face):

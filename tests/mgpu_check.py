@@ -23,6 +23,11 @@ from lfb200.model import LagrangianFilter
 from lfb200.synthetic import make_series
 
 
+def log(*a):
+    if os.environ.get("MGPU_VERBOSE"):
+        print(f"[rank {os.environ.get('RANK')}]", *a, file=sys.stderr, flush=True)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -39,16 +44,17 @@ def main():
         gl = g.slab(rank, world)
         ms = LagrangianFilter(gl, var_names_to_filter=var_names, velocity_names=vel_names, filter_params=fp, n_slots=3,
                               device=local, strict=strict, kernel=kernel)
-        init_model_comm(ms, rank, world)
+        log('created slab model'); init_model_comm(ms, rank, world); log('comm ready')
         mg = LagrangianFilter(g, var_names_to_filter=var_names, velocity_names=vel_names, filter_params=fp, n_slots=3,
                               device=local, strict=strict, kernel=kernel)
         for s, t in enumerate(times):
             for name in vel_names + var_names:
                 mg.upload_snapshot(s, name, fields[name][s], t)
                 ms.upload_snapshot(s, name, slab_of_parent(fields[name][s], g, rank, world, name if name in vel_names else "c"), t)
-        ms.init_from_data(); mg.init_from_data()
+        log('uploaded'); ms.init_from_data(); log('slab init done'); mg.init_from_data()
         for dt in (0.1, 0.1, 0.05, 0.25, 0.2, 0.3):
             ms.step(dt); mg.step(dt)
+        ms.sync(); log('stepped')
         worst = 0.0
         for name in ms.tracer_names:
             got = ms.tracer(name)
