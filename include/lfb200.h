@@ -120,6 +120,10 @@ int64_t lfb_parent_len(const lfb_handle *h, int field_id);
  * The copy runs on a side stream and overlaps with queued stage kernels that do not read `slot`. */
 int lfb_upload_snapshot(lfb_handle *h, int slot, int field_id, const double *parent, double time);
 int lfb_upload_snapshot_f32(lfb_handle *h, int slot, int field_id, const float *parent, double time);
+/* Asynchronous variant: returns as soon as the copy is queued.  `parent` must stay valid until
+ * lfb_wait_transfers(); the copy overlaps with queued stage kernels only if `parent` is page-locked
+ * (lfb_host_alloc or cudaHostRegister). */
+int lfb_upload_snapshot_async(lfb_handle *h, int slot, int field_id, const void *parent, int is_f32, double time);
 int lfb_invalidate_slot(lfb_handle *h, int slot);
 /* Re-tag a resident slot with a new pass time without touching its data. */
 int lfb_set_slot_time(lfb_handle *h, int slot, double time);
@@ -157,6 +161,15 @@ int lfb_run_until(lfb_handle *h, double t_stop, double dt, int n_align, const do
 /* ---- outputs (create_output_fields utils:898-1012; written with halos like JLD2Writer) ------- */
 int lfb_output(lfb_handle *h, int kind, int field, double *parent);
 int lfb_output_f32(lfb_handle *h, int kind, int field, float *parent);
+/* Asynchronous output: the combination is queued behind the steps issued so far, exported into a ring of
+ * device buffers and copied to `parent` on a separate stream, so the host can keep queuing time steps.
+ * `parent` (FP64, or FP32 when is_f32 != 0) may be read after lfb_wait_transfers(). */
+int lfb_output_async(lfb_handle *h, int kind, int field, void *parent, int is_f32);
+/* wait for every asynchronous upload and output issued so far */
+int lfb_wait_transfers(lfb_handle *h);
+/* page-locked host memory for the asynchronous transfers */
+int lfb_host_alloc(size_t bytes, void **ptr);
+int lfb_host_free(void *ptr);
 /* sum_forward_backward_contributions!, post:45-170, for one output time on host arrays:
  * out = fwd + sign * (w_hi*bwd_hi + (1-w_hi)*bwd_lo), computed on the device in FP64.
  * sign = +1 for filtered vars and xi, -1 for mean velocities (post:151-164). */

@@ -25,10 +25,11 @@ ERR_NAMES = {-1: "LFB_ERR_ARG", -2: "LFB_ERR_CUDA", -3: "LFB_ERR_STATE", -4: "LF
 # every symbol include/lfb200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "lfb_version", "lfb_last_error", "lfb_create", "lfb_destroy", "lfb_sync", "lfb_n_tracers", "lfb_tracer_index",
-    "lfb_parent_len", "lfb_upload_snapshot", "lfb_upload_snapshot_f32", "lfb_invalidate_slot", "lfb_set_slot_time",
+    "lfb_parent_len", "lfb_upload_snapshot", "lfb_upload_snapshot_f32", "lfb_upload_snapshot_async", "lfb_invalidate_slot", "lfb_set_slot_time",
     "lfb_set_direction", "lfb_set_mask", "lfb_init_from_data", "lfb_negate_maps", "lfb_reset_clock", "lfb_time",
     "lfb_iteration", "lfb_get_tracer", "lfb_set_tracer", "lfb_get_tendency", "lfb_step", "lfb_run_until",
-    "lfb_output", "lfb_output_f32", "lfb_combine", "lfb_comm_unique_id", "lfb_comm_init", "lfb_kernel_launches",
+    "lfb_output", "lfb_output_f32", "lfb_output_async", "lfb_wait_transfers", "lfb_host_alloc", "lfb_host_free",
+    "lfb_combine", "lfb_comm_unique_id", "lfb_comm_init", "lfb_kernel_launches",
     "lfb_stage_time_ms", "lfb_timer_start", "lfb_timer_stop", "lfb_kernel_name", "lfb_device_ptr", "lfb_layout",
 ]
 
@@ -68,6 +69,9 @@ def load():
         "lfb_create": (i32, [C.POINTER(Desc), C.POINTER(vp)]), "lfb_destroy": (i32, [vp]), "lfb_sync": (i32, [vp]),
         "lfb_n_tracers": (i32, [vp]), "lfb_tracer_index": (i32, [vp, i32, i32, i32]), "lfb_parent_len": (i64, [vp, i32]),
         "lfb_upload_snapshot": (i32, [vp, i32, i32, vp, f64]), "lfb_upload_snapshot_f32": (i32, [vp, i32, i32, vp, f64]),
+        "lfb_upload_snapshot_async": (i32, [vp, i32, i32, vp, i32, f64]),
+        "lfb_output_async": (i32, [vp, i32, i32, vp, i32]), "lfb_wait_transfers": (i32, [vp]),
+        "lfb_host_alloc": (i32, [C.c_size_t, C.POINTER(vp)]), "lfb_host_free": (i32, [vp]),
         "lfb_invalidate_slot": (i32, [vp, i32]), "lfb_set_slot_time": (i32, [vp, i32, f64]),
         "lfb_set_direction": (i32, [vp, i32]), "lfb_set_mask": (i32, [vp, vp]),
         "lfb_init_from_data": (i32, [vp]), "lfb_negate_maps": (i32, [vp]), "lfb_reset_clock": (i32, [vp]),

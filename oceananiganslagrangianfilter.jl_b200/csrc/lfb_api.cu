@@ -92,7 +92,11 @@ struct lfb_handle {
     double     time;
     int64_t    iteration;
     int        direction;
-    cudaStream_t compute, copy;
+    cudaStream_t compute, copy, d2h;
+    std::vector<void *> export_ring;       // dense parent arrays for asynchronous outputs
+    std::vector<cudaEvent_t> ev_export, ev_fetched;
+    std::vector<int> ring_used;
+    int        export_next;
     cudaEvent_t  ev_tmp, ev_t0, ev_t1;
     // statistics
     int64_t    launches;
@@ -272,6 +276,8 @@ extern "C" int lfb_create(const lfb_desc *desc, lfb_handle **out)
     }
     CU(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->d2h, cudaStreamNonBlocking));
+    h->export_next = 0;
     CU(cudaEventCreateWithFlags(&h->ev_tmp, cudaEventDisableTiming));
     CU(cudaEventCreate(&h->ev_t0));
     CU(cudaEventCreate(&h->ev_t1));
@@ -301,7 +307,10 @@ extern "C" int lfb_destroy(lfb_handle *h)
     for (int f = 0; f < N_FIELD_IDS; ++f) if (h->cur_in[f]) cudaFree(h->cur_in[f]);
     cudaFree(h->staging);
     if (h->send_lo) { cudaFree(h->send_lo); cudaFree(h->send_hi); cudaFree(h->recv_lo); cudaFree(h->recv_hi); }
-    cudaStreamDestroy(h->compute); cudaStreamDestroy(h->copy);
+    for (void *p : h->export_ring) cudaFree(p);
+    for (cudaEvent_t e : h->ev_export) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_fetched) cudaEventDestroy(e);
+    cudaStreamDestroy(h->compute); cudaStreamDestroy(h->copy); cudaStreamDestroy(h->d2h);
     cudaEventDestroy(h->ev_tmp); cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1);
     delete h;
     return LFB_OK;
@@ -313,6 +322,29 @@ extern "C" int lfb_sync(lfb_handle *h)
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->copy));
     CU(cudaStreamSynchronize(h->compute));
+    CU(cudaStreamSynchronize(h->d2h));
+    return LFB_OK;
+}
+
+extern "C" int lfb_wait_transfers(lfb_handle *h)
+{
+    if (!h) return fail(LFB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->copy));
+    CU(cudaStreamSynchronize(h->d2h));
+    return LFB_OK;
+}
+
+extern "C" int lfb_host_alloc(size_t bytes, void **ptr)
+{
+    if (!ptr || bytes == 0) return fail(LFB_ERR_ARG, "bad argument");
+    CU(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return LFB_OK;
+}
+
+extern "C" int lfb_host_free(void *ptr)
+{
+    if (ptr) CU(cudaFreeHost(ptr));
     return LFB_OK;
 }
 
@@ -334,7 +366,7 @@ extern "C" int64_t lfb_parent_len(const lfb_handle *h, int field_id)
 }
 
 // ---- input series --------------------------------------------------------------------------------
-static int upload_impl(lfb_handle *h, int slot, int field_id, const void *parent, int is_f32, double time)
+static int upload_impl(lfb_handle *h, int slot, int field_id, const void *parent, int is_f32, double time, int wait = 1)
 {
     if (!h || !parent) return fail(LFB_ERR_ARG, "null argument");
     if (slot < 0 || slot >= h->desc.n_slots) return fail(LFB_ERR_ARG, "slot %d out of range", slot);
@@ -357,7 +389,7 @@ static int upload_impl(lfb_handle *h, int slot, int field_id, const void *parent
     h->slot_time[slot] = time;
     h->slot_valid[slot] |= 1u << field_id;
     // the host buffer is only borrowed: wait for the H2D copy (not for the import kernel)
-    CU(cudaEventSynchronize(h->ev_tmp));
+    if (wait) CU(cudaEventSynchronize(h->ev_tmp));
     return LFB_OK;
 }
 
@@ -369,6 +401,11 @@ extern "C" int lfb_upload_snapshot(lfb_handle *h, int slot, int field_id, const 
 extern "C" int lfb_upload_snapshot_f32(lfb_handle *h, int slot, int field_id, const float *parent, double time)
 {
     return upload_impl(h, slot, field_id, parent, 1, time);
+}
+
+extern "C" int lfb_upload_snapshot_async(lfb_handle *h, int slot, int field_id, const void *parent, int is_f32, double time)
+{
+    return upload_impl(h, slot, field_id, parent, is_f32 != 0, time, 0);
 }
 
 extern "C" int lfb_invalidate_slot(lfb_handle *h, int slot)
@@ -795,10 +832,9 @@ extern "C" int lfb_get_tendency(lfb_handle *h, int tracer, double *parent)
 }
 
 // ---- outputs -------------------------------------------------------------------------------------
-static int output_impl(lfb_handle *h, int kind, int field, void *parent, int is_f32)
+// queue the output combination into h->scratch (interior, then the halo pattern of an Oceananigans computed Field)
+static int output_compute(lfb_handle *h, int kind, int field)
 {
-    if (!h || !parent) return fail(LFB_ERR_ARG, "null argument");
-    CU(cudaSetDevice(h->device));
     int fld;
     if (kind == LFB_OUT_FILTERED_VAR) {
         if (field < 0 || field >= h->desc.n_vars) return fail(LFB_ERR_ARG, "variable %d out of range", field);
@@ -826,9 +862,47 @@ static int output_impl(lfb_handle *h, int kind, int field, void *parent, int is_
     h->launches++;
     int rc = fill_all_halos(h, h->scratch, 1);
     if (rc) return rc;
-    rc = exchange_y(h, h->scratch, 1);
+    return exchange_y(h, h->scratch, 1);
+}
+
+static int output_impl(lfb_handle *h, int kind, int field, void *parent, int is_f32)
+{
+    if (!h || !parent) return fail(LFB_ERR_ARG, "null argument");
+    CU(cudaSetDevice(h->device));
+    int rc = output_compute(h, kind, field);
     if (rc) return rc;
     return download(h, h->scratch, parent, is_f32, -1);
+}
+
+extern "C" int lfb_output_async(lfb_handle *h, int kind, int field, void *parent, int is_f32)
+{
+    if (!h || !parent) return fail(LFB_ERR_ARG, "null argument");
+    CU(cudaSetDevice(h->device));
+    const int R = 4;
+    if (h->export_ring.empty()) {
+        h->export_ring.assign(R, nullptr);
+        h->ev_export.resize(R); h->ev_fetched.resize(R); h->ring_used.assign(R, 0);
+        for (int r = 0; r < R; ++r) {
+            CU(cudaMalloc(&h->export_ring[r], h->staging_bytes));
+            CU(cudaEventCreateWithFlags(&h->ev_export[r], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->ev_fetched[r], cudaEventDisableTiming));
+        }
+    }
+    const int r = h->export_next++ % R;
+    if (h->ring_used[r]) CU(cudaStreamWaitEvent(h->compute, h->ev_fetched[r], 0));   // previous copy out of this buffer
+    int rc = output_compute(h, kind, field);
+    if (rc) return rc;
+    int e[3];
+    parent_extents(h, -1, e);
+    const size_t n = (size_t)e[0] * e[1] * e[2];
+    CU(lfb_launch_export(h->export_ring[r], is_f32 != 0, h->scratch, &h->L, e[0], e[1], e[2], h->compute));
+    h->launches++;
+    CU(cudaEventRecord(h->ev_export[r], h->compute));
+    CU(cudaStreamWaitEvent(h->d2h, h->ev_export[r], 0));
+    CU(cudaMemcpyAsync(parent, h->export_ring[r], n * (is_f32 ? sizeof(float) : sizeof(double)), cudaMemcpyDeviceToHost, h->d2h));
+    CU(cudaEventRecord(h->ev_fetched[r], h->d2h));
+    h->ring_used[r] = 1;
+    return LFB_OK;
 }
 
 extern "C" int lfb_output(lfb_handle *h, int kind, int field, double *parent) { return output_impl(h, kind, field, parent, 0); }

@@ -49,6 +49,7 @@ class LagrangianFilter:
         d.relaxation = int(relax_timescale is not None)
         d.relax_timescale = float(relax_timescale or 0.0)
         self.n_slots = int(n_slots)
+        self._in_flight, self._pinned = [], []
         h = C.c_void_p()
         check(self.L.lfb_create(C.byref(d), C.byref(h)))
         self.h = h
@@ -64,8 +65,16 @@ class LagrangianFilter:
             check(self.L.lfb_set_mask(self.h, m.ctypes.data))
 
     # ------------------------------------------------------------------ lifecycle
+    def free_pinned(self):
+        """Releases every page-locked array handed out by pinned_empty (they must not be used afterwards)."""
+        for p in self._pinned:
+            self.L.lfb_host_free(p)
+        self._pinned = []
+
     def close(self):
         if getattr(self, "h", None):
+            self.L.lfb_wait_transfers(self.h)
+            self.free_pinned()
             self.L.lfb_destroy(self.h)
             self.h = None
 
@@ -93,16 +102,44 @@ class LagrangianFilter:
     def field_shape(self, name: str):
         return self.grid.face_shape("uvw".index(name)) if name in ("u", "v", "w") else self.center_shape
 
-    def upload_snapshot(self, slot: int, name: str, parent: np.ndarray, time: float):
+    def upload_snapshot(self, slot: int, name: str, parent: np.ndarray, time: float, wait: bool = True):
         """One field of one input snapshot (update_input_data! source data, utils:1036-1058).  Float32
-        arrays (the reference's on-disk precision) are sent as Float32 and widened on the device."""
+        arrays (the reference's on-disk precision) are sent as Float32 and widened on the device.
+        With wait=False the call returns once the copy is queued; the array is kept alive until
+        wait_transfers() and the copy overlaps with queued steps if it is page-locked (pinned_empty)."""
         shape = self.field_shape(name)
-        if np.asarray(parent).dtype == np.float32:
-            a = _lib.as_parent(parent, shape, np.float32)
+        f32 = np.asarray(parent).dtype == np.float32
+        a = _lib.as_parent(parent, shape, np.float32 if f32 else np.float64)
+        if not wait:
+            self._in_flight.append(a)
+            check(self.L.lfb_upload_snapshot_async(self.h, slot, self.field_id(name), a.ctypes.data, int(f32), float(time)))
+        elif f32:
             check(self.L.lfb_upload_snapshot_f32(self.h, slot, self.field_id(name), a.ctypes.data, float(time)))
         else:
-            a = _lib.as_parent(parent, shape, np.float64)
             check(self.L.lfb_upload_snapshot(self.h, slot, self.field_id(name), a.ctypes.data, float(time)))
+
+    def pinned_empty(self, shape, dtype=np.float64) -> np.ndarray:
+        """Fortran-ordered array in page-locked host memory (for asynchronous uploads / outputs)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape))
+        ptr = C.c_void_p()
+        check(self.L.lfb_host_alloc(max(1, n * dtype.itemsize), C.byref(ptr)))
+        buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape, order="F")
+        self._pinned.append(ptr)
+        return arr
+
+    def output_async(self, kind: int, field: int, out: np.ndarray):
+        """Queue an output into `out` (Fortran order, parent shape, float32 or float64); valid after wait_transfers()."""
+        if out.shape != self.center_shape or not out.flags.f_contiguous or out.dtype not in (np.float32, np.float64):
+            raise ValueError("output array must be a Fortran-ordered float32/float64 array of the parent shape")
+        self._in_flight.append(out)
+        check(self.L.lfb_output_async(self.h, kind, field, out.ctypes.data, int(out.dtype == np.float32)))
+        return out
+
+    def wait_transfers(self):
+        check(self.L.lfb_wait_transfers(self.h))
+        self._in_flight.clear()
 
     def set_slot_time(self, slot: int, time: float):
         check(self.L.lfb_set_slot_time(self.h, slot, float(time)))

@@ -95,9 +95,11 @@ class SnapshotFeeder:
 
     def _upload(self, pos: int, p: int, slot: int):
         n = self.indices[p]
+        if not self.all_resident:
+            self.model.wait_transfers()          # bound the number of host arrays kept alive for queued copies
         for name in self.names:
             arr = self.source.snapshot(name, n)
-            self.model.upload_snapshot(slot, name, arr, self.pass_times[pos])
+            self.model.upload_snapshot(slot, name, arr, self.pass_times[pos], wait=False)
             self.bytes_uploaded += np.asarray(arr).nbytes
         self.slot_of[pos] = slot
 
@@ -131,15 +133,20 @@ def _collect_outputs(model: LagrangianFilter, config: OfflineFilterConfig, dtype
     ident = "_Eulerian_filtered" if config.advection is None else "_Lagrangian_filtered"
     label = config.label
     out = {}
+
+    def queue(kind, index):
+        # asynchronous: the copy to the (page-locked) result array overlaps with the following time steps
+        return model.output_async(kind, index, model.pinned_empty(model.center_shape, dtype))
+
     for q, v in enumerate(config.var_names_to_filter):
-        out[v + label + ident] = model.output(_lib.OUT_FILTERED_VAR, q, dtype)
+        out[v + label + ident] = queue(_lib.OUT_FILTERED_VAR, q)
     vels = model.velocities_present
     if config.map_to_mean:
         for m, vel in enumerate(vels):
-            out["xi_" + vel + label] = model.output(_lib.OUT_XI, m, dtype)
+            out["xi_" + vel + label] = queue(_lib.OUT_XI, m)
     if config.compute_mean_velocities:
         for m, vel in enumerate(vels):
-            out[vel + label + ident] = model.output(_lib.OUT_MEAN_VEL, m, dtype)
+            out[vel + label + ident] = queue(_lib.OUT_MEAN_VEL, m)
     return out
 
 
@@ -157,6 +164,10 @@ def _run_pass(model, feeder, config, dtype, progress=True):
             tk = round(t / T_out) * T_out
             outputs[tk] = _collect_outputs(model, config, dtype)
             iterations[tk] = n
+    model.wait_transfers()
+    # results leave the page-locked staging arrays, which are released
+    outputs = {t: {k: np.array(v, order="F") for k, v in d.items()} for t, d in outputs.items()}
+    model.free_pinned()
     return outputs, iterations
 
 
