@@ -20,6 +20,7 @@
 extern "C" {
 cudaError_t lfb_launch_stage_generic(const LfbStageParams *P, int strict, cudaStream_t stream);
 cudaError_t lfb_launch_stage_zmarch(const LfbStageParams *P, cudaStream_t stream);
+cudaError_t lfb_launch_stage_zsplit(const LfbStageParams *P, cudaStream_t stream);
 int         lfb_zmarch_supported(const LfbStageParams *P);
 cudaError_t lfb_launch_interp_inputs(const LfbInterpParams *P, cudaStream_t stream);
 cudaError_t lfb_launch_fill_halo_axis(double *base, int64_t field_stride, int n_fields, const LfbLayout *L,
@@ -169,10 +170,11 @@ static int select_kernel(lfb_handle *h)
     for (int ax = 0; ax < 3; ++ax) P.vel_present[ax] = (h->desc.velocity_mask >> ax) & 1;
     P.j0 = 0; P.j1 = h->L.N[1];
     const int ok = lfb_zmarch_supported(&P) && !h->desc.strict;
-    if (h->desc.kernel == LFB_KERNEL_ZMARCH && !ok)
+    if ((h->desc.kernel == LFB_KERNEL_ZMARCH || h->desc.kernel == LFB_KERNEL_ZSPLIT) && !ok)
         return fail(LFB_ERR_ARG, "the z-marching kernel needs a (Periodic|slab, Periodic|slab, Bounded) grid with Nx %% 32 == 0, "
                                  "Ny %% 8 == 0, Nz >= 8, u,v,w all present, WENO advection, no relaxation and strict = 0");
-    h->use_zmarch = (h->desc.kernel != LFB_KERNEL_GENERIC) && ok;
+    h->use_zmarch = (h->desc.kernel != LFB_KERNEL_GENERIC) && ok;       // 0 generic, 1 z-march, 2 role-split z-march
+    if (h->use_zmarch && h->desc.kernel == LFB_KERNEL_ZSPLIT) h->use_zmarch = 2;
     return LFB_OK;
 }
 
@@ -711,11 +713,12 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
     CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, h->compute));
     const int Ny = h->L.N[1];
-    const int strip = h->use_zmarch ? 6 : h->L.H[1];      // rows per edge strip: one z-march tile row / the halo width
+    const int strip = h->use_zmarch == 2 ? 4 : (h->use_zmarch ? 6 : h->L.H[1]);      // rows per edge strip: one z-march tile row / the halo width
     const bool overlap = update && h->nranks > 1 && Ny >= 4 * strip;
     auto launch = [&](int j0, int j1) -> int {
         P.j0 = j0; P.j1 = j1;
-        if (h->use_zmarch && update) CU(lfb_launch_stage_zmarch(&P, h->compute));
+        if (h->use_zmarch == 2 && update) CU(lfb_launch_stage_zsplit(&P, h->compute));
+        else if (h->use_zmarch && update) CU(lfb_launch_stage_zmarch(&P, h->compute));
         else                         CU(lfb_launch_stage_generic(&P, h->desc.strict, h->compute));
         h->launches++;
         return LFB_OK;
@@ -1021,6 +1024,7 @@ extern "C" int lfb_timer_stop(lfb_handle *h, double *ms)
 extern "C" const char *lfb_kernel_name(const lfb_handle *h)
 {
     if (!h) return "";
+    if (h->use_zmarch == 2) return "zsplit";
     if (h->use_zmarch) return "zmarch";
     return h->desc.strict ? "generic-strict" : "generic";
 }

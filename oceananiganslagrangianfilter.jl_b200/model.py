@@ -17,7 +17,8 @@ from ._lib import check
 from .filter_utils import FilterParams, create_filtered_vars, tracer_layout
 from .grids import RectilinearGrid
 
-_KERNELS = {"auto": _lib.KERNEL_AUTO, "generic": _lib.KERNEL_GENERIC, "zmarch": _lib.KERNEL_ZMARCH}
+_KERNELS = {"auto": _lib.KERNEL_AUTO, "generic": _lib.KERNEL_GENERIC, "zmarch": _lib.KERNEL_ZMARCH,
+            "zsplit": _lib.KERNEL_ZSPLIT}
 
 
 class LagrangianFilter:

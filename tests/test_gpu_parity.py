@@ -238,8 +238,9 @@ ZM_CASES = [
 ]
 
 
+@pytest.mark.parametrize("kernel", ["zmarch", "zsplit"])
 @pytest.mark.parametrize("size,var_names,N,backward", ZM_CASES)
-def test_zmarch_kernel_vs_oracle(size, var_names, N, backward):
+def test_zmarch_kernel_vs_oracle(size, var_names, N, backward, kernel):
     """The production z-marching stage kernel (faces computed once, register z window, helper warps)
     against the CPU oracle: every tracer after several aligned and unaligned RK3 steps."""
     g = lfb200.RectilinearGrid(size=size, extent=tuple(float(s) for s in size), topology=("Periodic", "Periodic", "Bounded"))
@@ -247,8 +248,8 @@ def test_zmarch_kernel_vs_oracle(size, var_names, N, backward):
     times = [0.0, 0.5, 1.0]
     fields = make_series(g, times, var_names=var_names, velocity_names=vel_names, T_period=2.0)
     fp = lfb200.set_offline_BW2_filter_params(N=N, freq_c=2 * np.pi / 2.0)
-    o, m = make_pair(g, var_names, vel_names, fp, times, fields, kernel="zmarch", backward=backward)
-    assert m.kernel_name == "zmarch"
+    o, m = make_pair(g, var_names, vel_names, fp, times, fields, kernel=kernel, backward=backward)
+    assert m.kernel_name == kernel
     names = oracle_names(var_names, vel_names, fp)
     if backward:
         # initialise from the forward data, then run the backward pass on re-tagged slots
@@ -281,7 +282,7 @@ def test_zmarch_matches_generic_on_larger_grid():
     fp = lfb200.set_offline_BW2_filter_params(N=2, freq_c=2 * np.pi / 4.0)
     from lfb200.model import LagrangianFilter
     res = {}
-    for kernel in ("generic", "zmarch"):
+    for kernel in ("generic", "zmarch", "zsplit"):
         m = LagrangianFilter(g, var_names_to_filter=var_names, velocity_names=vel_names, filter_params=fp, n_slots=2,
                              kernel=kernel)
         for s, t in enumerate(times):
@@ -292,8 +293,9 @@ def test_zmarch_matches_generic_on_larger_grid():
             m.step(0.125)
         res[kernel] = [m.tracer(n) for n in m.tracer_names]
         m.close()
-    for a, b in zip(res["generic"], res["zmarch"]):
-        assert rel_l2(b, a) < TOL_STEP
+    for other in ("zmarch", "zsplit"):
+        for a, b in zip(res["generic"], res[other]):
+            assert rel_l2(b, a) < TOL_STEP
 
 
 def test_multi_gpu_slabs_match_single_gpu():
