@@ -422,3 +422,30 @@ def test_full_size_properties():
         a = base[n][H:-H, H:-H, :]
         b = sh[n][H:-H, H:-H, :]
         assert np.array_equal(np.roll(a, (37, 5), axis=(0, 1)), b), n
+
+
+def test_run_until_matches_host_alignment(golden_sim):
+    """lfb_run_until (Simulation time-step alignment on the C side) takes the same steps
+    as the host's aligned_time_steps: same clock, iteration count and state."""
+    g = golden_grid()
+    times, fields = golden_series(golden_sim)
+    fp = lfb200.set_offline_BW2_filter_params(N=2, freq_c=GOLDEN_RUN["freq_c"])
+    from lfb200.model import LagrangianFilter
+    states = []
+    for mode in ("host", "c"):
+        m = LagrangianFilter(g, var_names_to_filter=("b",), velocity_names=("u", "w"), filter_params=fp, n_slots=25,
+                             strict=True)
+        for s, t in enumerate(times):
+            for name in ("u", "w", "b"):
+                m.upload_snapshot(s, name, fields[name][s], t)
+        m.init_from_data()
+        if mode == "host":
+            for dt in lfb200.aligned_time_steps(86400.0, 1200.0, [3600.0, 8640.0]):
+                m.step(dt)
+        else:
+            m.run_until(86400.0, 1200.0, [3600.0, 8640.0])
+        assert m.time == 86400.0 and m.iteration == 80
+        states.append([m.tracer(n) for n in m.tracer_names])
+        m.close()
+    for a, b in zip(*states):
+        assert np.array_equal(a, b)
