@@ -177,6 +177,24 @@ int lfb_host_free(void *ptr);
 int lfb_combine(lfb_handle *h, int64_t n, const double *fwd, const double *bwd_lo, const double *bwd_hi,
                 double w_hi, double sign, double *out);
 
+/* ---- remap to the mean position (regrid_to_mean_position!, post:327-762) ------------------------ */
+typedef struct lfb_remap_desc {
+    int32_t size[3], halo[3], topology[3];   /* grid: exactly two axes must be non-Flat                  */
+    double  origin[3], spacing[3];           /* first face coordinate and spacing per axis               */
+    int32_t has_map[3];                      /* a xi map exists for this axis (velocity in velocity_names) */
+    int32_t npad;                            /* config.npad: periodic padding in cells (post:527-611)    */
+    int32_t device;
+    int32_t radius;                          /* search patch radius in cells; 0 = chosen from the data   */
+    int32_t reserved[4];
+} lfb_remap_desc;
+/* For one output time: interpolate every field from the displaced positions x + xi to the grid nodes:
+ * xi[axis] = parent array of xi_<vel> for that axis (NULL if no map), fields[v] / out[v] = parent arrays.
+ * Piecewise-linear interpolation on the Delaunay triangulation of the normalised, periodically padded
+ * cloud (scipy LinearNDInterpolator in the reference), 1-D edge rows on Bounded axes (numpy.interp),
+ * halos zero, NaN outside the hull.  The triangle search is shared by all fields. */
+int lfb_remap_to_mean(const lfb_remap_desc *desc, const double *const *xi, int n_fields, const double *const *fields,
+                      double *const *out);
+
 /* ---- multi-GPU: y-slab decomposition, one process per GPU ------------------------------------- */
 /* NCCL unique id (128 bytes) created on rank 0 and broadcast by the host (torch.distributed / MPI). */
 int lfb_comm_unique_id(void *id128);

@@ -29,7 +29,7 @@ EXPORTS = [
     "lfb_set_direction", "lfb_set_mask", "lfb_init_from_data", "lfb_negate_maps", "lfb_reset_clock", "lfb_time",
     "lfb_iteration", "lfb_get_tracer", "lfb_set_tracer", "lfb_get_tendency", "lfb_step", "lfb_run_until",
     "lfb_output", "lfb_output_f32", "lfb_output_async", "lfb_wait_transfers", "lfb_host_alloc", "lfb_host_free",
-    "lfb_combine", "lfb_comm_unique_id", "lfb_comm_init", "lfb_kernel_launches",
+    "lfb_combine", "lfb_remap_to_mean", "lfb_comm_unique_id", "lfb_comm_init", "lfb_kernel_launches",
     "lfb_stage_time_ms", "lfb_timer_start", "lfb_timer_stop", "lfb_kernel_name", "lfb_device_ptr", "lfb_layout",
 ]
 
@@ -49,6 +49,12 @@ class Desc(C.Structure):
                 ("with_maps", C.c_int32), ("advection", C.c_int32), ("n_slots", C.c_int32), ("device", C.c_int32),
                 ("strict", C.c_int32), ("kernel", C.c_int32), ("relaxation", C.c_int32),
                 ("relax_timescale", C.c_double), ("reserved", C.c_int32 * 8)]
+
+
+class RemapDesc(C.Structure):
+    _fields_ = [("size", C.c_int32 * 3), ("halo", C.c_int32 * 3), ("topology", C.c_int32 * 3),
+                ("origin", C.c_double * 3), ("spacing", C.c_double * 3), ("has_map", C.c_int32 * 3),
+                ("npad", C.c_int32), ("device", C.c_int32), ("radius", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 _lib = None
@@ -81,6 +87,7 @@ def load():
         "lfb_step": (i32, [vp, f64]), "lfb_run_until": (i32, [vp, f64, f64, i32, C.POINTER(f64)]),
         "lfb_output": (i32, [vp, i32, i32, vp]), "lfb_output_f32": (i32, [vp, i32, i32, vp]),
         "lfb_combine": (i32, [vp, i64, vp, vp, vp, f64, f64, vp]),
+        "lfb_remap_to_mean": (i32, [C.POINTER(RemapDesc), C.POINTER(vp), i32, C.POINTER(vp), C.POINTER(vp)]),
         "lfb_comm_unique_id": (i32, [vp]), "lfb_comm_init": (i32, [vp, vp, i32, i32]),
         "lfb_kernel_launches": (i64, [vp]), "lfb_stage_time_ms": (i32, [vp, i32, C.POINTER(f64), C.POINTER(i64)]),
         "lfb_timer_start": (i32, [vp]), "lfb_timer_stop": (i32, [vp, C.POINTER(f64)]),

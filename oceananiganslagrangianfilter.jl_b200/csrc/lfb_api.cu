@@ -51,6 +51,8 @@ static int fail(int code, const char *fmt, ...)
     return code;
 }
 
+extern "C" void lfb_internal_set_error(const char *msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+
 #define CU(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \

@@ -118,7 +118,7 @@ def sum_forward_backward_contributions(config, fwd: Dict[float, Dict[str, np.nda
 def regrid_to_mean_position(config, out: FilterOutput, extra_vars_to_regrid: Sequence[str] = ()):
     """Interpolates every `<var>_Lagrangian_filtered` field from the displaced positions x + xi to the
     grid nodes (generalised Lagrangian mean position), adding `<name>_at_mean` (reference post:327-762)."""
-    from .remap import remap_to_mean
+    from .remap import remap_to_mean, remap_to_mean_device
     if getattr(config, "advection", True) is None:
         raise ValueError("Regridding to mean position is not meaningful for Eulerian filtering")
     label = config.label
@@ -133,8 +133,8 @@ def regrid_to_mean_position(config, out: FilterOutput, extra_vars_to_regrid: Seq
     for k in range(len(out.times)):
         xi = {vel: out.fields["xi_" + vel + label][k] for vel in config.velocity_names
               if "xi_" + vel + label in out.fields}
-        res = remap_to_mean({n: out.fields[n][k] for n in names}, xi, g.N, g.H, g.topology, g.origin, g.spacing,
-                            npad=config.npad)
+        remap = remap_to_mean_device if len(g.nonflat_axes) == 2 else remap_to_mean
+        res = remap({n: out.fields[n][k] for n in names}, xi, g.N, g.H, g.topology, g.origin, g.spacing, npad=config.npad)
         for n in names:
             out.fields.setdefault(n + "_at_mean", []).append(res[n + "_at_mean"])
     log.info("Wrote regridded data to new variables with _at_mean suffix")

@@ -1,10 +1,11 @@
 """Remap of filtered fields to the mean position (reference regrid_to_mean_position!,
 src/Utils/post_processing_utils.jl:327-762).
 
-Host path: like the reference, which leaves Julia for this step and calls
-scipy.interpolate.LinearNDInterpolator / numpy.interp through PythonCall (post:8-13, 634, 670, 685),
-this module builds the padded, normalised point cloud and hands it to the same scipy routines.
-It is the reference's own algorithm and library for this step, not a stand-in for a device kernel.
+Grids with two non-Flat axes (the reference's 2-D examples and its golden test case) are remapped on the
+GPU by `remap_to_mean_device` -> lfb_remap_to_mean (csrc/lfb_remap.cu: local Delaunay walk + barycentric
+interpolation, shared by all variables of an output time).  For grids with three non-Flat axes this module
+does what the reference does -- it leaves for scipy.interpolate.LinearNDInterpolator (post:8-13, 634, 685) --
+because a device 3-D Delaunay is not built yet.
 """
 from __future__ import annotations
 
@@ -12,6 +13,8 @@ from typing import Dict
 
 import numpy as np
 from scipy.interpolate import LinearNDInterpolator
+
+from . import _lib
 
 
 def centre_nodes(N, H, x0, delta):
@@ -113,3 +116,32 @@ def remap_to_mean(fields: Dict[str, np.ndarray], xi: Dict[str, np.ndarray], N, H
                 s[ax] = slice(full[ax] - H[ax], full[ax]); res[tuple(s)] = 0.0
         out[nm + "_at_mean"] = res
     return out
+
+
+def remap_to_mean_device(fields: Dict[str, np.ndarray], xi: Dict[str, np.ndarray], N, H, topology, origin, delta,
+                         npad: int = 5, device: int = 0, radius: int = 0) -> Dict[str, np.ndarray]:
+    """Same contract as remap_to_mean, computed by liblfb200 (two non-Flat axes only)."""
+    import ctypes as C
+    L = _lib.load()
+    d = _lib.RemapDesc()
+    shape = tuple(N[ax] + 2 * H[ax] for ax in range(3))
+    for ax in range(3):
+        d.size[ax], d.halo[ax] = int(N[ax]), int(H[ax])
+        d.topology[ax] = _lib.TOPOLOGY[topology[ax]]
+        d.origin[ax], d.spacing[ax] = float(origin[ax]), float(delta[ax])
+        d.has_map[ax] = int("uvw"[ax] in xi)
+    d.npad, d.device, d.radius = int(npad), int(device), int(radius)
+    keep = []
+
+    def ptr(a):
+        a = _lib.as_parent(a, shape, np.float64)
+        keep.append(a)
+        return a.ctypes.data
+
+    xi_ptrs = (C.c_void_p * 3)(*[ptr(xi["uvw"[ax]]) if "uvw"[ax] in xi else None for ax in range(3)])
+    names = list(fields.keys())
+    f_ptrs = (C.c_void_p * len(names))(*[ptr(fields[n]) for n in names])
+    outs = [np.empty(shape, dtype=np.float64, order="F") for _ in names]
+    o_ptrs = (C.c_void_p * len(names))(*[o.ctypes.data for o in outs])
+    _lib.check(L.lfb_remap_to_mean(C.byref(d), xi_ptrs, len(names), f_ptrs, o_ptrs))
+    return {n + "_at_mean": o for n, o in zip(names, outs)}

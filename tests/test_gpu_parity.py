@@ -449,3 +449,59 @@ def test_run_until_matches_host_alignment(golden_sim):
         m.close()
     for a, b in zip(*states):
         assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------- remap to mean position
+def test_device_remap_matches_golden(golden_offline):
+    """regrid_to_mean_position on the GPU (local Delaunay walk) against the reference's pinned `*_at_mean`
+    fields (scipy / Qhull inside the reference), all 25 output times."""
+    from lfb200.remap import remap_to_mean_device
+    names = ["b_Lagrangian_filtered", "u_Lagrangian_filtered", "w_Lagrangian_filtered"]
+    for n in range(25):
+        fields = {k: golden_offline[k][n] for k in names}
+        xi = {"u": golden_offline["xi_u"][n], "w": golden_offline["xi_w"][n]}
+        out = remap_to_mean_device(fields, xi, GOLDEN_GRID["N"], GOLDEN_GRID["H"], GOLDEN_GRID["topology"],
+                                   GOLDEN_GRID["origin"], GOLDEN_GRID["delta"], npad=5)
+        for k in names:
+            ref, got = golden_offline[k + "_at_mean"][n], out[k + "_at_mean"]
+            assert np.array_equal(np.isnan(got), np.isnan(ref)), (n, k)
+            assert np.nanmax(np.abs(got - ref)) <= 1e-12 * np.nanmax(np.abs(ref)), (n, k)
+
+
+@pytest.mark.parametrize("size,topology,amp", [
+    ((48, 36), ("Periodic", "Flat", "Bounded"), 0.6),
+    ((40, 30), ("Periodic", "Flat", "Bounded"), 1.7),      # displacements beyond one cell: larger patches
+    ((32, 24), ("Periodic", "Periodic", "Flat"), 0.8),
+    ((30, 20), ("Bounded", "Flat", "Bounded"), 0.5),
+    ((200, 16), ("Periodic", "Flat", "Bounded"), 0.7),     # strongly anisotropic normalised cells
+])
+def test_device_remap_matches_scipy_oracle(size, topology, amp):
+    import remap_oracle as ro
+    from lfb200.remap import remap_to_mean_device
+    g = lfb200.RectilinearGrid(size=size, extent=tuple(float(s) * (3.0 if n == 0 else 1.0) for n, s in enumerate(size)),
+                               topology=topology)
+    axes = g.nonflat_axes
+    rng = np.random.default_rng(11)
+    shape = g.center_shape()
+    coords = [g.nodes(ax) for ax in range(3)]
+    mesh = np.meshgrid(*[coords[ax] if ax in axes else np.zeros(1) for ax in range(3)], indexing="ij")
+
+    def smooth(phase):
+        out = 0
+        for ax in axes:
+            out = out + np.sin(2 * np.pi * (mesh[ax] - g.origin[ax]) / g.L[ax] * (1 + ax) + phase + ax)
+        return out / len(axes)
+
+    xi = {}
+    for ax in axes:
+        f = smooth(0.3 * ax) * amp * g.spacing[ax]
+        if topology[ax] == "Bounded":          # no normal displacement at the walls
+            f = f * np.sin(np.pi * (mesh[ax] - g.origin[ax]) / g.L[ax])
+        xi["uvw"[ax]] = np.asfortranarray(f + 0.05 * g.spacing[ax] * rng.standard_normal(shape))
+    fields = {"T": np.asfortranarray(smooth(1.0) + 0.1 * rng.standard_normal(shape)),
+              "b": np.asfortranarray(np.tanh(3 * smooth(2.0)))}
+    want = ro.remap_to_mean(fields, xi, g.N, g.H, g.topology, g.origin, g.spacing, npad=5)
+    got = remap_to_mean_device(fields, xi, g.N, g.H, g.topology, g.origin, g.spacing, npad=5)
+    for k in want:
+        assert np.array_equal(np.isnan(got[k]), np.isnan(want[k])), k
+        assert np.nanmax(np.abs(got[k] - want[k])) <= 1e-10 * np.nanmax(np.abs(want[k])), k
