@@ -31,6 +31,7 @@ struct RemapParams {
     int    has_map[2];
     double origin[2], delta[2], L[2];
     double mn[2], rg[2];    // normalisation of the padded cloud
+    double pad[2];          // width npad * delta of the periodic padding (post:527-611)
     int    r[2];            // patch radius in cells
     double maxdisp[2];      // max |xi| in cells (for the patch sufficiency check)
     int64_t stride[2];      // element strides of the two axes in the parent arrays
@@ -43,19 +44,38 @@ __device__ __forceinline__ double orient2d(double ax, double ay, double bx, doub
 
 struct Cand { double x, y; int64_t idx; };
 
+// Position along axis q of the periodic image of lattice point `qi` that sits at lattice offset `w` periods from it,
+// or false if the reference's padded cloud does not hold that image: the cloud has the point wrapped into
+// [lo, lo + L) (post:427-429), its copy one period down if the wrapped point lies within `pad` of the upper end and
+// its copy one period up if it lies within `pad` of the lower end (post:527-611) -- nothing further out, which
+// changes the triangulation near periodic edges when the normalised cells are strongly anisotropic.
+__device__ __forceinline__ bool image_position(const RemapParams &P, int q, int qi, int w, double disp, double &x)
+{
+    const double lo = P.origin[q];
+    const double X = lo + P.delta[q] * (qi + 0.5) + disp;
+    if (!P.periodic[q]) { x = X; return true; }
+    const double fl = floor((X - lo) / P.L[q]);
+    const double Xw = X - fl * P.L[q];
+    const int m = w + (int)fl;                 // image index relative to the wrapped point
+    if (m == 0) { x = Xw; return true; }
+    if (m == -1 && Xw > lo + P.L[q] - P.pad[q] && Xw < lo + P.L[q]) { x = Xw - P.L[q]; return true; }
+    if (m == 1 && Xw < lo + P.pad[q] && Xw > lo) { x = Xw + P.L[q]; return true; }
+    return false;
+}
+
 // lattice neighbour (p0, p1) of the patch: normalised position of its (periodic image of the) data point
 __device__ __forceinline__ bool candidate(const RemapParams &P, const double *__restrict__ xi0, const double *__restrict__ xi1,
                                           int p0, int p1, Cand &c)
 {
-    double s0 = 0, s1 = 0;
-    int q0 = p0, q1 = p1;
-    if (P.periodic[0]) { int w = 0; while (q0 < 0) { q0 += P.n[0]; --w; } while (q0 >= P.n[0]) { q0 -= P.n[0]; ++w; } s0 = w * P.L[0]; }
+    int q0 = p0, q1 = p1, w0 = 0, w1 = 0;
+    if (P.periodic[0]) { while (q0 < 0) { q0 += P.n[0]; --w0; } while (q0 >= P.n[0]) { q0 -= P.n[0]; ++w0; } }
     else if (p0 < 0 || p0 >= P.n[0]) return false;
-    if (P.periodic[1]) { int w = 0; while (q1 < 0) { q1 += P.n[1]; --w; } while (q1 >= P.n[1]) { q1 -= P.n[1]; ++w; } s1 = w * P.L[1]; }
+    if (P.periodic[1]) { while (q1 < 0) { q1 += P.n[1]; --w1; } while (q1 >= P.n[1]) { q1 -= P.n[1]; ++w1; } }
     else if (p1 < 0 || p1 >= P.n[1]) return false;
     const int64_t idx = (int64_t)(q0 + P.H[0]) * P.stride[0] + (int64_t)(q1 + P.H[1]) * P.stride[1];
-    const double x0 = P.origin[0] + P.delta[0] * (q0 + 0.5) + (P.has_map[0] ? xi0[idx] : 0.0) + s0;
-    const double x1 = P.origin[1] + P.delta[1] * (q1 + 0.5) + (P.has_map[1] ? xi1[idx] : 0.0) + s1;
+    double x0, x1;
+    if (!image_position(P, 0, q0, w0, P.has_map[0] ? xi0[idx] : 0.0, x0)) return false;
+    if (!image_position(P, 1, q1, w1, P.has_map[1] ? xi1[idx] : 0.0, x1)) return false;
     c.x = (x0 - P.mn[0]) / P.rg[0];
     c.y = (x1 - P.mn[1]) / P.rg[1];
     c.idx = idx;
@@ -131,6 +151,9 @@ __global__ void lfb_remap2d_locate(const RemapParams P, const double *__restrict
     const double safe0 = (r0 - P.maxdisp[0] - 0.5) * h0, safe1 = (r1 - P.maxdisp[1] - 0.5) * h1;
     const bool edge0_lo = !P.periodic[0] && i0 - r0 < 0, edge0_hi = !P.periodic[0] && i0 + r0 >= P.n[0];
     const bool edge1_lo = !P.periodic[1] && i1 - r1 < 0, edge1_hi = !P.periodic[1] && i1 + r1 >= P.n[1];
+    // nodes on the first / last row of a Bounded axis are overwritten by the 1-D edge interpolation; their hull
+    // triangles can be arbitrarily flat, so they are not checked
+    if ((!P.periodic[0] && (i0 == 0 || i0 == P.n[0] - 1)) || (!P.periodic[1] && (i1 == 0 || i1 == P.n[1] - 1))) return;
     bool bad = false;
     if (!edge0_lo && ccx - rad < qx - safe0) bad = true;
     if (!edge0_hi && ccx + rad > qx + safe0) bad = true;
@@ -230,7 +253,7 @@ extern "C" int lfb_remap_to_mean(const lfb_remap_desc *D, const double *const *x
                 }
             }
         if (!(md < 1e300)) RFAIL(LFB_ERR_ARG, "non-finite displacement");
-        P.mn[q] = mn; P.rg[q] = mx - mn; P.maxdisp[q] = md;
+        P.mn[q] = mn; P.rg[q] = mx - mn; P.maxdisp[q] = md; P.pad[q] = pad;
     }
     double *d_xi[2] = {nullptr, nullptr}, *d_f = nullptr, *d_out = nullptr, *d_w = nullptr;
     int64_t *d_tri = nullptr;
