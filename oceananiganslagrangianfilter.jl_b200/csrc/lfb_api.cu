@@ -22,6 +22,9 @@ cudaError_t lfb_launch_stage_generic(const LfbStageParams *P, int strict, cudaSt
 cudaError_t lfb_launch_stage_zmarch(const LfbStageParams *P, cudaStream_t stream);
 cudaError_t lfb_launch_stage_zsplit(const LfbStageParams *P, cudaStream_t stream);
 int         lfb_zmarch_supported(const LfbStageParams *P);
+cudaError_t lfb_launch_stage_ztma(const LfbStageParams *P, cudaStream_t stream);
+int         lfb_ztma_supported(const LfbStageParams *P);
+int         lfb_ztma_tile_rows(void);
 cudaError_t lfb_launch_interp_inputs(const LfbInterpParams *P, cudaStream_t stream);
 cudaError_t lfb_launch_fill_halo_axis(double *base, int64_t field_stride, int n_fields, const LfbLayout *L,
                                       int ax, int mode, cudaStream_t stream);
@@ -172,11 +175,18 @@ static int select_kernel(lfb_handle *h)
     for (int ax = 0; ax < 3; ++ax) P.vel_present[ax] = (h->desc.velocity_mask >> ax) & 1;
     P.j0 = 0; P.j1 = h->L.N[1];
     const int ok = lfb_zmarch_supported(&P) && !h->desc.strict;
-    if ((h->desc.kernel == LFB_KERNEL_ZMARCH || h->desc.kernel == LFB_KERNEL_ZSPLIT) && !ok)
+    if ((h->desc.kernel == LFB_KERNEL_ZMARCH || h->desc.kernel == LFB_KERNEL_ZSPLIT || h->desc.kernel == LFB_KERNEL_ZTMA) && !ok)
         return fail(LFB_ERR_ARG, "the z-marching kernel needs a (Periodic|slab, Periodic|slab, Bounded) grid with Nx %% 32 == 0, "
                                  "Ny %% 8 == 0, Nz >= 8, u,v,w all present, WENO advection, no relaxation and strict = 0");
-    h->use_zmarch = (h->desc.kernel != LFB_KERNEL_GENERIC) && ok;       // 0 generic, 1 z-march, 2 role-split z-march
-    if (h->use_zmarch && h->desc.kernel == LFB_KERNEL_ZSPLIT) h->use_zmarch = 2;
+    // 0 generic, 1 z-march (cp.async), 2 role-split z-march, 3 TMA-staged z-march (what `auto` picks)
+    h->use_zmarch = 0;
+    if (h->desc.kernel != LFB_KERNEL_GENERIC && ok) {
+        if (h->desc.kernel == LFB_KERNEL_ZMARCH) h->use_zmarch = 1;
+        else if (h->desc.kernel == LFB_KERNEL_ZSPLIT) h->use_zmarch = 2;
+        else if (lfb_ztma_supported(&P)) h->use_zmarch = 3;
+        else if (h->desc.kernel == LFB_KERNEL_ZTMA) return fail(LFB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        else h->use_zmarch = 1;
+    }
     return LFB_OK;
 }
 
@@ -715,11 +725,13 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
     CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, h->compute));
     const int Ny = h->L.N[1];
-    const int strip = h->use_zmarch == 2 ? 4 : (h->use_zmarch ? 6 : h->L.H[1]);      // rows per edge strip: one z-march tile row / the halo width
+    // rows per edge strip: one z-march tile row / the halo width
+    const int strip = h->use_zmarch == 3 ? lfb_ztma_tile_rows() : (h->use_zmarch == 2 ? 4 : (h->use_zmarch ? 6 : h->L.H[1]));
     const bool overlap = update && h->nranks > 1 && Ny >= 4 * strip;
     auto launch = [&](int j0, int j1) -> int {
         P.j0 = j0; P.j1 = j1;
-        if (h->use_zmarch == 2 && update) CU(lfb_launch_stage_zsplit(&P, h->compute));
+        if (h->use_zmarch == 3 && update) CU(lfb_launch_stage_ztma(&P, h->compute));
+        else if (h->use_zmarch == 2 && update) CU(lfb_launch_stage_zsplit(&P, h->compute));
         else if (h->use_zmarch && update) CU(lfb_launch_stage_zmarch(&P, h->compute));
         else                         CU(lfb_launch_stage_generic(&P, h->desc.strict, h->compute));
         h->launches++;
@@ -1026,6 +1038,7 @@ extern "C" int lfb_timer_stop(lfb_handle *h, double *ms)
 extern "C" const char *lfb_kernel_name(const lfb_handle *h)
 {
     if (!h) return "";
+    if (h->use_zmarch == 3) return "ztma";
     if (h->use_zmarch == 2) return "zsplit";
     if (h->use_zmarch) return "zmarch";
     return h->desc.strict ? "generic-strict" : "generic";

@@ -18,7 +18,7 @@ from .filter_utils import FilterParams, create_filtered_vars, tracer_layout
 from .grids import RectilinearGrid
 
 _KERNELS = {"auto": _lib.KERNEL_AUTO, "generic": _lib.KERNEL_GENERIC, "zmarch": _lib.KERNEL_ZMARCH,
-            "zsplit": _lib.KERNEL_ZSPLIT}
+            "zsplit": _lib.KERNEL_ZSPLIT, "ztma": _lib.KERNEL_ZTMA}
 
 
 class LagrangianFilter:

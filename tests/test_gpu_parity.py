@@ -238,7 +238,7 @@ ZM_CASES = [
 ]
 
 
-@pytest.mark.parametrize("kernel", ["zmarch", "zsplit"])
+@pytest.mark.parametrize("kernel", ["ztma", "zmarch", "zsplit"])
 @pytest.mark.parametrize("size,var_names,N,backward", ZM_CASES)
 def test_zmarch_kernel_vs_oracle(size, var_names, N, backward, kernel):
     """The production z-marching stage kernel (faces computed once, register z window, helper warps)
@@ -282,7 +282,7 @@ def test_zmarch_matches_generic_on_larger_grid():
     fp = lfb200.set_offline_BW2_filter_params(N=2, freq_c=2 * np.pi / 4.0)
     from lfb200.model import LagrangianFilter
     res = {}
-    for kernel in ("generic", "zmarch", "zsplit"):
+    for kernel in ("generic", "ztma", "zmarch", "zsplit"):
         m = LagrangianFilter(g, var_names_to_filter=var_names, velocity_names=vel_names, filter_params=fp, n_slots=2,
                              kernel=kernel)
         for s, t in enumerate(times):
@@ -293,7 +293,7 @@ def test_zmarch_matches_generic_on_larger_grid():
             m.step(0.125)
         res[kernel] = [m.tracer(n) for n in m.tracer_names]
         m.close()
-    for other in ("zmarch", "zsplit"):
+    for other in ("ztma", "zmarch", "zsplit"):
         for a, b in zip(res["generic"], res[other]):
             assert rel_l2(b, a) < TOL_STEP
 
@@ -407,7 +407,7 @@ def test_full_size_properties():
         m.close()
         return out
 
-    base = run("zmarch")
+    base = run("auto")
     # uniform variable: tracers uniform over the interior
     tc = base["T_C1"][H:-H, H:-H, H:-H]
     assert np.ptp(tc) <= 1e-13 * abs(tc.mean()), np.ptp(tc)
@@ -417,7 +417,7 @@ def test_full_size_properties():
         assert rel_l2(base[n], gen[n]) <= TOL_STEP, n
     del gen
     # translation equivariance (37 and 5 are not multiples of the 32 x 6 tile)
-    sh = run("zmarch", shift=(37, 5), want=("b_S1", "xi_v_C1"))
+    sh = run("auto", shift=(37, 5), want=("b_S1", "xi_v_C1"))
     for n in sh:
         a = base[n][H:-H, H:-H, :]
         b = sh[n][H:-H, H:-H, :]
