@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblfb200.so")
+LIB_PATH = os.environ.get("LFB200_LIB") or os.path.join(HERE, "liblfb200.so")      # override: kernel experiments only
 
 MAX_COEFFS, MAX_VARS = 8, 8
 PERIODIC, BOUNDED, FLAT = 0, 1, 2

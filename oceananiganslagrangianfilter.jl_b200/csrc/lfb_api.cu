@@ -719,6 +719,7 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
     P.dt = dt; P.gamma = gamma; P.zeta = zeta;
     P.first_stage = first; P.store_G = store_G; P.update = update;
     P.j0 = 0; P.j1 = h->L.N[1];
+    P.scratch = h->scratch;
 
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));

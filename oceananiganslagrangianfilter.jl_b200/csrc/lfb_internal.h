@@ -75,6 +75,7 @@ struct LfbStageParams {
     // sub-range of the local grid this launch covers (boundary strips / interior when overlapping
     // the halo exchange): cells j in [j0, j1)
     int     j0, j1;
+    double *scratch;          // one spare field (store target of inactive rows in partial tiles of the z-march kernels)
 };
 
 // Output combinations (create_output_fields, utils:898-1012): out = sum_i wc[i] U[tc[i]] + ws[i] U[tc[i]+1]

@@ -3,76 +3,87 @@
 // Same fused work as lfb_stage_generic / lfb_stage_zmarch (WENO5-Z flux divergence, c div(U), forcing, RK3
 // substep, tendency caching, periodic halo images; reference call sites: compute_Gc! / tracer_tendency,
 // lagrangian_filter_tendency_kernel_functions.jl:36-61, lagrangian_filter_rk3_substep.jl:31-61,
-// cache_lagrangian_filter_tendencies.jl:8-31, update_lagrangian_filter_state.jl:33-34),
-// organised around the two limits this stencil has on B200: the FP64 pipe (64 lanes per SM) and the warp
-// schedulers' issue slots (an FP64 instruction occupies the pipe for two cycles, so every other instruction
-// competes with it one-for-two).  Relative to lfb_stage_zmarch:
+// cache_lagrangian_filter_tendencies.jl:8-31, update_lagrangian_filter_state.jl:33-34).
+//
+// What bounds this stencil on B200 is the warp schedulers' issue port, not HBM: an FP64 instruction holds the
+// sub-partition's port for two cycles and nothing else issues in its shadow (measured: 1 DFMA + 1 FFMA per
+// thread cost 3 cycles, scratch microbenchmark quoted in DESIGN.md), so the time of a plane is about
+// 2 x (FP64 instructions) + (all other instructions), per warp, summed over the warps of a sub-partition.  The
+// kernel is therefore organised to execute as few instructions as possible:
 //   * every input tile is brought into shared memory by TMA (cp.async.bulk.tensor + mbarrier): the haloed
 //     40 x (TY+6) plane of each tracer, the u / v / w face-velocity tiles, G^- and the forcing variable.  One
 //     elected lane issues them two planes ahead; no thread computes a global load address, stages a halo
-//     element or publishes a velocity any more.  The tracer planes live in an 8-deep ring, so the plane that
-//     feeds the z window (k+4) and the plane the in-plane stencils read (k) are the same TMA load;
+//     element or publishes a velocity.  The tracer planes live in an 8-deep ring, so the plane that feeds the
+//     z window (k+4) and the plane the in-plane stencils read (k) are the same TMA load;
 //   * upwinding is done on addresses, not values: the five cells of a face stencil are loaded in upwind order
 //     (mirrored shared-memory addressing), so no FP64 select or negation is executed; along z the register
 //     window is used by a warp-uniform branch per direction;
-//   * the arithmetic per face is shorter: smoothness indicators scaled by 4/3 (one multiply less each), the
-//     blend written as x1 - (A0 y0 / 2 + A2 y2 / 3) / den with y = second differences already at hand, a cubic
-//     reciprocal refinement folded into the last FMA, fluxes and divergences in units of face velocity
-//     (areas / volume applied once per axis).
+//   * the arithmetic per face is short (47 FP64 instructions in x / y, 36 in z): smoothness indicators scaled
+//     by 4/3 with eps folded into the curvature term, the blend written as x1 - (A0 y0 / 2 + A2 y2 / 3) / den
+//     with y = second differences already at hand, a cubic reciprocal refinement folded into the last FMA,
+//     fluxes and divergences in units of face velocity (areas / volume applied once per axis);
+//   * the march is unrolled over the 8-plane period of the rings, so every ring offset, flux buffer and
+//     mbarrier parity is an immediate; all shared-memory addresses of a thread derive from four registers;
+//   * two planes are computed per block barrier.
 // One block = the tracers of one (field, coefficient-set) item on a 32 x TY tile, marching over all Nz planes;
 // a thread owns one cell column of one tracer and computes its west, south and top faces; the faces on the
-// east / north tile edge are computed by helper warps, fluxes are exchanged through shared memory with one
-// bar.sync per plane (that barrier also orders the reuse of the TMA ring slots).
+// east / north tile edge are computed by helper warps, fluxes are exchanged through shared memory (that
+// barrier also orders the reuse of the TMA ring slots).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "lfb_zm_common.cuh"
 
 #define ZT_TX 32
-#define ZT_CW 40          // haloed tile width: 4 + 32 + 4 columns (TMA needs a 16-byte aligned inner start coordinate, so
-                          // the 3-wide halo is widened to 4)
+#define ZT_CW 40          // width of the pitch-40 tiles: 4 + 32 + 4 columns (TMA needs a 16-byte aligned inner start
+                          // coordinate, so the 3-wide halo is widened to 4)
 #define ZT_HX 4
-#define ZT_UW 34          // u tile width (west + east faces, padded to a 16-byte multiple)
 #define ZT_RC 8           // ring of haloed tracer planes: k .. k+4 live, 2 in flight, 1 being released
-#define ZT_RI 4           // ring of per-plane input tiles
+#define ZT_RI 4           // ring of per-plane input tiles, of flux buffers and of group mbarriers
 #define ZT_D  2           // planes the producer runs ahead
 
 struct LfbZtParams {
     LfbStageParams S;
     alignas(64) CUtensorMap mC;                  // U_old stack  (x, y, z, tracer), box 40 x (TY+6)
     alignas(64) CUtensorMap mG;                  // G stack      (x, y, z, tracer), box 32 x TY
-    alignas(64) CUtensorMap mU;                  // u            (x, y, z),         box 34 x TY
+    alignas(64) CUtensorMap mU;                  // u            (x, y, z),         box 40 x TY
     alignas(64) CUtensorMap mV;                  // v                               box 32 x (TY+1)
-    alignas(64) CUtensorMap mW;                  // w                               box 32 x TY
+    alignas(64) CUtensorMap mW;                  // w                               box 32 x TY x 2 (bottom and top faces)
     alignas(64) CUtensorMap mF[LFB_MAX_VARS];    // original variables              box 32 x TY
     double k133, k13, k16, eps43, rd[3];         // 13/3, 1/3, 1/6, 4/3 eps, area / volume per axis
+    double *scratch;                             // one field: store target of the rows beyond j1 in partial tiles
 };
 
+// Shared memory (doubles).  Two tile geometries: pitch 40 (x halo of 4: tracer planes, u, x fluxes; a thread's
+// own cell sits at (ty [+3]) * 40 + tx + 4) and pitch 32 (v, w, G^-, forcing variable, y fluxes; own cell at
+// ty * 32 + tx).  Per-tracer tiles are strided by CTP (pitch 40) or VT (pitch 32) doubles.
 template <int NSUB, int TY>
 struct ZtSmem {
     static constexpr int CH = TY + 6;
-    static constexpr int CT = CH * ZT_CW;                        // doubles of one haloed tracer tile = the TMA box
-    static constexpr int CTP = (CT + 15) / 16 * 16;              // padded to 128 bytes
+    static constexpr int CTP = CH * ZT_CW;                       // haloed tracer tile = the TMA box (multiple of 16)
     static constexpr int NT = ZT_TX * TY;
-    static constexpr int UT = (TY * ZT_UW + 15) / 16 * 16;       // [TY][34]
+    static constexpr int UT = TY * ZT_CW;                        // [TY][40]
     static constexpr int VT = (TY + 1) * 32;                     // [TY+1][32]
-    static constexpr int OFF_U = 0, OFF_V = UT, OFF_W = OFF_V + VT, OFF_G = OFF_W + NT, OFF_F = OFF_G + NSUB * NT;
-    static constexpr int ISLOT = OFF_F + NT;                     // doubles per input slot
+    static constexpr int OFF_U = 0, OFF_V = UT, OFF_W = OFF_V + VT, OFF_G = OFF_W + 2 * NT, OFF_F = OFF_G + NSUB * VT,
+                         OFF_Z = OFF_F + NT;                     // a zero (second source of a filtered variable)
+    static constexpr int ISLOT = OFF_Z + 16;                     // doubles per input slot
     static constexpr int CSLOT = NSUB * CTP;
-    static constexpr int FBUF = NSUB * (UT + VT);                // Fx[NSUB][TY][34], Fy[NSUB][TY+1][32]
+    static constexpr int FBUF = NSUB * (CTP + VT);               // Fx[NSUB] (tracer-tile geometry), Fy[NSUB][TY+1][32]
     static constexpr int O_C = 0;
     static constexpr int O_IN = O_C + ZT_RC * CSLOT;
-    static constexpr int O_W0 = O_IN + ZT_RI * ISLOT;            // w at the bottom faces of plane 0
-    static constexpr int O_FL = O_W0 + NT;
-    static constexpr int O_BAR = O_FL + 2 * FBUF;                // ZT_RI group barriers + the prologue barrier
+    static constexpr int O_FL = O_IN + ZT_RI * ISLOT;
+    static constexpr int O_BAR = O_FL + ZT_RI * FBUF;            // ZT_RI group barriers + the prologue barrier
     static constexpr int DOUBLES = O_BAR + 8;
-    static constexpr int BYTES = DOUBLES * 8 + 128;              // + slack to align the base to 128 bytes
+    static constexpr int BYTES = DOUBLES * 8;
     static constexpr int NMAIN = NSUB * NT;
     static constexpr int THREADS = NMAIN + NSUB * 32 + 32;
     static_assert(NSUB * TY < 32, "east-edge faces and the producer lane share one warp");
-    static_assert(NT % 16 == 0 && VT % 16 == 0, "TMA destinations must stay 128-byte aligned");
+    static_assert(CTP % 16 == 0 && NT % 16 == 0 && VT % 16 == 0 && UT % 16 == 0, "TMA destinations must stay 128-byte aligned");
+    static_assert(BYTES <= 227 * 1024, "shared memory");
 };
 
 // ---- mbarrier / TMA -----------------------------------------------------------------------------------------------
@@ -110,23 +121,23 @@ __device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap *map
 // ---- arithmetic ---------------------------------------------------------------------------------------------------
 struct ZtK { double k133, k13, k16, eps43; };
 
-// WENO5-Z blend.  b_s = 4/3 beta_s, y0 = s0 - s1, y2 = s1 - s2 (second differences of the differences),
-// x1 = dn/3 + do/6 the increment of the central candidate.  With A_s = (G_s + tau^2) prod_{j != s} G_j,
-// G_s = (b_s + 4/3 eps)^2:   face - n = x1 - (A0 y0 / 2 + A2 y2 / 3) / (3 A0 + 6 A1 + A2)
-// (identical to sum alpha_s q_s / sum alpha_s of SURVEY.md App. A.5; the common scale of beta, eps, tau cancels).
-__device__ __forceinline__ double zt_blend(double b0, double b1, double b2, double y0, double y2, double x1, const ZtK &K)
+// WENO5-Z blend.  g_s = 4/3 (beta_s + eps) (eps is folded into the curvature terms by the callers), y0 = s0 - s1 and
+// y2 = s1 - s2 the second differences of the differences, x1 = dn/3 + do/6 the increment of the central candidate.
+// With G_s = g_s^2, tau = g0 - g2, A_s = (G_s + tau^2) prod_{j != s} G_j:
+//     face - n = x1 - (A0 y0 / 2 + A2 y2 / 3) / (3 A0 + 6 A1 + A2)
+// which is sum alpha_s q_s / sum alpha_s of SURVEY.md App. A.5 brought to one denominator (the common scale 4/3 of
+// beta, eps and tau cancels).  One reciprocal: hardware seed (~20 bits) + one cubic step, folded into the last FMA.
+__device__ __forceinline__ double zt_blend(double g0, double g1, double g2, double y0, double y2, double x1, const ZtK &K)
 {
-    const double tau = b0 - b2;
-    const double tt = tau * tau;
-    const double g0 = b0 + K.eps43, g1 = b1 + K.eps43, g2 = b2 + K.eps43;
+    const double tau = g0 - g2;
     const double G0 = g0 * g0, G1 = g1 * g1, G2 = g2 * g2;
-    const double A0 = (G0 + tt) * (G1 * G2);
-    const double A1 = (G1 + tt) * (G0 * G2);
-    const double A2 = (G2 + tt) * (G0 * G1);
+    const double A0 = fma(tau, tau, G0) * (G1 * G2);
+    const double A1 = fma(tau, tau, G1) * (G0 * G2);
+    const double A2 = fma(tau, tau, G2) * (G0 * G1);
     const double den = fma(3.0, A0, fma(6.0, A1, A2));
     const double num = fma(0.5, A0 * y0, K.k13 * (A2 * y2));
     double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));       // ~20 bits; one cubic step -> ~60 bits
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
     const double e = fma(-den, r, 1.0);
     const double t = fma(e, e, e);
     r = fma(r, t, r);
@@ -138,21 +149,21 @@ __device__ __forceinline__ double zt_inc(double dp, double do_, double dn, doubl
 {
     const double s0 = de - dn, s1 = dn - do_, s2 = do_ - dp;
     const double t0 = fma(-3.0, dn, de), t1 = dn + do_, t2 = fma(3.0, do_, -dp);
-    const double b0 = fma(t0, t0, (K.k133 * s0) * s0);
-    const double b1 = fma(t1, t1, (K.k133 * s1) * s1);
-    const double b2 = fma(t2, t2, (K.k133 * s2) * s2);
-    return zt_blend(b0, b1, b2, s0 - s1, s1 - s2, fma(K.k13, dn, K.k16 * do_), K);
+    const double g0 = fma(t0, t0, fma(K.k133 * s0, s0, K.eps43));
+    const double g1 = fma(t1, t1, fma(K.k133 * s1, s1, K.eps43));
+    const double g2 = fma(t2, t2, fma(K.k133 * s2, s2, K.eps43));
+    return zt_blend(g0, g1, g2, s0 - s1, s1 - s2, fma(K.k13, dn, K.k16 * do_), K);
 }
 
-// ... with the curvature terms Q_s = 13/3 s_s^2 supplied (z direction, register window)
+// ... with the curvature terms Q_s = 13/3 s_s^2 + 4/3 eps supplied (z direction, register window)
 __device__ __forceinline__ double zt_inc_q(double dp, double do_, double dn, double de, double Q2, double Q1, double Q0, const ZtK &K)
 {
     const double t0 = fma(-3.0, dn, de), t1 = dn + do_, t2 = fma(3.0, do_, -dp);
-    const double b0 = fma(t0, t0, Q0);
-    const double b1 = fma(t1, t1, Q1);
-    const double b2 = fma(t2, t2, Q2);
+    const double g0 = fma(t0, t0, Q0);
+    const double g1 = fma(t1, t1, Q1);
+    const double g2 = fma(t2, t2, Q2);
     const double y0 = fma(-2.0, dn, de) + do_, y2 = fma(-2.0, do_, dn) + dp;
-    return zt_blend(b0, b1, b2, y0, y2, fma(K.k13, dn, K.k16 * do_), K);
+    return zt_blend(g0, g1, g2, y0, y2, fma(K.k13, dn, K.k16 * do_), K);
 }
 
 // Upwind face value at the low face of the cell at shared byte address `a` along the axis with byte stride S:
@@ -188,19 +199,23 @@ __device__ __noinline__ double zt_top_face_buffer(int m, int Nz, double cw, doub
     return 0.5 * (ck + ck1);
 }
 
+#ifndef ZT_PB
+#define ZT_PB 2           // planes per block barrier
+#endif
+
 template <int NSUB, int TY>
 __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(const __grid_constant__ LfbZtParams P)
 {
     using SM = ZtSmem<NSUB, TY>;
-    extern __shared__ double zt_smem_raw[];
-    const unsigned sbase = ((unsigned)__cvta_generic_to_shared(zt_smem_raw) + 127u) & ~127u;
+    extern __shared__ __align__(1024) double zt_smem[];
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(zt_smem);
     constexpr int ROW_B = 8 * ZT_CW;
-    constexpr unsigned CSLOT_B = 8u * SM::CSLOT, ISLOT_B = 8u * SM::ISLOT, FBUF_B = 8u * SM::FBUF, CTP_B = 8u * SM::CTP;
-    constexpr unsigned oC = 8u * SM::O_C, oIN = 8u * SM::O_IN, oW0 = 8u * SM::O_W0, oFL = 8u * SM::O_FL, oBAR = 8u * SM::O_BAR;
+    constexpr unsigned CSLOT_B = 8u * SM::CSLOT, ISLOT_B = 8u * SM::ISLOT, FBUF_B = 8u * SM::FBUF, CTP_B = 8u * SM::CTP,
+                       VT_B = 8u * SM::VT, NT_B = 8u * SM::NT;
+    constexpr unsigned oC = 8u * SM::O_C, oIN = 8u * SM::O_IN, oFL = 8u * SM::O_FL, oBAR = 8u * SM::O_BAR;
     constexpr unsigned oU = oIN + 8u * SM::OFF_U, oV = oIN + 8u * SM::OFF_V, oW = oIN + 8u * SM::OFF_W,
-                       oG = oIN + 8u * SM::OFF_G, oF = oIN + 8u * SM::OFF_F;
-    constexpr unsigned oFX = oFL, oFY = oFL + 8u * NSUB * SM::UT;
-    constexpr unsigned CBOX_B = 8u * SM::CT, NT_B = 8u * SM::NT;
+                       oG = oIN + 8u * SM::OFF_G, oF = oIN + 8u * SM::OFF_F, oZ = oIN + 8u * SM::OFF_Z;
+    constexpr unsigned oFX = oFL, oFY = oFL + NSUB * CTP_B;
     const LfbStageParams &S = P.S;
     const LfbLayout &L = S.L;
     const int tid = threadIdx.x;
@@ -216,9 +231,11 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     const unsigned bar0 = sbase + oBAR, barP = bar0 + 8u * ZT_RI;
 
     if (tid == 0) {
+        if (sbase & 127u) __trap();                       // the TMA destinations assume a 128-byte aligned window
         for (int b = 0; b <= ZT_RI; ++b) mbar_init(bar0 + 8u * b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (tid < ZT_RI) sts(sbase + oZ + tid * ISLOT_B, 0.0);
     __syncthreads();
 
     if (tid >= SM::NMAIN) {
@@ -231,10 +248,10 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             if (xl < NSUB * TY) { kind = 2; sub = xl / TY; ty = xl % TY; tx = ZT_TX; }
             else { kind = xl == 31 ? 3 : 0; sub = 0; tx = 0; ty = 0; }
         }
-        // One loop for the whole warp (bar.sync is warp-aligned): the producer lane issues the TMA loads of plane
-        // k + ZT_D, the face lanes compute their edge face of plane k, idle lanes only keep the barrier count.
+        // One loop for the whole warp (bar.sync is warp-aligned): the producer lane issues the TMA loads of the planes
+        // ZT_D ahead, the face lanes compute their edge faces, idle lanes only keep the barrier count.
         const int cx = L.xoff + i0 - ZT_HX, cy = L.H[1] + j0 - 3, ix = L.xoff + i0, iy = L.H[1] + j0, z0 = L.H[2];
-        const unsigned in_bytes = 8u * (ZT_UW * TY + 32 * (TY + 1) + 32 * TY) + (use_G ? NSUB * NT_B : 0u) + (item_var ? NT_B : 0u);
+        const unsigned in_bytes = 8u * (ZT_CW * TY + 32 * (TY + 1) + 2 * 32 * TY) + (use_G ? NSUB * NT_B : 0u) + (item_var ? NT_B : 0u);
         auto issue_C = [&](int pz, unsigned bar) {            // haloed tracer planes at z index pz (-2 .. Nz+2)
             const unsigned dst = sbase + oC + (unsigned)((pz + 2) & (ZT_RC - 1)) * CSLOT_B;
 #pragma unroll
@@ -243,41 +260,46 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         auto issue_group = [&](int g) {                       // inputs of plane g and tracer plane g + 4
             const unsigned bar = bar0 + 8u * (g & (ZT_RI - 1));
             const bool withC = g + 4 <= Nz + 2;
-            mbar_expect_tx(bar, in_bytes + (withC ? NSUB * CBOX_B : 0u));
+            mbar_expect_tx(bar, in_bytes + (withC ? NSUB * CTP_B : 0u));
             if (withC) issue_C(g + 4, bar);
             const unsigned is = sbase + (unsigned)(g & (ZT_RI - 1)) * ISLOT_B;
-            tma_load_3d(is + oU, &P.mU, ix, iy, z0 + g, bar);
+            tma_load_3d(is + oU, &P.mU, cx, iy, z0 + g, bar);
             tma_load_3d(is + oV, &P.mV, ix, iy, z0 + g, bar);
-            tma_load_3d(is + oW, &P.mW, ix, iy, z0 + g + 1, bar);
+            tma_load_3d(is + oW, &P.mW, ix, iy, z0 + g, bar);
             if (use_G) {
 #pragma unroll
-                for (int s = 0; s < NSUB; ++s) tma_load_4d(is + oG + s * NT_B, &P.mG, ix, iy, z0 + g, item.tracer_c + s, bar);
+                for (int s = 0; s < NSUB; ++s) tma_load_4d(is + oG + s * VT_B, &P.mG, ix, iy, z0 + g, item.tracer_c + s, bar);
             }
             if (item_var) tma_load_3d(is + oF, &P.mF[item.src], ix, iy, z0 + g, bar);
         };
         if (kind == 3) {
-            mbar_expect_tx(barP, 6u * NSUB * CBOX_B + NT_B);
+            mbar_expect_tx(barP, 6u * NSUB * CTP_B);
             for (int pz = -2; pz <= 3; ++pz) issue_C(pz, barP);
-            tma_load_3d(sbase + oW0, &P.mW, ix, iy, z0, barP);
             for (int g = 0; g < ZT_D; ++g) issue_group(g);
         }
         __syncwarp();
         const bool face_lane = kind == 1 || kind == 2;
         const unsigned aT = sbase + oC + 8u * (sub * SM::CTP + (ty + 3) * ZT_CW + tx + ZT_HX);
-        const unsigned aQ = sbase + (kind == 1 ? oV + 8u * (ty * 32 + tx) : oU + 8u * (ty * ZT_UW + tx));
-        const unsigned aF = sbase + (kind == 1 ? oFY + 8u * (sub * SM::VT + ty * 32 + tx) : oFX + 8u * (sub * SM::UT + ty * ZT_UW + tx));
+        const unsigned aQ = sbase + (kind == 1 ? oV + 8u * (ty * 32 + tx) : oU + 8u * (ty * ZT_CW + tx + ZT_HX));
+        const unsigned aF = sbase + (kind == 1 ? oFY + 8u * (sub * SM::VT + ty * 32 + tx)
+                                               : oFX + 8u * (sub * SM::CTP + (ty + 3) * ZT_CW + tx + ZT_HX));
         if (face_lane) mbar_wait(barP, 0);
         __syncwarp();
         block_barrier();                 // prologue barrier: see the main warps
-        for (int k = 0; k < Nz; ++k) {
-            if (kind == 3) {
-                if (k + ZT_D < Nz) issue_group(k + ZT_D);
-            } else if (face_lane) {
-                mbar_wait(bar0 + 8u * (k & (ZT_RI - 1)), (k / ZT_RI) & 1);
-                const unsigned cs = (unsigned)((k + 2) & (ZT_RC - 1)) * CSLOT_B;
-                const double q = lds(aQ + (unsigned)(k & (ZT_RI - 1)) * ISLOT_B);
-                const double cf = kind == 1 ? zt_face<ROW_B>(aT + cs, q, K) : zt_face<8>(aT + cs, q, K);
-                sts(aF + (unsigned)(k & 1) * FBUF_B, q * cf);
+        for (int k0 = 0; k0 < Nz; k0 += ZT_PB) {
+#pragma unroll
+            for (int p = 0; p < ZT_PB; ++p) {
+                const int k = k0 + p;
+                if (k >= Nz) break;
+                if (kind == 3) {
+                    if (k + ZT_D < Nz) issue_group(k + ZT_D);
+                } else if (face_lane) {
+                    mbar_wait(bar0 + 8u * (k & (ZT_RI - 1)), (k / ZT_RI) & 1);
+                    const unsigned cs = (unsigned)((k + 2) & (ZT_RC - 1)) * CSLOT_B;
+                    const double q = lds(aQ + (unsigned)(k & (ZT_RI - 1)) * ISLOT_B);
+                    const double cf = kind == 1 ? zt_face<ROW_B>(aT + cs, q, K) : zt_face<8>(aT + cs, q, K);
+                    sts(aF + (unsigned)(k & (ZT_RI - 1)) * FBUF_B, q * cf);
+                }
             }
             __syncwarp();
             block_barrier();
@@ -288,78 +310,97 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     // ============ main warps: one cell column of one tracer per thread ============
     const int t = tid % SM::NT, sub = tid / SM::NT;
     const int tx = t % ZT_TX, ty = t / ZT_TX;
-    const unsigned aC = sbase + oC + 8u * (sub * SM::CTP + (ty + 3) * ZT_CW + tx + ZT_HX);     // own cell in a tracer tile
-    const unsigned a32 = sbase + 8u * t;                                                    // pitch-32 tiles: v, w, G, f, Fy
-    const unsigned a34 = sbase + 8u * (ty * ZT_UW + tx);                                    // pitch-34 tiles: u, Fx
+    // the four address registers: own cell in the pitch-32 / pitch-40 tiles, shared by the tracers or per tracer
+    const unsigned a32 = sbase + 8u * t, a32s = a32 + sub * VT_B;
+    const unsigned a40 = sbase + 8u * (ty * ZT_CW + tx + ZT_HX), a40s = a40 + 3 * ROW_B + sub * CTP_B;
     const int partner_off = NSUB == 2 ? (sub ? -(int)CTP_B : (int)CTP_B) : 0;
     const bool active = j0 + ty < S.j1;                              // partial tiles at the end of the y range
-    const int64_t off0 = L.at(i0 + tx, j0 + ty, 0) + (int64_t)(item.tracer_c + sub) * L.len;
-    double *__restrict__ pUn = S.U_new + off0;
-    double *__restrict__ pG = S.G + off0;
     const int64_t plane = L.plane;
-    const bool need_var = item_var && sub == 0;
+    // rows beyond j1 (partial tiles) compute like the others but store into the scratch field
+    const int64_t cell0 = L.at(i0 + tx, j0 + ty, 0);
+    double *__restrict__ pUn = active ? S.U_new + cell0 + (int64_t)(item.tracer_c + sub) * L.len : P.scratch + cell0;
+    const int64_t g_off = active ? (S.G - S.U_new) : 0;              // pG = pUn + g_off
     // offsets of this column's periodic images in the halo (0 = none); y only when the y halo is not owned by a neighbour rank
     int64_t xwrap = 0, ywrap = 0;
-    {
+    if (active) {
         const int i = i0 + tx, j = j0 + ty;
         if (L.fuse_halo[0]) { if (i < L.H[0]) xwrap = L.N[0]; else if (i >= L.N[0] - L.H[0]) xwrap = -L.N[0]; }
         if (L.fuse_halo[1]) {
             if (j < L.H[1]) ywrap = (int64_t)L.N[1] * L.pitch; else if (j >= L.N[1] - L.H[1]) ywrap = -(int64_t)L.N[1] * L.pitch;
         }
     }
-    // forcing = k_src * src + (k_own * own + k_oth * partner)   (create_forcing, utils:731-865)
+    // block-uniform: does any column of this tile have a periodic image?
+    const bool tile_wraps = (L.fuse_halo[0] && (i0 < L.H[0] || i0 + ZT_TX > L.N[0] - L.H[0])) ||
+                            (L.fuse_halo[1] && (j0 < L.H[1] || j0 + TY > L.N[1] - L.H[1]));
+    // forcing = k_src * (src1 + src2) + (k_own * own + k_oth * partner)   (create_forcing, utils:731-865): the sources
+    // are two shared-memory values -- the variable and a zero, or the two faces of the cell for a map (k_src carries
+    // the 1/2 of the face average)
     double k_src, k_own, k_oth;
+    unsigned aS1, aS2;
     {
         const double c = item.c, d = item.d, n2 = c * c + d * d;
         k_own = -c;
         k_oth = NSUB == 1 ? 0.0 : (sub == 0 ? -d : d);
-        if (item.is_map) k_src = (NSUB == 2 && sub == 1) ? -d / n2 : -c / n2;
-        else             k_src = sub == 0 ? 1.0 : 0.0;
+        if (item.is_map) {
+            k_src = 0.5 * ((NSUB == 2 && sub == 1) ? -d / n2 : -c / n2);
+            if (item.src == 0)      { aS1 = a40 + oU; aS2 = aS1 + 8; }
+            else if (item.src == 1) { aS1 = a32 + oV; aS2 = aS1 + 8 * 32; }
+            else                    { aS1 = a32 + oW; aS2 = aS1 + NT_B; }
+        } else {
+            k_src = sub == 0 ? 1.0 : 0.0;
+            aS1 = a32 + oF; aS2 = sbase + oZ;
+        }
     }
-    const int map_axis = item.is_map ? item.src : -1;
     const double dtg = S.dt * S.gamma, dtz = S.dt * S.zeta;
     const double rdx = P.rd[0], rdy = P.rd[1], rdz = P.rd[2];
+    const double nrdx = -rdx, nrdy = -rdy;
 
     // ---- prologue: the z window of the column -------------------------------------------------------------
     double d0, d1, d2, d3, d4;                   // d[k-2..k+2], d[m] = c[m+1] - c[m]
-    double Qa, Qb, Qc, Qd;                       // Q[k-1..k+2], Q[m] = 13/3 (d[m] - d[m-1])^2
+    double Qa, Qb, Qc, Qd;                       // Q[k-1..k+2], Q[m] = 13/3 (d[m] - d[m-1])^2 + 4/3 eps
     double ck, ck1;                              // c[k], c[k+1]
-    double Fb, wb;
+    double Fb = 0.0;                             // flux through the bottom face of cell k
     mbar_wait(barP, 0);
     {
+        const unsigned aC = a40s + oC;
         const double cm2 = lds(aC + 0 * CSLOT_B), cm1 = lds(aC + 1 * CSLOT_B);
         ck = lds(aC + 2 * CSLOT_B); ck1 = lds(aC + 3 * CSLOT_B);
         const double ck2 = lds(aC + 4 * CSLOT_B), ck3 = lds(aC + 5 * CSLOT_B);
         d0 = cm1 - cm2; d1 = ck - cm1; d2 = ck1 - ck; d3 = ck2 - ck1; d4 = ck3 - ck2;
         double s;
-        s = d1 - d0; Qa = (K.k133 * s) * s;
-        s = d2 - d1; Qb = (K.k133 * s) * s;
-        s = d3 - d2; Qc = (K.k133 * s) * s;
-        s = d4 - d3; Qd = (K.k133 * s) * s;
-        wb = lds(a32 + oW0);
-        Fb = wb * ck;                                    // wall face m = 1: Centered2 on the mirrored halo
+        s = d1 - d0; Qa = fma(K.k133 * s, s, K.eps43);
+        s = d2 - d1; Qb = fma(K.k133 * s, s, K.eps43);
+        s = d3 - d2; Qc = fma(K.k133 * s, s, K.eps43);
+        s = d4 - d3; Qd = fma(K.k133 * s, s, K.eps43);
     }
     // The first in-loop TMA load reuses the ring slot of plane -2: every thread must have read its prologue values,
     // and (main threads pass this barrier only after their wait on barP) the prologue loads must have landed, before
     // the producer lane issues it.
     block_barrier();
 
-#pragma unroll 2
-    for (int k = 0; k < Nz; ++k) {
-        const unsigned is = (unsigned)(k & (ZT_RI - 1)) * ISLOT_B;
-        const unsigned cs = (unsigned)((k + 2) & (ZT_RC - 1)) * CSLOT_B;
-        const unsigned fb = (unsigned)(k & 1) * FBUF_B;
-        mbar_wait(bar0 + 8u * (k & (ZT_RI - 1)), (k / ZT_RI) & 1);
-        // ---- faces of plane k ----------------------------------------------------------------------------
-        const double cu = lds(a34 + oU + is), cv = lds(a32 + oV + is), cw = lds(a32 + oW + is);
-        double other = 0.0;
-        if (NSUB == 2) other = lds(aC + cs + partner_off);
-        const double Fw = cu * zt_face<8>(aC + cs, cu, K);
-        const double Fs = cv * zt_face<ROW_B>(aC + cs, cv, K);
-        sts(a34 + oFX + 8u * sub * SM::UT + fb, Fw);
-        sts(a32 + oFY + 8u * sub * SM::VT + fb, Fs);
+    double part[ZT_PB], base[ZT_PB];             // own part of the tendency / of the substep, carried over the barrier
+
+    // Faces and own tendency part of plane k.  J >= 0: k = 8 m + 2 + J is known modulo the ring period, so every
+    // ring offset, flux buffer and mbarrier parity is an immediate and the plane is interior (top face index
+    // m = k + 2 in 4 .. Nz - 2: WENO5); J < 0: any plane, everything computed from k.
+    auto plane_step = [&](const int k, auto jtag, const int p) {
+        constexpr int J = decltype(jtag)::value;
+        constexpr bool FAST = J >= 0;
+        const int kk = FAST ? 2 + J : k;         // k modulo 8 where it matters
+        const unsigned is = (unsigned)(kk & (ZT_RI - 1)) * ISLOT_B;
+        const unsigned fb = (unsigned)(kk & (ZT_RI - 1)) * FBUF_B;
+        const unsigned aCk = a40s + oC + (unsigned)((kk + 2) & (ZT_RC - 1)) * CSLOT_B;
+        mbar_wait(bar0 + 8u * (kk & (ZT_RI - 1)), (kk / ZT_RI) & 1);
+        const double cu = lds(a40 + oU + is), cv = lds(a32 + oV + is);
+        const double wb = lds(a32 + oW + is), cw = lds(a32 + oW + NT_B + is);
+        const double Fw = cu * zt_face<8>(aCk, cu, K);
+        const double Fs = cv * zt_face<ROW_B>(aCk, cv, K);
+        sts(a40s + oFX + fb, Fw);
+        sts(a32s + oFY + fb, Fs);
+        if (!FAST && k == 0) Fb = wb * ck;               // wall face m = 1: Centered2 on the mirrored halo
         double ct;
-        if (k >= 2 && k <= Nz - 4) {                     // top face of cell k: 1-based face index m = k + 2 in 4 .. Nz - 2
+        if (FAST || (k >= 2 && k <= Nz - 4)) {
+            // the window is used by a warp-uniform branch per direction (both only in warps that straddle w = 0)
             const bool left = cw > 0.0;
             const unsigned ml = __ballot_sync(0xffffffffu, left);
             double incL = 0.0, incR = 0.0;
@@ -370,47 +411,84 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             ct = zt_top_face_buffer(k + 2, Nz, cw, d1, d2, d3, ck, ck1);
         }
         const double Ft = cw * ct;
-        block_barrier();
-
-        // ---- tendency, RK3 substep, advance the window -------------------------------------------------
+        // ---- own part of the tendency: c du - dF per axis in units of face velocity, forcing, G^- part of the substep ----
+        const double ue = lds(a40 + oU + is + 8), vn = lds(a32 + oV + is + 8 * 32);
+        const double src = lds(aS1 + is) + lds(aS2 + is);
+        double forcing = fma(k_src, src, k_own * ck);
+        if (NSUB == 2) forcing = fma(k_oth, lds(aCk + partner_off), forcing);
+        const double az = fma(ck, cw - wb, Fb - Ft);
+        part[p] = fma(rdx, fma(ck, ue - cu, Fw), fma(rdy, fma(ck, vn - cv, Fs), fma(rdz, az, forcing)));
+        base[p] = S.first_stage ? ck : fma(dtz, lds(a32s + oG + is), ck);
+        // ---- advance the window to cell k+1: d[k+3] = c[k+4] - c[k+3] from the ring ----
         {
-            const double Fe = lds(a34 + oFX + 8u * sub * SM::UT + fb + 8), Fn = lds(a32 + oFY + 8u * sub * SM::VT + fb + 8 * 32);
-            const double ue = lds(a34 + oU + is + 8), vn = lds(a32 + oV + is + 8 * 32);
-            const double ax = fma(ck, ue - cu, Fw - Fe);          // c du - dF per axis, in units of face velocity
-            const double ay = fma(ck, vn - cv, Fs - Fn);
-            const double az = fma(ck, cw - wb, Fb - Ft);
-            double src;
-            if (map_axis >= 0) src = map_axis == 0 ? 0.5 * (cu + ue) : (map_axis == 1 ? 0.5 * (cv + vn) : 0.5 * (wb + cw));
-            else src = need_var ? lds(a32 + oF + is) : 0.0;
-            const double forcing = fma(k_src, src, fma(k_own, ck, k_oth * other));
-            const double Gn = fma(rdx, ax, fma(rdy, ay, fma(rdz, az, forcing)));
-            double unew;
-            if (S.first_stage) unew = fma(dtg, Gn, ck);
-            else               unew = fma(dtg, Gn, fma(dtz, lds(a32 + oG + 8u * sub * SM::NT + is), ck));
-            if (active) {
-                pUn[0] = unew;
-                // periodic halo images of the new state (the tracer halo fill of update_state!, fused)
-                if (xwrap) pUn[xwrap] = unew;
-                if (ywrap) { pUn[ywrap] = unew; if (xwrap) pUn[xwrap + ywrap] = unew; }
-                if (S.store_G) pG[0] = Gn;
-            }
-            // advance the window to cell k+1: d[k+3] = c[k+4] - c[k+3] from the ring
-            Fb = Ft; wb = cw;
-            const double c3 = lds(aC + (unsigned)((k + 5) & (ZT_RC - 1)) * CSLOT_B);
-            const double c4 = lds(aC + (unsigned)((k + 6) & (ZT_RC - 1)) * CSLOT_B);
+            Fb = Ft;
+            const unsigned aC = a40s + oC;
+            const double c2 = lds(aC + (unsigned)((kk + 4) & (ZT_RC - 1)) * CSLOT_B);
+            const double c3 = lds(aC + (unsigned)((kk + 5) & (ZT_RC - 1)) * CSLOT_B);
+            const double c4 = lds(aC + (unsigned)((kk + 6) & (ZT_RC - 1)) * CSLOT_B);
             const double dnew = c4 - c3;
             const double s = dnew - d4;
             d0 = d1; d1 = d2; d2 = d3; d3 = d4; d4 = dnew;
-            Qa = Qb; Qb = Qc; Qc = Qd; Qd = (K.k133 * s) * s;
-            ck = ck1;
-            ck1 = lds(aC + (unsigned)((k + 4) & (ZT_RC - 1)) * CSLOT_B);  // c[k+2]
+            Qa = Qb; Qb = Qc; Qc = Qd; Qd = fma(K.k133 * s, s, K.eps43);
+            ck = ck1; ck1 = c2;
         }
-        pUn += plane; pG += plane;
+    };
+    // neighbour fluxes of plane k (behind its barrier), RK3 substep, stores
+    auto finish_plane = [&](const int k, auto jtag, const int p) {
+        constexpr int J = decltype(jtag)::value;
+        const int kk = J >= 0 ? 2 + J : k;
+        const unsigned fb = (unsigned)(kk & (ZT_RI - 1)) * FBUF_B;
+        const double Fe = lds(a40s + oFX + fb + 8), Fn = lds(a32s + oFY + fb + 8 * 32);
+        const double Gn = fma(nrdx, Fe, fma(nrdy, Fn, part[p]));
+        const double unew = fma(dtg, Gn, base[p]);
+        pUn[0] = unew;
+        if (S.store_G) pUn[g_off] = Gn;
+        if (tile_wraps) {
+            // periodic halo images of the new state (the tracer halo fill of update_state!, fused)
+            if (xwrap) pUn[xwrap] = unew;
+            if (ywrap) { pUn[ywrap] = unew; if (xwrap) pUn[xwrap + ywrap] = unew; }
+        }
+        pUn += plane;
+    };
+    using Dyn = std::integral_constant<int, -1>;
+    // generic planes [ka, kb), ZT_PB per barrier
+    auto generic_range = [&](int ka, const int kb) {
+#pragma unroll 1
+        for (; ka < kb; ka += ZT_PB) {
+#pragma unroll
+            for (int p = 0; p < ZT_PB; ++p) if (ka + p < Nz) plane_step(ka + p, Dyn(), p);
+            block_barrier();
+#pragma unroll
+            for (int p = 0; p < ZT_PB; ++p) if (ka + p < Nz) finish_plane(ka + p, Dyn(), p);
+        }
+    };
+    static_assert(8 % ZT_PB == 0 && 2 % ZT_PB == 0, "ZT_PB must be 1 or 2");
+    int k = 2;
+    generic_range(0, 2);
+    // interior planes in chunks of the ring period: k = 2, 10, 18, ... while the whole chunk is interior
+#pragma unroll 1
+    for (; k + 7 <= Nz - 4; k += 8) {
+#define ZT_PLANE(J) plane_step(k + J, std::integral_constant<int, J>(), J % ZT_PB)
+#define ZT_FINISH(J) finish_plane(k + J, std::integral_constant<int, J>(), J % ZT_PB)
+#if ZT_PB == 2
+        ZT_PLANE(0); ZT_PLANE(1); block_barrier(); ZT_FINISH(0); ZT_FINISH(1);
+        ZT_PLANE(2); ZT_PLANE(3); block_barrier(); ZT_FINISH(2); ZT_FINISH(3);
+        ZT_PLANE(4); ZT_PLANE(5); block_barrier(); ZT_FINISH(4); ZT_FINISH(5);
+        ZT_PLANE(6); ZT_PLANE(7); block_barrier(); ZT_FINISH(6); ZT_FINISH(7);
+#else
+        ZT_PLANE(0); block_barrier(); ZT_FINISH(0); ZT_PLANE(1); block_barrier(); ZT_FINISH(1);
+        ZT_PLANE(2); block_barrier(); ZT_FINISH(2); ZT_PLANE(3); block_barrier(); ZT_FINISH(3);
+        ZT_PLANE(4); block_barrier(); ZT_FINISH(4); ZT_PLANE(5); block_barrier(); ZT_FINISH(5);
+        ZT_PLANE(6); block_barrier(); ZT_FINISH(6); ZT_PLANE(7); block_barrier(); ZT_FINISH(7);
+#endif
+#undef ZT_PLANE
+#undef ZT_FINISH
     }
+    generic_range(k, Nz);
 }
 
 #ifndef ZT_TY
-#define ZT_TY 6
+#define ZT_TY 8
 #endif
 
 // ---- host side --------------------------------------------------------------------------------------------------
@@ -432,15 +510,15 @@ static zt_encode_fn zt_encoder()
     return fn;
 }
 
-// tensor map over one field (rank 3) or a stack of n fields (rank 4) in the padded layout L, box bx x by x 1 (x 1)
-static int zt_make_map(CUtensorMap *m, const LfbLayout &L, const void *base, int n_stack, int bx, int by)
+// tensor map over one field (rank 3) or a stack of n fields (rank 4) in the padded layout L, box bx x by x bz (x 1)
+static int zt_make_map(CUtensorMap *m, const LfbLayout &L, const void *base, int n_stack, int bx, int by, int bz = 1)
 {
     zt_encode_fn enc = zt_encoder();
     if (!enc) return -1;
     const cuuint32_t rank = n_stack > 0 ? 4 : 3;
     cuuint64_t dim[4] = {(cuuint64_t)L.pitch, (cuuint64_t)L.rows, (cuuint64_t)L.planes, (cuuint64_t)(n_stack > 0 ? n_stack : 1)};
     cuuint64_t str[3] = {(cuuint64_t)L.pitch * 8, (cuuint64_t)L.plane * 8, (cuuint64_t)L.len * 8};
-    cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, const_cast<void *>(base), dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -481,14 +559,15 @@ static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
     int bad = 0;
     bad |= zt_make_map(&P.mC, L, S->U_old, n_t, ZT_CW, TY + 6);
     bad |= zt_make_map(&P.mG, L, S->G, n_t, 32, TY);
-    bad |= zt_make_map(&P.mU, L, S->vel[0], 0, ZT_UW, TY);
+    bad |= zt_make_map(&P.mU, L, S->vel[0], 0, ZT_CW, TY);
     bad |= zt_make_map(&P.mV, L, S->vel[1], 0, 32, TY + 1);
-    bad |= zt_make_map(&P.mW, L, S->vel[2], 0, 32, TY);
+    bad |= zt_make_map(&P.mW, L, S->vel[2], 0, 32, TY, 2);
     for (int q = 0; q < LFB_MAX_VARS; ++q)
         if (S->var[q]) bad |= zt_make_map(&P.mF[q], L, S->var[q], 0, 32, TY);
     if (bad) return cudaErrorInvalidValue;
     P.k133 = 13.0 / 3.0; P.k13 = 1.0 / 3.0; P.k16 = 1.0 / 6.0; P.eps43 = LFB_WENO_EPS * (4.0 / 3.0);
     for (int a = 0; a < 3; ++a) P.rd[a] = S->area[a] / S->volume;
+    P.scratch = S->scratch;
     const int ytiles = (S->j1 - S->j0 + TY - 1) / TY;
     dim3 grid(S->n_items * ytiles, L.N[0] / ZT_TX, 1);
     lfb_stage_ztma<NSUB, TY><<<grid, SM::THREADS, SM::BYTES, stream>>>(P);
