@@ -168,10 +168,14 @@ __device__ __forceinline__ double zt_inc_q(double dp, double do_, double dn, dou
 
 // Upwind face value at the low face of the cell at shared byte address `a` along the axis with byte stride S:
 // the stencil is read in upwind order (p, o, n | e, f), mirrored when the face velocity is not positive.
+// q > 0 decided on the high word (an integer compare instead of a two-cycle FP64 one).  Differs from q > 0.0 only for
+// positive q below 2^-1022 * 2^-20 (high word zero), where the flux q * face vanishes anyway.
+__device__ __forceinline__ bool zt_positive(double q) { return __double2hiint(q) > 0; }
+
 template <int S>
 __device__ __forceinline__ double zt_face(unsigned a, double q, const ZtK &K)
 {
-    const bool left = q > 0.0;
+    const bool left = zt_positive(q);
     const int step = left ? S : -S;
     const unsigned an = left ? a - S : a;
     const double n = lds(an), e = lds(an + step), o = lds(an - step);
@@ -287,13 +291,17 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         __syncwarp();
         block_barrier();                 // prologue barrier: see the main warps
         for (int k0 = 0; k0 < Nz; k0 += ZT_PB) {
+            // the loads of the next barrier interval are issued together at the start of this one, so the consumers
+            // can wait for them before this interval's barrier without stalling
+            if (kind == 3) {
+#pragma unroll
+                for (int p = 0; p < ZT_PB; ++p) if (k0 + ZT_D + p < Nz && (ZT_PB == ZT_D || p == 0)) issue_group(k0 + ZT_D + p);
+            }
 #pragma unroll
             for (int p = 0; p < ZT_PB; ++p) {
                 const int k = k0 + p;
                 if (k >= Nz) break;
-                if (kind == 3) {
-                    if (k + ZT_D < Nz) issue_group(k + ZT_D);
-                } else if (face_lane) {
+                if (face_lane) {
                     mbar_wait(bar0 + 8u * (k & (ZT_RI - 1)), (k / ZT_RI) & 1);
                     const unsigned cs = (unsigned)((k + 2) & (ZT_RC - 1)) * CSLOT_B;
                     const double q = lds(aQ + (unsigned)(k & (ZT_RI - 1)) * ISLOT_B);
@@ -358,14 +366,15 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     // ---- prologue: the z window of the column -------------------------------------------------------------
     double d0, d1, d2, d3, d4;                   // d[k-2..k+2], d[m] = c[m+1] - c[m]
     double Qa, Qb, Qc, Qd;                       // Q[k-1..k+2], Q[m] = 13/3 (d[m] - d[m-1])^2 + 4/3 eps
-    double ck, ck1;                              // c[k], c[k+1]
-    double Fb = 0.0;                             // flux through the bottom face of cell k
+    double ck, ck1, ck3;                         // c[k], c[k+1], c[k+3]
+    double Fb = 0.0, wb = 0.0;                   // flux through / w at the bottom face of cell k
     mbar_wait(barP, 0);
     {
         const unsigned aC = a40s + oC;
         const double cm2 = lds(aC + 0 * CSLOT_B), cm1 = lds(aC + 1 * CSLOT_B);
         ck = lds(aC + 2 * CSLOT_B); ck1 = lds(aC + 3 * CSLOT_B);
-        const double ck2 = lds(aC + 4 * CSLOT_B), ck3 = lds(aC + 5 * CSLOT_B);
+        const double ck2 = lds(aC + 4 * CSLOT_B);
+        ck3 = lds(aC + 5 * CSLOT_B);
         d0 = cm1 - cm2; d1 = ck - cm1; d2 = ck1 - ck; d3 = ck2 - ck1; d4 = ck3 - ck2;
         double s;
         s = d1 - d0; Qa = fma(K.k133 * s, s, K.eps43);
@@ -390,9 +399,9 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         const unsigned is = (unsigned)(kk & (ZT_RI - 1)) * ISLOT_B;
         const unsigned fb = (unsigned)(kk & (ZT_RI - 1)) * FBUF_B;
         const unsigned aCk = a40s + oC + (unsigned)((kk + 2) & (ZT_RC - 1)) * CSLOT_B;
-        mbar_wait(bar0 + 8u * (kk & (ZT_RI - 1)), (kk / ZT_RI) & 1);
         const double cu = lds(a40 + oU + is), cv = lds(a32 + oV + is);
-        const double wb = lds(a32 + oW + is), cw = lds(a32 + oW + NT_B + is);
+        const double cw = lds(a32 + oW + NT_B + is);
+        if (!FAST && k == 0) wb = lds(a32 + oW + is);
         const double Fw = cu * zt_face<8>(aCk, cu, K);
         const double Fs = cv * zt_face<ROW_B>(aCk, cv, K);
         sts(a40s + oFX + fb, Fw);
@@ -401,12 +410,12 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         double ct;
         if (FAST || (k >= 2 && k <= Nz - 4)) {
             // the window is used by a warp-uniform branch per direction (both only in warps that straddle w = 0)
-            const bool left = cw > 0.0;
+            const bool left = zt_positive(cw);
             const unsigned ml = __ballot_sync(0xffffffffu, left);
-            double incL = 0.0, incR = 0.0;
-            if (ml != 0u) incL = zt_inc_q(d0, d1, d2, d3, Qa, Qb, Qc, K);
-            if (ml != 0xffffffffu) incR = zt_inc_q(d4, d3, d2, d1, Qd, Qc, Qb, K);
-            ct = left ? ck + incL : ck1 - incR;
+            double ctL = ck, ctR = ck1;
+            if (ml != 0u) ctL = ck + zt_inc_q(d0, d1, d2, d3, Qa, Qb, Qc, K);
+            if (ml != 0xffffffffu) ctR = ck1 - zt_inc_q(d4, d3, d2, d1, Qd, Qc, Qb, K);
+            ct = left ? ctL : ctR;
         } else {
             ct = zt_top_face_buffer(k + 2, Nz, cw, d1, d2, d3, ck, ck1);
         }
@@ -421,17 +430,23 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         base[p] = S.first_stage ? ck : fma(dtz, lds(a32s + oG + is), ck);
         // ---- advance the window to cell k+1: d[k+3] = c[k+4] - c[k+3] from the ring ----
         {
-            Fb = Ft;
-            const unsigned aC = a40s + oC;
-            const double c2 = lds(aC + (unsigned)((kk + 4) & (ZT_RC - 1)) * CSLOT_B);
-            const double c3 = lds(aC + (unsigned)((kk + 5) & (ZT_RC - 1)) * CSLOT_B);
-            const double c4 = lds(aC + (unsigned)((kk + 6) & (ZT_RC - 1)) * CSLOT_B);
-            const double dnew = c4 - c3;
+            Fb = Ft; wb = cw;
+            const double c2 = lds(a40s + oC + (unsigned)((kk + 4) & (ZT_RC - 1)) * CSLOT_B);
+            const double c4 = lds(a40s + oC + (unsigned)((kk + 6) & (ZT_RC - 1)) * CSLOT_B);
+            const double dnew = c4 - ck3;
             const double s = dnew - d4;
             d0 = d1; d1 = d2; d2 = d3; d3 = d4; d4 = dnew;
             Qa = Qb; Qb = Qc; Qc = Qd; Qd = fma(K.k133 * s, s, K.eps43);
-            ck = ck1; ck1 = c2;
+            ck = ck1; ck1 = c2; ck3 = c4;
         }
+    };
+    // wait for the TMA group of plane k.  It is called before the barrier of the interval before, so that the code
+    // from one barrier to the next wait is a single basic block in which the finish of the planes just synchronised
+    // and the loads of the next planes overlap.
+    auto wait_plane = [&](const int k, auto jtag) {
+        constexpr int J = decltype(jtag)::value;
+        const int kk = J >= 0 ? 2 + J : k;
+        mbar_wait(bar0 + 8u * (kk & (ZT_RI - 1)), (kk / ZT_RI) & 1);
     };
     // neighbour fluxes of plane k (behind its barrier), RK3 substep, stores
     auto finish_plane = [&](const int k, auto jtag, const int p) {
@@ -457,6 +472,8 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         for (; ka < kb; ka += ZT_PB) {
 #pragma unroll
             for (int p = 0; p < ZT_PB; ++p) if (ka + p < Nz) plane_step(ka + p, Dyn(), p);
+#pragma unroll
+            for (int p = 0; p < ZT_PB; ++p) if (ka + ZT_PB + p < Nz) wait_plane(ka + ZT_PB + p, Dyn());
             block_barrier();
 #pragma unroll
             for (int p = 0; p < ZT_PB; ++p) if (ka + p < Nz) finish_plane(ka + p, Dyn(), p);
@@ -464,25 +481,29 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     };
     static_assert(8 % ZT_PB == 0 && 2 % ZT_PB == 0, "ZT_PB must be 1 or 2");
     int k = 2;
+#pragma unroll
+    for (int p = 0; p < ZT_PB; ++p) wait_plane(p, Dyn());
     generic_range(0, 2);
     // interior planes in chunks of the ring period: k = 2, 10, 18, ... while the whole chunk is interior
 #pragma unroll 1
     for (; k + 7 <= Nz - 4; k += 8) {
 #define ZT_PLANE(J) plane_step(k + J, std::integral_constant<int, J>(), J % ZT_PB)
 #define ZT_FINISH(J) finish_plane(k + J, std::integral_constant<int, J>(), J % ZT_PB)
+#define ZT_WAIT(J) wait_plane(k + J, std::integral_constant<int, J>())
 #if ZT_PB == 2
-        ZT_PLANE(0); ZT_PLANE(1); block_barrier(); ZT_FINISH(0); ZT_FINISH(1);
-        ZT_PLANE(2); ZT_PLANE(3); block_barrier(); ZT_FINISH(2); ZT_FINISH(3);
-        ZT_PLANE(4); ZT_PLANE(5); block_barrier(); ZT_FINISH(4); ZT_FINISH(5);
-        ZT_PLANE(6); ZT_PLANE(7); block_barrier(); ZT_FINISH(6); ZT_FINISH(7);
+        ZT_PLANE(0); ZT_PLANE(1); ZT_WAIT(2); ZT_WAIT(3); block_barrier(); ZT_FINISH(0); ZT_FINISH(1);
+        ZT_PLANE(2); ZT_PLANE(3); ZT_WAIT(4); ZT_WAIT(5); block_barrier(); ZT_FINISH(2); ZT_FINISH(3);
+        ZT_PLANE(4); ZT_PLANE(5); ZT_WAIT(6); ZT_WAIT(7); block_barrier(); ZT_FINISH(4); ZT_FINISH(5);
+        ZT_PLANE(6); ZT_PLANE(7); ZT_WAIT(8); ZT_WAIT(9); block_barrier(); ZT_FINISH(6); ZT_FINISH(7);
 #else
-        ZT_PLANE(0); block_barrier(); ZT_FINISH(0); ZT_PLANE(1); block_barrier(); ZT_FINISH(1);
-        ZT_PLANE(2); block_barrier(); ZT_FINISH(2); ZT_PLANE(3); block_barrier(); ZT_FINISH(3);
-        ZT_PLANE(4); block_barrier(); ZT_FINISH(4); ZT_PLANE(5); block_barrier(); ZT_FINISH(5);
-        ZT_PLANE(6); block_barrier(); ZT_FINISH(6); ZT_PLANE(7); block_barrier(); ZT_FINISH(7);
+        ZT_PLANE(0); ZT_WAIT(1); block_barrier(); ZT_FINISH(0); ZT_PLANE(1); ZT_WAIT(2); block_barrier(); ZT_FINISH(1);
+        ZT_PLANE(2); ZT_WAIT(3); block_barrier(); ZT_FINISH(2); ZT_PLANE(3); ZT_WAIT(4); block_barrier(); ZT_FINISH(3);
+        ZT_PLANE(4); ZT_WAIT(5); block_barrier(); ZT_FINISH(4); ZT_PLANE(5); ZT_WAIT(6); block_barrier(); ZT_FINISH(5);
+        ZT_PLANE(6); ZT_WAIT(7); block_barrier(); ZT_FINISH(6); ZT_PLANE(7); ZT_WAIT(8); block_barrier(); ZT_FINISH(7);
 #endif
 #undef ZT_PLANE
 #undef ZT_FINISH
+#undef ZT_WAIT
     }
     generic_range(k, Nz);
 }
