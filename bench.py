@@ -319,10 +319,21 @@ def main():
         stage_avg_ms = stage_ms / max(stage_n, 1)
         bytes_per_launch = cells_local * algorithmic_bytes_per_cell_step() / 3.0
         achieved = bytes_per_launch / (stage_avg_ms * 1e-3) / 1e9
+        # DRAM bytes per launch of this kernel on this grid from the committed `ncu --set full` capture (it cannot be
+        # measured from inside the bench); null for configurations that were not captured
+        traffic = None
+        try:
+            for cap in json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))):
+                if cap["kernel"] == m.kernel_name and cap["grid"] == list(args.size) and cap["n_gpus"] == world:
+                    traffic = cap["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": m.kernel_name, "launch_ms": stage_avg_ms, "peak_source": which,
+                    "traffic": traffic, "kernel": m.kernel_name, "launch_ms": stage_avg_ms, "peak_source": which,
                     "algorithmic_bytes_per_launch": bytes_per_launch,
-                    "note": "FP64 WENO5-Z is FP64-pipe bound before it is HBM bound; see DESIGN.md"}
+                    "note": "FP64 WENO5-Z is bound by the warp schedulers' issue port (an FP64 instruction holds it for two "
+                            "cycles) before it is HBM bound: with no other instruction at all the ceiling would be 58 % of "
+                            "the HBM peak; see DESIGN.md section 5"}
         cpu = None
         if not args.no_cpu and world == 1:
             rate, cms = cpu_port_rate(args.cpu_size, 2, 1)
