@@ -4,7 +4,7 @@
 
 Every rank steps its y-slab of a small 3-D problem (NCCL halo exchange overlapped with the interior)
 and, on the same GPU, the undecomposed problem; the slab must reproduce its rows of the global run:
-bit-exact with the strict generic kernel, <= 1e-12 with the z-marching kernel.  Prints one line per
+bit-exact with the strict generic kernel, <= 1e-12 with the z-marching kernels (cp.async and TMA-staged).  Prints one line per
 kernel from rank 0 and exits non-zero on mismatch."""
 import os
 import sys
@@ -35,7 +35,9 @@ def main():
     ok = True
     for topo_y, kernel, strict, size in (("Periodic", "generic", True, (32, 16 * world, 10)),
                                          ("Bounded", "generic", True, (32, 16 * world, 10)),
-                                         ("Periodic", "zmarch", False, (64, 32 * world, 16))):
+                                         ("Periodic", "zmarch", False, (64, 32 * world, 16)),
+                                         ("Periodic", "ztma", False, (64, 32 * world, 24)),
+                                         ("Periodic", "ztma", False, (32, 20 * world, 12))):
         g = lfb200.RectilinearGrid(size=size, extent=tuple(float(s) for s in size), topology=("Periodic", topo_y, "Bounded"))
         var_names, vel_names = ("T", "b"), ("u", "v", "w")
         times = [0.0, 0.5, 1.0]
