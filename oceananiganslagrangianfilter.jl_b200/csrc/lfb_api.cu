@@ -702,6 +702,12 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
             const double *b = h->slot_field[(size_t)s2 * N_FIELD_IDS + f];
             const bool neg = backward && f < 3;
             const double *use = a;
+            if (f >= 3 && h->use_zmarch == 3 && update) {
+                // the TMA z-march kernel reads both snapshots of a variable and interpolates in its forcing term
+                P.var_fused = 1; P.var_w1 = w1; P.var_w2 = w2;
+                P.var[f - 3] = a; P.var2[f - 3] = interp ? b : a;
+                continue;
+            }
             if (interp || neg) {
                 const int q = I.n_fields++;
                 I.s1[q] = a; I.s2[q] = b; I.dst[q] = h->cur_in[f]; I.negate[q] = neg;

@@ -76,6 +76,11 @@ struct LfbStageParams {
     // the halo exchange): cells j in [j0, j1)
     int     j0, j1;
     double *scratch;          // one spare field (store target of inactive rows in partial tiles of the z-march kernels)
+    // var_fused: the original variables are NOT interpolated in time by lfb_interp_inputs; var[q] / var2[q] are the two
+    // bracketing snapshots and the stage kernel forms var_w1 * var[q] + var_w2 * var2[q] itself (TMA z-march kernel)
+    int     var_fused;
+    const double *var2[LFB_MAX_VARS];
+    double  var_w1, var_w2;
 };
 
 // Output combinations (create_output_fields, utils:898-1012): out = sum_i wc[i] U[tc[i]] + ws[i] U[tc[i]+1]

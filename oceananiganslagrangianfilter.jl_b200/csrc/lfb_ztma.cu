@@ -53,7 +53,8 @@ struct LfbZtParams {
     alignas(64) CUtensorMap mU;                  // u            (x, y, z),         box 40 x TY
     alignas(64) CUtensorMap mV;                  // v                               box 32 x (TY+1)
     alignas(64) CUtensorMap mW;                  // w                               box 32 x TY x 2 (bottom and top faces)
-    alignas(64) CUtensorMap mF[LFB_MAX_VARS];    // original variables              box 32 x TY
+    alignas(64) CUtensorMap mF[LFB_MAX_VARS];    // original variables, snapshot at or before the stage time, box 32 x TY
+    alignas(64) CUtensorMap mF2[LFB_MAX_VARS];   // ... snapshot after it (linear interpolation in the forcing term)
     double k133, k13, k16, eps43, rd[3];         // 13/3, 1/3, 1/6, 4/3 eps, area / volume per axis
     double *scratch;                             // one field: store target of the rows beyond j1 in partial tiles
 };
@@ -69,8 +70,8 @@ struct ZtSmem {
     static constexpr int UT = TY * ZT_CW;                        // [TY][40]
     static constexpr int VT = (TY + 1) * 32;                     // [TY+1][32]
     static constexpr int OFF_U = 0, OFF_V = UT, OFF_W = OFF_V + VT, OFF_G = OFF_W + 2 * NT, OFF_F = OFF_G + NSUB * VT,
-                         OFF_Z = OFF_F + NT;                     // a zero (second source of a filtered variable)
-    static constexpr int ISLOT = OFF_Z + 16;                     // doubles per input slot
+                         OFF_F2 = OFF_F + NT;                    // forcing variable: the two bracketing snapshots
+    static constexpr int ISLOT = OFF_F2 + NT;                    // doubles per input slot
     static constexpr int CSLOT = NSUB * CTP;
     static constexpr int FBUF = NSUB * (CTP + VT);               // Fx[NSUB] (tracer-tile geometry), Fy[NSUB][TY+1][32]
     static constexpr int O_C = 0;
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
                        VT_B = 8u * SM::VT, NT_B = 8u * SM::NT;
     constexpr unsigned oC = 8u * SM::O_C, oIN = 8u * SM::O_IN, oFL = 8u * SM::O_FL, oBAR = 8u * SM::O_BAR;
     constexpr unsigned oU = oIN + 8u * SM::OFF_U, oV = oIN + 8u * SM::OFF_V, oW = oIN + 8u * SM::OFF_W,
-                       oG = oIN + 8u * SM::OFF_G, oF = oIN + 8u * SM::OFF_F, oZ = oIN + 8u * SM::OFF_Z;
+                       oG = oIN + 8u * SM::OFF_G, oF = oIN + 8u * SM::OFF_F, oF2 = oIN + 8u * SM::OFF_F2;
     constexpr unsigned oFX = oFL, oFY = oFL + NSUB * CTP_B;
     const LfbStageParams &S = P.S;
     const LfbLayout &L = S.L;
@@ -239,7 +240,6 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         for (int b = 0; b <= ZT_RI; ++b) mbar_init(bar0 + 8u * b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < ZT_RI) sts(sbase + oZ + tid * ISLOT_B, 0.0);
     __syncthreads();
 
     if (tid >= SM::NMAIN) {
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         // One loop for the whole warp (bar.sync is warp-aligned): the producer lane issues the TMA loads of the planes
         // ZT_D ahead, the face lanes compute their edge faces, idle lanes only keep the barrier count.
         const int cx = L.xoff + i0 - ZT_HX, cy = L.H[1] + j0 - 3, ix = L.xoff + i0, iy = L.H[1] + j0, z0 = L.H[2];
-        const unsigned in_bytes = 8u * (ZT_CW * TY + 32 * (TY + 1) + 2 * 32 * TY) + (use_G ? NSUB * NT_B : 0u) + (item_var ? NT_B : 0u);
+        const unsigned in_bytes = 8u * (ZT_CW * TY + 32 * (TY + 1) + 2 * 32 * TY) + (use_G ? NSUB * NT_B : 0u) + (item_var ? 2 * NT_B : 0u);
         auto issue_C = [&](int pz, unsigned bar) {            // haloed tracer planes at z index pz (-2 .. Nz+2)
             const unsigned dst = sbase + oC + (unsigned)((pz + 2) & (ZT_RC - 1)) * CSLOT_B;
 #pragma unroll
@@ -274,7 +274,10 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
 #pragma unroll
                 for (int s = 0; s < NSUB; ++s) tma_load_4d(is + oG + s * VT_B, &P.mG, ix, iy, z0 + g, item.tracer_c + s, bar);
             }
-            if (item_var) tma_load_3d(is + oF, &P.mF[item.src], ix, iy, z0 + g, bar);
+            if (item_var) {
+                tma_load_3d(is + oF, &P.mF[item.src], ix, iy, z0 + g, bar);
+                tma_load_3d(is + oF2, &P.mF2[item.src], ix, iy, z0 + g, bar);
+            }
         };
         if (kind == 3) {
             mbar_expect_tx(barP, 6u * NSUB * CTP_B);
@@ -340,23 +343,24 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     // block-uniform: does any column of this tile have a periodic image?
     const bool tile_wraps = (L.fuse_halo[0] && (i0 < L.H[0] || i0 + ZT_TX > L.N[0] - L.H[0])) ||
                             (L.fuse_halo[1] && (j0 < L.H[1] || j0 + TY > L.N[1] - L.H[1]));
-    // forcing = k_src * (src1 + src2) + (k_own * own + k_oth * partner)   (create_forcing, utils:731-865): the sources
-    // are two shared-memory values -- the variable and a zero, or the two faces of the cell for a map (k_src carries
-    // the 1/2 of the face average)
-    double k_src, k_own, k_oth;
+    // forcing = kA * src1 + kB * src2 + (k_own * own + k_oth * partner)   (create_forcing, utils:731-865).  The sources
+    // are two shared-memory values: the two faces of the cell for a map (kA = kB carry the 1/2 of the face average),
+    // the two bracketing snapshots of the variable for a filtered variable (kA, kB = the weights of the linear
+    // interpolation in time of update_input_data!, utils:1036-1058)
+    double kA, kB, k_own, k_oth;
     unsigned aS1, aS2;
     {
         const double c = item.c, d = item.d, n2 = c * c + d * d;
         k_own = -c;
         k_oth = NSUB == 1 ? 0.0 : (sub == 0 ? -d : d);
         if (item.is_map) {
-            k_src = 0.5 * ((NSUB == 2 && sub == 1) ? -d / n2 : -c / n2);
+            kA = kB = 0.5 * ((NSUB == 2 && sub == 1) ? -d / n2 : -c / n2);
             if (item.src == 0)      { aS1 = a40 + oU; aS2 = aS1 + 8; }
             else if (item.src == 1) { aS1 = a32 + oV; aS2 = aS1 + 8 * 32; }
             else                    { aS1 = a32 + oW; aS2 = aS1 + NT_B; }
         } else {
-            k_src = sub == 0 ? 1.0 : 0.0;
-            aS1 = a32 + oF; aS2 = sbase + oZ;
+            kA = sub == 0 ? S.var_w1 : 0.0; kB = sub == 0 ? S.var_w2 : 0.0;
+            aS1 = a32 + oF; aS2 = a32 + oF2;
         }
     }
     const double dtg = S.dt * S.gamma, dtz = S.dt * S.zeta;
@@ -422,8 +426,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         const double Ft = cw * ct;
         // ---- own part of the tendency: c du - dF per axis in units of face velocity, forcing, G^- part of the substep ----
         const double ue = lds(a40 + oU + is + 8), vn = lds(a32 + oV + is + 8 * 32);
-        const double src = lds(aS1 + is) + lds(aS2 + is);
-        double forcing = fma(k_src, src, k_own * ck);
+        double forcing = fma(kA, lds(aS1 + is), fma(kB, lds(aS2 + is), k_own * ck));
         if (NSUB == 2) forcing = fma(k_oth, lds(aCk + partner_off), forcing);
         const double az = fma(ck, cw - wb, Fb - Ft);
         part[p] = fma(rdx, fma(ck, ue - cu, Fw), fma(rdy, fma(ck, vn - cv, Fs), fma(rdz, az, forcing)));
@@ -583,8 +586,13 @@ static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
     bad |= zt_make_map(&P.mU, L, S->vel[0], 0, ZT_CW, TY);
     bad |= zt_make_map(&P.mV, L, S->vel[1], 0, 32, TY + 1);
     bad |= zt_make_map(&P.mW, L, S->vel[2], 0, 32, TY, 2);
+    LfbStageParams &SS = P.S;
+    if (!SS.var_fused) { SS.var_w1 = 1.0; SS.var_w2 = 0.0; }         // inputs already interpolated: one source
     for (int q = 0; q < LFB_MAX_VARS; ++q)
-        if (S->var[q]) bad |= zt_make_map(&P.mF[q], L, S->var[q], 0, 32, TY);
+        if (S->var[q]) {
+            bad |= zt_make_map(&P.mF[q], L, S->var[q], 0, 32, TY);
+            bad |= zt_make_map(&P.mF2[q], L, S->var_fused ? S->var2[q] : S->var[q], 0, 32, TY);
+        }
     if (bad) return cudaErrorInvalidValue;
     P.k133 = 13.0 / 3.0; P.k13 = 1.0 / 3.0; P.k16 = 1.0 / 6.0; P.eps43 = LFB_WENO_EPS * (4.0 / 3.0);
     for (int a = 0; a < 3; ++a) P.rd[a] = S->area[a] / S->volume;
