@@ -180,7 +180,7 @@ int lfb_combine(lfb_handle *h, int64_t n, const double *fwd, const double *bwd_l
 
 /* ---- remap to the mean position (regrid_to_mean_position!, post:327-762) ------------------------ */
 typedef struct lfb_remap_desc {
-    int32_t size[3], halo[3], topology[3];   /* grid: exactly two axes must be non-Flat                  */
+    int32_t size[3], halo[3], topology[3];   /* grid: two or three axes must be non-Flat                 */
     double  origin[3], spacing[3];           /* first face coordinate and spacing per axis               */
     int32_t has_map[3];                      /* a xi map exists for this axis (velocity in velocity_names) */
     int32_t npad;                            /* config.npad: periodic padding in cells (post:527-611)    */
@@ -191,8 +191,9 @@ typedef struct lfb_remap_desc {
 /* For one output time: interpolate every field from the displaced positions x + xi to the grid nodes:
  * xi[axis] = parent array of xi_<vel> for that axis (NULL if no map), fields[v] / out[v] = parent arrays.
  * Piecewise-linear interpolation on the Delaunay triangulation of the normalised, periodically padded
- * cloud (scipy LinearNDInterpolator in the reference), 1-D edge rows on Bounded axes (numpy.interp),
- * halos zero, NaN outside the hull.  The triangle search is shared by all fields. */
+ * cloud (scipy LinearNDInterpolator in the reference; tetrahedra on grids with three non-Flat axes), the
+ * reference's edge fix on Bounded axes (numpy.interp along edge rows in 2-D, a 2-D interpolation on the
+ * edge planes in 3-D), halos zero, NaN outside the hull.  The simplex search is shared by all fields. */
 int lfb_remap_to_mean(const lfb_remap_desc *desc, const double *const *xi, int n_fields, const double *const *fields,
                       double *const *out);
 

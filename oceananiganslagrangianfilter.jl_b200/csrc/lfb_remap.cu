@@ -59,7 +59,9 @@ __device__ __forceinline__ bool image_position(const RemapParams &P, int q, int 
     const int m = w + (int)fl;                 // image index relative to the wrapped point
     if (m == 0) { x = Xw; return true; }
     if (m == -1 && Xw > lo + P.L[q] - P.pad[q] && Xw < lo + P.L[q]) { x = Xw - P.L[q]; return true; }
-    if (m == 1 && Xw < lo + P.pad[q] && Xw > lo) { x = Xw + P.L[q]; return true; }
+    // one copy per point: the reference shifts its copy down first, and a copy that was shifted down is not shifted up
+    // again (post:537-541), so on an axis shorter than 2 npad cells the points within `pad` of both ends have no upper copy
+    if (m == 1 && Xw < lo + P.pad[q] && Xw > lo && !(Xw > lo + P.L[q] - P.pad[q])) { x = Xw + P.L[q]; return true; }
     return false;
 }
 
@@ -205,9 +207,380 @@ __global__ void lfb_remap2d_edge(const RemapParams P, const double *__restrict__
     out[(int64_t)(i + P.H[od]) * P.stride[od] + (int64_t)(edge + P.H[bd]) * P.stride[bd]] = res;
 }
 
+// ======================================================================================================================
+// Three non-Flat axes.  Same idea one dimension up: the Delaunay tetrahedron that contains a node is built locally.
+// The nearest data point a and its nearest neighbour b form a Delaunay edge; the point c with the smallest circumcircle
+// through a, b makes (a, b, c) a Delaunay face (the sphere having that circle as a great circle is empty: any point
+// inside it would give a smaller circle through a, b); the Delaunay tetrahedron on the node's side of a face (a, b, c)
+// is completed by the point d whose circumsphere centre lies lowest along the face normal; if the node is outside
+// (a, b, c, d) the walk continues through the face with the most negative barycentric coordinate.  The circumsphere of
+// the tetrahedron found is checked against the patch of lattice neighbours that was searched.
+struct RemapAxis {
+    int     n, H, periodic, has_map, r;
+    double  origin, delta, L, mn, rg, pad, maxdisp;
+    int64_t stride;
+};
+struct Remap3Params { RemapAxis ax[3]; };
+
+// as image_position, for one RemapAxis (reference padding rule: post:427-429, 527-611)
+__device__ __forceinline__ bool axis_image(const RemapAxis &A, int qi, int w, double disp, double &x)
+{
+    const double lo = A.origin;
+    const double X = lo + A.delta * (qi + 0.5) + disp;
+    if (!A.periodic) { x = X; return true; }
+    const double fl = floor((X - lo) / A.L);
+    const double Xw = X - fl * A.L;
+    const int m = w + (int)fl;
+    if (m == 0) { x = Xw; return true; }
+    if (m == -1 && Xw > lo + A.L - A.pad && Xw < lo + A.L) { x = Xw - A.L; return true; }
+    if (m == 1 && Xw < lo + A.pad && Xw > lo && !(Xw > lo + A.L - A.pad)) { x = Xw + A.L; return true; }    // see image_position
+    return false;
+}
+
+struct Cand3 { double x, y, z; int64_t idx; int p0, p1, p2; };
+
+__device__ __forceinline__ bool candidate3(const Remap3Params &P, const double *__restrict__ xi0, const double *__restrict__ xi1,
+                                           const double *__restrict__ xi2, int p0, int p1, int p2, Cand3 &c)
+{
+    int q[3] = {p0, p1, p2}, w[3] = {0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const RemapAxis &A = P.ax[a];
+        if (A.periodic) { while (q[a] < 0) { q[a] += A.n; --w[a]; } while (q[a] >= A.n) { q[a] -= A.n; ++w[a]; } }
+        else if (q[a] < 0 || q[a] >= A.n) return false;
+    }
+    const int64_t idx = (int64_t)(q[0] + P.ax[0].H) * P.ax[0].stride + (int64_t)(q[1] + P.ax[1].H) * P.ax[1].stride +
+                        (int64_t)(q[2] + P.ax[2].H) * P.ax[2].stride;
+    double x0, x1, x2;
+    if (!axis_image(P.ax[0], q[0], w[0], P.ax[0].has_map ? xi0[idx] : 0.0, x0)) return false;
+    if (!axis_image(P.ax[1], q[1], w[1], P.ax[1].has_map ? xi1[idx] : 0.0, x1)) return false;
+    if (!axis_image(P.ax[2], q[2], w[2], P.ax[2].has_map ? xi2[idx] : 0.0, x2)) return false;
+    c.x = (x0 - P.ax[0].mn) / P.ax[0].rg;
+    c.y = (x1 - P.ax[1].mn) / P.ax[1].rg;
+    c.z = (x2 - P.ax[2].mn) / P.ax[2].rg;
+    c.idx = idx; c.p0 = p0; c.p1 = p1; c.p2 = p2;
+    return true;
+}
+
+__device__ __forceinline__ bool same3(const Cand3 &a, int p0, int p1, int p2) { return a.p0 == p0 && a.p1 == p1 && a.p2 == p2; }
+
+// 6 x signed volume of (a, b, c, d): positive when d lies on the side of plane (a, b, c) its normal (b-a) x (c-a) points to
+__device__ __forceinline__ double orient3(const Cand3 &a, const Cand3 &b, const Cand3 &c, double dx, double dy, double dz)
+{
+    const double bx = b.x - a.x, by = b.y - a.y, bz = b.z - a.z, cx = c.x - a.x, cy = c.y - a.y, cz = c.z - a.z;
+    const double ex = dx - a.x, ey = dy - a.y, ez = dz - a.z;
+    return (by * cz - bz * cy) * ex + (bz * cx - bx * cz) * ey + (bx * cy - by * cx) * ez;
+}
+
+// one thread per interior node: Delaunay tetrahedron containing the node + barycentric weights
+__global__ void lfb_remap3d_locate(const Remap3Params P, const double *__restrict__ xi0, const double *__restrict__ xi1,
+                                   const double *__restrict__ xi2, int64_t *__restrict__ tet, double *__restrict__ wgt,
+                                   int *__restrict__ too_small)
+{
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+    if (i0 >= P.ax[0].n) return;
+    const int64_t node = ((int64_t)i2 * P.ax[1].n + i1) * P.ax[0].n + i0;
+    const double qx = (P.ax[0].origin + P.ax[0].delta * (i0 + 0.5) - P.ax[0].mn) / P.ax[0].rg;
+    const double qy = (P.ax[1].origin + P.ax[1].delta * (i1 + 0.5) - P.ax[1].mn) / P.ax[1].rg;
+    const double qz = (P.ax[2].origin + P.ax[2].delta * (i2 + 0.5) - P.ax[2].mn) / P.ax[2].rg;
+    const int r0 = P.ax[0].r, r1 = P.ax[1].r, r2 = P.ax[2].r;
+    Cand3 a, b, c, d, t;
+    auto none = [&]() {
+        for (int v = 0; v < 4; ++v) { tet[4 * node + v] = -1; wgt[4 * node + v] = 0.0; }
+    };
+    // a: nearest data point to the node
+    double best = INFINITY;
+    bool have = false;
+    for (int d2 = -r2; d2 <= r2; ++d2)
+        for (int d1 = -r1; d1 <= r1; ++d1)
+            for (int d0 = -r0; d0 <= r0; ++d0) {
+                if (!candidate3(P, xi0, xi1, xi2, i0 + d0, i1 + d1, i2 + d2, t)) continue;
+                const double dd = (t.x - qx) * (t.x - qx) + (t.y - qy) * (t.y - qy) + (t.z - qz) * (t.z - qz);
+                if (dd < best) { best = dd; a = t; have = true; }
+            }
+    if (!have) { none(); return; }
+    // b: nearest neighbour of a (a Delaunay edge)
+    best = INFINITY; have = false;
+    for (int d2 = -r2; d2 <= r2; ++d2)
+        for (int d1 = -r1; d1 <= r1; ++d1)
+            for (int d0 = -r0; d0 <= r0; ++d0) {
+                const int p0 = i0 + d0, p1 = i1 + d1, p2 = i2 + d2;
+                if (same3(a, p0, p1, p2) || !candidate3(P, xi0, xi1, xi2, p0, p1, p2, t)) continue;
+                const double dd = (t.x - a.x) * (t.x - a.x) + (t.y - a.y) * (t.y - a.y) + (t.z - a.z) * (t.z - a.z);
+                if (dd < best) { best = dd; b = t; have = true; }
+            }
+    if (!have) { none(); return; }
+    // c: smallest circumcircle through a, b: R^2 = |ab|^2 |ac|^2 |bc|^2 / (4 |ab x ac|^2)
+    {
+        const double ux = b.x - a.x, uy = b.y - a.y, uz = b.z - a.z, uu = ux * ux + uy * uy + uz * uz;
+        double bn = 0, bd = -1;
+        have = false;
+        for (int d2 = -r2; d2 <= r2; ++d2)
+            for (int d1 = -r1; d1 <= r1; ++d1)
+                for (int d0 = -r0; d0 <= r0; ++d0) {
+                    const int p0 = i0 + d0, p1 = i1 + d1, p2 = i2 + d2;
+                    if (same3(a, p0, p1, p2) || same3(b, p0, p1, p2) || !candidate3(P, xi0, xi1, xi2, p0, p1, p2, t)) continue;
+                    const double vx = t.x - a.x, vy = t.y - a.y, vz = t.z - a.z, vv = vx * vx + vy * vy + vz * vz;
+                    const double wx = t.x - b.x, wy = t.y - b.y, wz = t.z - b.z, ww = wx * wx + wy * wy + wz * wz;
+                    const double cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
+                    const double cc = cx * cx + cy * cy + cz * cz;
+                    if (!(cc > 1e-30 * uu * vv)) continue;                  // collinear
+                    const double num = uu * vv * ww;
+                    if (!have || num * bd < bn * cc) { bn = num; bd = cc; c = t; have = true; }
+                }
+        if (!have) { none(); return; }
+    }
+    if (orient3(a, b, c, qx, qy, qz) < 0) { t = b; b = c; c = t; }
+    bool found = false;
+    double wa = 0, wb = 0, wc = 0, wd = 0, scx = 0, scy = 0, scz = 0, srad2 = 0;
+    for (int step = 0; step < 96; ++step) {
+        // circumcentre o and radius of the face, unit normal towards the node's side
+        const double ux = b.x - a.x, uy = b.y - a.y, uz = b.z - a.z, vx = c.x - a.x, vy = c.y - a.y, vz = c.z - a.z;
+        const double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+        const double nn = nx * nx + ny * ny + nz * nz, uu = ux * ux + uy * uy + uz * uz, vv = vx * vx + vy * vy + vz * vz;
+        // o - a = (|u|^2 (v x n) + |v|^2 (n x u)) / (2 |n|^2)
+        const double ox = (uu * (vy * nz - vz * ny) + vv * (ny * uz - nz * uy)) / (2 * nn);
+        const double oy = (uu * (vz * nx - vx * nz) + vv * (nz * ux - nx * uz)) / (2 * nn);
+        const double oz = (uu * (vx * ny - vy * nx) + vv * (nx * uy - ny * ux)) / (2 * nn);
+        const double R2 = ox * ox + oy * oy + oz * oz;
+        const double inv_n = rsqrt(nn);
+        const double ex = nx * inv_n, ey = ny * inv_n, ez = nz * inv_n;
+        double bt = INFINITY;
+        bool any = false;
+        for (int d2 = -r2; d2 <= r2; ++d2)
+            for (int d1 = -r1; d1 <= r1; ++d1)
+                for (int d0 = -r0; d0 <= r0; ++d0) {
+                    const int p0 = i0 + d0, p1 = i1 + d1, p2 = i2 + d2;
+                    if (same3(a, p0, p1, p2) || same3(b, p0, p1, p2) || same3(c, p0, p1, p2)) continue;
+                    if (!candidate3(P, xi0, xi1, xi2, p0, p1, p2, t)) continue;
+                    const double px = t.x - a.x - ox, py = t.y - a.y - oy, pz = t.z - a.z - oz;
+                    const double h = px * ex + py * ey + pz * ez;
+                    if (!(h > 1e-14)) continue;                             // not on the node's side of the face
+                    const double tt = (px * px + py * py + pz * pz - R2) / (2 * h);
+                    if (tt < bt) { bt = tt; d = t; any = true; }
+                }
+        if (!any) break;                                                    // the node is outside the convex hull
+        const double vol = orient3(a, b, c, d.x, d.y, d.z);
+        // barycentric coordinates of the node: replace one vertex by the node in the orientation determinant
+        Cand3 qn; qn.x = qx; qn.y = qy; qn.z = qz;
+        wd = orient3(a, b, c, qx, qy, qz) / vol;
+        wa = orient3(qn, b, c, d.x, d.y, d.z) / vol;
+        wb = orient3(a, qn, c, d.x, d.y, d.z) / vol;
+        wc = orient3(a, b, qn, d.x, d.y, d.z) / vol;
+        if (wa >= 0 && wb >= 0 && wc >= 0) {
+            found = true;
+            scx = a.x + ox + bt * ex; scy = a.y + oy + bt * ey; scz = a.z + oz + bt * ez;
+            srad2 = R2 + bt * bt;
+            break;
+        }
+        // leave through the face opposite the most negative coordinate; orient the new face towards the node
+        if (wa <= wb && wa <= wc)      { a = d; }          // face (d, b, c)
+        else if (wb <= wa && wb <= wc) { b = d; }          // face (a, d, c)
+        else                           { c = d; }          // face (a, b, d)
+        if (orient3(a, b, c, qx, qy, qz) < 0) { t = b; b = c; c = t; }
+    }
+    if (!found) { none(); return; }
+    tet[4 * node] = a.idx; tet[4 * node + 1] = b.idx; tet[4 * node + 2] = c.idx; tet[4 * node + 3] = d.idx;
+    wgt[4 * node] = wa; wgt[4 * node + 1] = wb; wgt[4 * node + 2] = wc; wgt[4 * node + 3] = 1.0 - wa - wb - wc;
+    // patch sufficiency: the circumsphere must stay inside the part of space the patch is guaranteed to cover.  Nodes
+    // on the first / last plane of a Bounded axis are overwritten by the edge-plane interpolation and are not checked.
+    const int ii[3] = {i0, i1, i2};
+    const double qq[3] = {qx, qy, qz}, sc[3] = {scx, scy, scz};
+    const double rad = sqrt(srad2);
+    bool bad = false;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const RemapAxis &A = P.ax[q];
+        if (!A.periodic && (ii[q] == 0 || ii[q] == A.n - 1)) return;
+        const double safe = (A.r - A.maxdisp - 0.5) * A.delta / A.rg;
+        const bool edge_lo = !A.periodic && ii[q] - A.r < 0, edge_hi = !A.periodic && ii[q] + A.r >= A.n;
+        if (!edge_lo && sc[q] - rad < qq[q] - safe) bad = true;
+        if (!edge_hi && sc[q] + rad > qq[q] + safe) bad = true;
+    }
+    if (bad) atomicAdd(too_small, 1);
+}
+
+__global__ void lfb_remap3d_apply(const Remap3Params P, const int64_t *__restrict__ tet, const double *__restrict__ wgt,
+                                  const double *__restrict__ f, double *__restrict__ out)
+{
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+    if (i0 >= P.ax[0].n) return;
+    const int64_t node = ((int64_t)i2 * P.ax[1].n + i1) * P.ax[0].n + i0;
+    const int64_t o = (int64_t)(i0 + P.ax[0].H) * P.ax[0].stride + (int64_t)(i1 + P.ax[1].H) * P.ax[1].stride +
+                      (int64_t)(i2 + P.ax[2].H) * P.ax[2].stride;
+    if (tet[4 * node] < 0) { out[o] = nan(""); return; }
+    out[o] = wgt[4 * node] * f[tet[4 * node]] + wgt[4 * node + 1] * f[tet[4 * node + 1]] + wgt[4 * node + 2] * f[tet[4 * node + 2]] +
+             wgt[4 * node + 3] * f[tet[4 * node + 3]];
+}
+
 extern "C" void lfb_internal_set_error(const char *msg);      // lfb_api.cu: message returned by lfb_last_error()
 #define RFAIL(code, ...) do { char m_[256]; snprintf(m_, sizeof(m_), __VA_ARGS__); lfb_internal_set_error(m_); return code; } while (0)
 #define RCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) RFAIL(LFB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+// normalisation extents of the reference's padded cloud along axis `a` (post:527-628) over the points of the index box
+// [lo, hi) and the largest displacement in cells
+static int cloud_extent(const lfb_remap_desc *D, const double *xi_a, int a, const int lo[3], const int hi[3], const int64_t st[3],
+                        double *mn_out, double *rg_out, double *md_out)
+{
+    const bool periodic = D->topology[a] == LFB_PERIODIC, has_map = D->has_map[a] && xi_a;
+    const double x0 = D->origin[a], dl = D->spacing[a], L = dl * D->size[a], xe = x0 + L, pad = D->npad * dl;
+    double mn = INFINITY, mx = -INFINITY, md = 0;
+    for (int k = lo[2]; k < hi[2]; ++k)
+        for (int j = lo[1]; j < hi[1]; ++j)
+            for (int i = lo[0]; i < hi[0]; ++i) {
+                const int ii[3] = {i, j, k};
+                const int64_t idx = (int64_t)(i + D->halo[0]) * st[0] + (int64_t)(j + D->halo[1]) * st[1] + (int64_t)(k + D->halo[2]) * st[2];
+                const double d = has_map ? xi_a[idx] : 0.0;
+                double X = x0 + dl * (ii[a] + 0.5) + d;
+                if (fabs(d) / dl > md) md = fabs(d) / dl;
+                if (periodic && has_map) X -= floor((X - x0) / L) * L;
+                if (X < mn) mn = X;
+                if (X > mx) mx = X;
+                if (periodic) {
+                    if (X > xe - pad && X < xe) { if (X - L < mn) mn = X - L; }
+                    else if (X < x0 + pad && X > x0) { if (X + L > mx) mx = X + L; }
+                }
+            }
+    if (!(md < 1e300)) return -1;
+    *mn_out = mn; *rg_out = mx - mn; *md_out = md;
+    return 0;
+}
+
+// grids with three non-Flat axes: 3-D walk for the bulk, then the reference's edge-plane interpolation on every
+// Bounded axis (a 2-D LinearNDInterpolator over the points of the first / last index plane, normalised by the extents
+// of that cut, post:678-745), halos zero
+static int remap3(const lfb_remap_desc *D, const double *const *xi, int n_fields, const double *const *fields, double *const *out)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) RFAIL(LFB_ERR_CUDA, "no CUDA device available; liblfb200 has no CPU fallback");
+    RCU(cudaSetDevice(D->device));
+    int64_t ext[3], st[3];
+    for (int a = 0; a < 3; ++a) ext[a] = D->size[a] + 2 * D->halo[a];
+    st[0] = 1; st[1] = ext[0]; st[2] = ext[0] * ext[1];
+    const int64_t len = ext[0] * ext[1] * ext[2];
+    Remap3Params P;
+    memset(&P, 0, sizeof(P));
+    const int lo[3] = {0, 0, 0}, hi[3] = {D->size[0], D->size[1], D->size[2]};
+    for (int a = 0; a < 3; ++a) {
+        RemapAxis &A = P.ax[a];
+        A.n = D->size[a]; A.H = D->halo[a]; A.periodic = D->topology[a] == LFB_PERIODIC; A.has_map = D->has_map[a] && xi[a];
+        A.origin = D->origin[a]; A.delta = D->spacing[a]; A.L = A.delta * A.n; A.pad = D->npad * A.delta; A.stride = st[a];
+        if (cloud_extent(D, xi[a], a, lo, hi, st, &A.mn, &A.rg, &A.maxdisp)) RFAIL(LFB_ERR_ARG, "non-finite displacement");
+    }
+    double *d_xi[3] = {nullptr, nullptr, nullptr}, *d_f = nullptr, *d_out = nullptr, *d_w = nullptr, *d_pw = nullptr;
+    int64_t *d_tet = nullptr, *d_ptri = nullptr;
+    int *d_flag = nullptr;
+    const int64_t nodes = (int64_t)P.ax[0].n * P.ax[1].n * P.ax[2].n;
+    auto cleanup = [&]() {
+        for (int a = 0; a < 3; ++a) cudaFree(d_xi[a]);
+        cudaFree(d_f); cudaFree(d_out); cudaFree(d_w); cudaFree(d_tet); cudaFree(d_flag); cudaFree(d_pw); cudaFree(d_ptri);
+    };
+#define RCU3(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); RFAIL(LFB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    for (int a = 0; a < 3; ++a)
+        if (P.ax[a].has_map) {
+            RCU3(cudaMalloc(&d_xi[a], len * sizeof(double)));
+            RCU3(cudaMemcpy(d_xi[a], xi[a], len * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    RCU3(cudaMalloc(&d_f, len * sizeof(double)));
+    RCU3(cudaMalloc(&d_out, len * sizeof(double)));
+    RCU3(cudaMalloc(&d_w, 4 * nodes * sizeof(double)));
+    RCU3(cudaMalloc(&d_tet, 4 * nodes * sizeof(int64_t)));
+    RCU3(cudaMalloc(&d_flag, sizeof(int)));
+    // patch radius: displacement + the reach of a lattice circumsphere in normalised cells + margin; doubled while the check fails
+    double hn[3], diag = 0;
+    for (int a = 0; a < 3; ++a) { hn[a] = P.ax[a].delta / P.ax[a].rg; diag += hn[a] * hn[a]; }
+    diag = 0.5 * sqrt(diag);
+    int r[3];
+    for (int a = 0; a < 3; ++a) {
+        r[a] = (int)ceil(P.ax[a].maxdisp) + 2 + (int)fmin(ceil(diag / hn[a]) - 1, 12.0);
+        if (D->radius > 0) r[a] = D->radius;
+        if (r[a] > P.ax[a].n) r[a] = P.ax[a].n;
+    }
+    dim3 block(64, 1, 1), grid((P.ax[0].n + 63) / 64, P.ax[1].n, P.ax[2].n);
+    int flag = 1;
+    for (int attempt = 0; attempt < 3 && flag; ++attempt) {
+        for (int a = 0; a < 3; ++a) P.ax[a].r = r[a];
+        RCU3(cudaMemset(d_flag, 0, sizeof(int)));
+        lfb_remap3d_locate<<<grid, block>>>(P, d_xi[0], d_xi[1], d_xi[2], d_tet, d_w, d_flag);
+        RCU3(cudaGetLastError());
+        RCU3(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (flag) for (int a = 0; a < 3; ++a) { r[a] = r[a] * 2; if (r[a] > P.ax[a].n) r[a] = P.ax[a].n; }
+    }
+    if (flag) { cleanup(); RFAIL(LFB_ERR_STATE, "remap patch too small even at radius (%d, %d, %d): displacements too large for the local search", P.ax[0].r, P.ax[1].r, P.ax[2].r); }
+
+    // edge planes of the Bounded axes: triangle + weights per plane, shared by all fields
+    struct Plane { RemapParams P2; int64_t base; int64_t off; int n0, n1; };
+    std::vector<Plane> planes;
+    int64_t plane_nodes = 0;
+    for (int q = 0; q < 3; ++q) {
+        if (D->topology[q] != LFB_BOUNDED) continue;
+        const int o0 = q == 0 ? 1 : 0, o1 = q == 2 ? 1 : 2;
+        for (int edge : {0, D->size[q] - 1}) {
+            Plane pl;
+            memset(&pl, 0, sizeof(pl));
+            int plo[3] = {0, 0, 0}, phi[3] = {D->size[0], D->size[1], D->size[2]};
+            plo[q] = edge; phi[q] = edge + 1;
+            const int oa[2] = {o0, o1};
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const int a = oa[s2];
+                RemapParams &R = pl.P2;
+                R.n[s2] = D->size[a]; R.H[s2] = D->halo[a]; R.e[s2] = (int)ext[a];
+                R.periodic[s2] = D->topology[a] == LFB_PERIODIC; R.has_map[s2] = P.ax[a].has_map;
+                R.origin[s2] = D->origin[a]; R.delta[s2] = D->spacing[a]; R.L[s2] = P.ax[a].L; R.stride[s2] = st[a];
+                R.pad[s2] = P.ax[a].pad;
+                if (cloud_extent(D, xi[a], a, plo, phi, st, &R.mn[s2], &R.rg[s2], &R.maxdisp[s2])) { cleanup(); RFAIL(LFB_ERR_ARG, "non-finite displacement"); }
+            }
+            pl.base = (int64_t)(edge + D->halo[q]) * st[q];
+            pl.off = plane_nodes; pl.n0 = pl.P2.n[0]; pl.n1 = pl.P2.n[1];
+            plane_nodes += (int64_t)pl.n0 * pl.n1;
+            planes.push_back(pl);
+        }
+    }
+    if (!planes.empty()) {
+        RCU3(cudaMalloc(&d_pw, 3 * plane_nodes * sizeof(double)));
+        RCU3(cudaMalloc(&d_ptri, 3 * plane_nodes * sizeof(int64_t)));
+    }
+    int axis_of_plane = 0;
+    (void)axis_of_plane;
+    for (size_t ip = 0; ip < planes.size(); ++ip) {
+        Plane &pl = planes[ip];
+        RemapParams &R = pl.P2;
+        // which 3-D axes are the plane's two axes (for the xi pointers)
+        int oa[2] = {-1, -1};
+        for (int a = 0, s2 = 0; a < 3 && s2 < 2; ++a) if (st[a] == R.stride[s2]) oa[s2++] = a;
+        const double h0 = R.delta[0] / R.rg[0], h1 = R.delta[1] / R.rg[1];
+        int rr[2];
+        rr[0] = (int)ceil(R.maxdisp[0]) + 3 + (h0 < h1 ? (int)fmin(ceil(h1 / h0) - 1, 12.0) : 0);
+        rr[1] = (int)ceil(R.maxdisp[1]) + 3 + (h1 < h0 ? (int)fmin(ceil(h0 / h1) - 1, 12.0) : 0);
+        dim3 g2((R.n[0] + 63) / 64, R.n[1], 1);
+        int f2 = 1;
+        for (int attempt = 0; attempt < 4 && f2; ++attempt) {
+            R.r[0] = rr[0] > R.n[0] ? R.n[0] : rr[0]; R.r[1] = rr[1] > R.n[1] ? R.n[1] : rr[1];
+            RCU3(cudaMemset(d_flag, 0, sizeof(int)));
+            lfb_remap2d_locate<<<g2, block>>>(R, d_xi[oa[0]] ? d_xi[oa[0]] + pl.base : nullptr, d_xi[oa[1]] ? d_xi[oa[1]] + pl.base : nullptr,
+                                              d_ptri + 3 * pl.off, d_pw + 3 * pl.off, d_flag);
+            RCU3(cudaGetLastError());
+            RCU3(cudaMemcpy(&f2, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+            if (f2) { rr[0] *= 2; rr[1] *= 2; }
+        }
+        if (f2) { cleanup(); RFAIL(LFB_ERR_STATE, "remap patch too small on an edge plane"); }
+    }
+    for (int v = 0; v < n_fields; ++v) {
+        RCU3(cudaMemcpy(d_f, fields[v], len * sizeof(double), cudaMemcpyHostToDevice));
+        RCU3(cudaMemset(d_out, 0, len * sizeof(double)));                      // halos stay zero (post:748)
+        lfb_remap3d_apply<<<grid, block>>>(P, d_tet, d_w, d_f, d_out);
+        RCU3(cudaGetLastError());
+        for (Plane &pl : planes) {                                              // bounded dims in axis order (post:641)
+            dim3 g2((pl.n0 + 63) / 64, pl.n1, 1);
+            lfb_remap2d_apply<<<g2, block>>>(pl.P2, d_ptri + 3 * pl.off, d_pw + 3 * pl.off, d_f + pl.base, d_out + pl.base);
+            RCU3(cudaGetLastError());
+        }
+        RCU3(cudaMemcpy(out[v], d_out, len * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    cleanup();
+#undef RCU3
+    return LFB_OK;
+}
 
 extern "C" int lfb_remap_to_mean(const lfb_remap_desc *D, const double *const *xi, int n_fields, const double *const *fields,
                                  double *const *out)
@@ -215,7 +588,8 @@ extern "C" int lfb_remap_to_mean(const lfb_remap_desc *D, const double *const *x
     if (!D || !xi || !fields || !out || n_fields < 1) RFAIL(LFB_ERR_ARG, "bad argument");
     int ax[3], nt = 0;
     for (int a = 0; a < 3; ++a) if (D->topology[a] != LFB_FLAT) ax[nt++] = a;
-    if (nt != 2) RFAIL(LFB_ERR_ARG, "the device remap handles grids with exactly two non-Flat axes (got %d)", nt);
+    if (nt == 3) return remap3(D, xi, n_fields, fields, out);
+    if (nt != 2) RFAIL(LFB_ERR_ARG, "the device remap handles grids with two or three non-Flat axes (got %d)", nt);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) RFAIL(LFB_ERR_CUDA, "no CUDA device available; liblfb200 has no CPU fallback");
     RCU(cudaSetDevice(D->device));
@@ -249,7 +623,7 @@ extern "C" int lfb_remap_to_mean(const lfb_remap_desc *D, const double *const *x
                 if (X > mx) mx = X;
                 if (P.periodic[q]) {
                     if (X > hi - pad && X < hi) { if (X - P.L[q] < mn) mn = X - P.L[q]; }
-                    if (X < lo + pad && X > lo) { if (X + P.L[q] > mx) mx = X + P.L[q]; }
+                    else if (X < lo + pad && X > lo) { if (X + P.L[q] > mx) mx = X + P.L[q]; }
                 }
             }
         if (!(md < 1e300)) RFAIL(LFB_ERR_ARG, "non-finite displacement");

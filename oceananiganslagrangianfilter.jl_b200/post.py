@@ -133,7 +133,7 @@ def regrid_to_mean_position(config, out: FilterOutput, extra_vars_to_regrid: Seq
     for k in range(len(out.times)):
         xi = {vel: out.fields["xi_" + vel + label][k] for vel in config.velocity_names
               if "xi_" + vel + label in out.fields}
-        remap = remap_to_mean_device if len(g.nonflat_axes) == 2 else remap_to_mean
+        remap = remap_to_mean_device if len(g.nonflat_axes) >= 2 else remap_to_mean
         res = remap({n: out.fields[n][k] for n in names}, xi, g.N, g.H, g.topology, g.origin, g.spacing, npad=config.npad)
         for n in names:
             out.fields.setdefault(n + "_at_mean", []).append(res[n + "_at_mean"])

@@ -1,11 +1,12 @@
 """Remap of filtered fields to the mean position (reference regrid_to_mean_position!,
 src/Utils/post_processing_utils.jl:327-762).
 
-Grids with two non-Flat axes (the reference's 2-D examples and its golden test case) are remapped on the
-GPU by `remap_to_mean_device` -> lfb_remap_to_mean (csrc/lfb_remap.cu: local Delaunay walk + barycentric
-interpolation, shared by all variables of an output time).  For grids with three non-Flat axes this module
-does what the reference does -- it leaves for scipy.interpolate.LinearNDInterpolator (post:8-13, 634, 685) --
-because a device 3-D Delaunay is not built yet.
+`remap_to_mean_device` -> lfb_remap_to_mean (csrc/lfb_remap.cu) remaps on the GPU: for every grid node the
+Delaunay triangle (two non-Flat axes) or tetrahedron (three) that contains it is constructed locally by a walk
+over a patch of lattice neighbours, followed by barycentric interpolation and the reference's edge fix on
+Bounded axes; the search is shared by all variables of an output time.  `remap_to_mean` is the host form of the
+same step with the calls the reference itself makes (scipy.interpolate.LinearNDInterpolator through PythonCall,
+post:8-13, 634, 685); the product path (`post.regrid_to_mean_position`) uses the device form.
 """
 from __future__ import annotations
 
@@ -120,7 +121,7 @@ def remap_to_mean(fields: Dict[str, np.ndarray], xi: Dict[str, np.ndarray], N, H
 
 def remap_to_mean_device(fields: Dict[str, np.ndarray], xi: Dict[str, np.ndarray], N, H, topology, origin, delta,
                          npad: int = 5, device: int = 0, radius: int = 0) -> Dict[str, np.ndarray]:
-    """Same contract as remap_to_mean, computed by liblfb200 (two non-Flat axes only)."""
+    """Same contract as remap_to_mean, computed by liblfb200 (two or three non-Flat axes)."""
     import ctypes as C
     L = _lib.load()
     d = _lib.RemapDesc()
