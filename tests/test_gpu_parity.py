@@ -547,3 +547,34 @@ def test_device_remap_3d_matches_scipy_oracle(size, topology, amp):
     for k in want:
         assert np.array_equal(np.isnan(got[k]), np.isnan(want[k])), k
         assert np.nanmax(np.abs(got[k] - want[k])) <= 1e-10 * np.nanmax(np.abs(want[k])), k
+
+
+def test_device_remap_3d_reproduces_linear_function_at_size():
+    """Size-independent property of the remap: piecewise-linear interpolation on ANY triangulation reproduces a
+    linear function of the displaced coordinate.  With f = alpha (z + xi_z) + beta carried by the data points the
+    remapped field must equal alpha z + beta at every node that is not on the first / last plane of the Bounded
+    axis (those planes are overwritten by the reference's 2-D edge interpolation, which ignores xi_z)
+    (96 x 64 x 40, displacements up to 0.8 cells)."""
+    from lfb200.remap import remap_to_mean_device
+    size, topology = (96, 64, 40), ("Periodic", "Periodic", "Bounded")
+    g = lfb200.RectilinearGrid(size=size, extent=(192.0, 64.0, 20.0), topology=topology)
+    rng = np.random.default_rng(9)
+    shape = g.center_shape()
+    mesh = np.meshgrid(*[g.nodes(ax) for ax in range(3)], indexing="ij")
+    xi = {}
+    for ax in range(3):
+        f = 0.7 * g.spacing[ax] * np.sin(2 * np.pi * mesh[(ax + 1) % 3] / g.L[(ax + 1) % 3] * 3 + ax) * np.cos(2 * np.pi * mesh[ax] / g.L[ax] * 2)
+        f = f + 0.05 * g.spacing[ax] * rng.standard_normal(shape)
+        if topology[ax] == "Bounded":
+            f = f * np.sin(np.pi * (mesh[ax] - g.origin[ax]) / g.L[ax])
+        xi["uvw"[ax]] = np.asfortranarray(f)
+    alpha, beta = 0.37, -1.25
+    fields = {"lin": np.asfortranarray(alpha * (mesh[2] + xi["w"]) + beta)}
+    got = remap_to_mean_device(fields, xi, g.N, g.H, g.topology, g.origin, g.spacing, npad=5)["lin_at_mean"]
+    H = g.H
+    inner = tuple(slice(H[ax], H[ax] + size[ax]) for ax in range(3))
+    want = (alpha * mesh[2] + beta)[inner]
+    assert not np.isnan(got[inner]).any()
+    assert np.abs(got[inner] - want)[:, :, 1:-1].max() <= 1e-12 * np.abs(want).max()
+    halo = got.copy(); halo[inner] = 0.0
+    assert not halo.any()
