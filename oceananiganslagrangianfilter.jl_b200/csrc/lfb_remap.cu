@@ -17,7 +17,9 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <vector>
 
@@ -272,13 +274,13 @@ __device__ __forceinline__ double orient3(const Cand3 &a, const Cand3 &b, const 
     return (by * cz - bz * cy) * ex + (bz * cx - bx * cz) * ey + (bx * cy - by * cx) * ez;
 }
 
-// one thread per interior node: Delaunay tetrahedron containing the node + barycentric weights
-__global__ void lfb_remap3d_locate(const Remap3Params P, const double *__restrict__ xi0, const double *__restrict__ xi1,
-                                   const double *__restrict__ xi2, int64_t *__restrict__ tet, double *__restrict__ wgt,
-                                   int *__restrict__ too_small)
+// Delaunay tetrahedron containing node (i0, i1, i2) + barycentric weights.  `src(p0, p1, p2, t)` delivers the data point
+// at lattice offset (p0, p1, p2) (false if the reference's cloud does not hold that image): from global memory, or from
+// the patch a block has staged in shared memory.
+template <class Src>
+__device__ __forceinline__ void remap3_locate_node(const Remap3Params &P, const Src &src, int i0, int i1, int i2,
+                                                   int64_t *__restrict__ tet, double *__restrict__ wgt, int *__restrict__ too_small)
 {
-    const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
-    if (i0 >= P.ax[0].n) return;
     const int64_t node = ((int64_t)i2 * P.ax[1].n + i1) * P.ax[0].n + i0;
     const double qx = (P.ax[0].origin + P.ax[0].delta * (i0 + 0.5) - P.ax[0].mn) / P.ax[0].rg;
     const double qy = (P.ax[1].origin + P.ax[1].delta * (i1 + 0.5) - P.ax[1].mn) / P.ax[1].rg;
@@ -294,7 +296,7 @@ __global__ void lfb_remap3d_locate(const Remap3Params P, const double *__restric
     for (int d2 = -r2; d2 <= r2; ++d2)
         for (int d1 = -r1; d1 <= r1; ++d1)
             for (int d0 = -r0; d0 <= r0; ++d0) {
-                if (!candidate3(P, xi0, xi1, xi2, i0 + d0, i1 + d1, i2 + d2, t)) continue;
+                if (!src(i0 + d0, i1 + d1, i2 + d2, t)) continue;
                 const double dd = (t.x - qx) * (t.x - qx) + (t.y - qy) * (t.y - qy) + (t.z - qz) * (t.z - qz);
                 if (dd < best) { best = dd; a = t; have = true; }
             }
@@ -305,7 +307,7 @@ __global__ void lfb_remap3d_locate(const Remap3Params P, const double *__restric
         for (int d1 = -r1; d1 <= r1; ++d1)
             for (int d0 = -r0; d0 <= r0; ++d0) {
                 const int p0 = i0 + d0, p1 = i1 + d1, p2 = i2 + d2;
-                if (same3(a, p0, p1, p2) || !candidate3(P, xi0, xi1, xi2, p0, p1, p2, t)) continue;
+                if (same3(a, p0, p1, p2) || !src(p0, p1, p2, t)) continue;
                 const double dd = (t.x - a.x) * (t.x - a.x) + (t.y - a.y) * (t.y - a.y) + (t.z - a.z) * (t.z - a.z);
                 if (dd < best) { best = dd; b = t; have = true; }
             }
@@ -319,7 +321,7 @@ __global__ void lfb_remap3d_locate(const Remap3Params P, const double *__restric
             for (int d1 = -r1; d1 <= r1; ++d1)
                 for (int d0 = -r0; d0 <= r0; ++d0) {
                     const int p0 = i0 + d0, p1 = i1 + d1, p2 = i2 + d2;
-                    if (same3(a, p0, p1, p2) || same3(b, p0, p1, p2) || !candidate3(P, xi0, xi1, xi2, p0, p1, p2, t)) continue;
+                    if (same3(a, p0, p1, p2) || same3(b, p0, p1, p2) || !src(p0, p1, p2, t)) continue;
                     const double vx = t.x - a.x, vy = t.y - a.y, vz = t.z - a.z, vv = vx * vx + vy * vy + vz * vz;
                     const double wx = t.x - b.x, wy = t.y - b.y, wz = t.z - b.z, ww = wx * wx + wy * wy + wz * wz;
                     const double cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
@@ -352,7 +354,7 @@ __global__ void lfb_remap3d_locate(const Remap3Params P, const double *__restric
                 for (int d0 = -r0; d0 <= r0; ++d0) {
                     const int p0 = i0 + d0, p1 = i1 + d1, p2 = i2 + d2;
                     if (same3(a, p0, p1, p2) || same3(b, p0, p1, p2) || same3(c, p0, p1, p2)) continue;
-                    if (!candidate3(P, xi0, xi1, xi2, p0, p1, p2, t)) continue;
+                    if (!src(p0, p1, p2, t)) continue;
                     const double px = t.x - a.x - ox, py = t.y - a.y - oy, pz = t.z - a.z - oz;
                     const double h = px * ex + py * ey + pz * ez;
                     if (!(h > 1e-14)) continue;                             // not on the node's side of the face
@@ -380,7 +382,21 @@ __global__ void lfb_remap3d_locate(const Remap3Params P, const double *__restric
         if (orient3(a, b, c, qx, qy, qz) < 0) { t = b; b = c; c = t; }
     }
     if (!found) { none(); return; }
-    tet[4 * node] = a.idx; tet[4 * node + 1] = b.idx; tet[4 * node + 2] = c.idx; tet[4 * node + 3] = d.idx;
+    {
+        const Cand3 *vv[4] = {&a, &b, &c, &d};
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            int q[3] = {vv[v]->p0, vv[v]->p1, vv[v]->p2};
+            int64_t idx = 0;
+#pragma unroll
+            for (int ax = 0; ax < 3; ++ax) {
+                const RemapAxis &A = P.ax[ax];
+                if (A.periodic) { q[ax] %= A.n; if (q[ax] < 0) q[ax] += A.n; }
+                idx += (int64_t)(q[ax] + A.H) * A.stride;
+            }
+            tet[4 * node + v] = idx;
+        }
+    }
     wgt[4 * node] = wa; wgt[4 * node + 1] = wb; wgt[4 * node + 2] = wc; wgt[4 * node + 3] = 1.0 - wa - wb - wc;
     // patch sufficiency: the circumsphere must stay inside the part of space the patch is guaranteed to cover.  Nodes
     // on the first / last plane of a Bounded axis are overwritten by the edge-plane interpolation and are not checked.
@@ -398,6 +414,66 @@ __global__ void lfb_remap3d_locate(const Remap3Params P, const double *__restric
         if (!edge_hi && sc[q] + rad > qq[q] + safe) bad = true;
     }
     if (bad) atomicAdd(too_small, 1);
+}
+
+// candidate sources
+struct Src3Global {
+    const Remap3Params &P;
+    const double *xi0, *xi1, *xi2;
+    __device__ __forceinline__ bool operator()(int p0, int p1, int p2, Cand3 &t) const { return candidate3(P, xi0, xi1, xi2, p0, p1, p2, t); }
+};
+
+// one thread per interior node, candidates evaluated from global memory (any patch radius)
+__global__ void lfb_remap3d_locate(const Remap3Params P, const double *__restrict__ xi0, const double *__restrict__ xi1,
+                                   const double *__restrict__ xi2, int64_t *__restrict__ tet, double *__restrict__ wgt,
+                                   int *__restrict__ too_small)
+{
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
+    if (i0 >= P.ax[0].n) return;
+    const Src3Global src = {P, xi0, xi1, xi2};
+    remap3_locate_node(P, src, i0, i1, i2, tet, wgt, too_small);
+}
+
+// The same with the patch of a block of 32 x R3_BY nodes staged once in shared memory (normalised positions of every
+// lattice neighbour any node of the block can reach; x = +inf marks an image the cloud does not hold), so a candidate
+// costs three shared-memory loads instead of three global loads, a wrap, a floor and three divisions.
+#define R3_BX 32
+#define R3_BY 4
+struct Src3Shared {
+    const double *px, *py, *pz;
+    int b0, b1, b2, e0, e1;          // lattice offset of patch entry 0 and the patch extents in x, y
+    __device__ __forceinline__ bool operator()(int p0, int p1, int p2, Cand3 &t) const
+    {
+        const int e = ((p2 - b2) * e1 + (p1 - b1)) * e0 + (p0 - b0);
+        const double x = px[e];
+        if (!(x < 1e300)) return false;
+        t.x = x; t.y = py[e]; t.z = pz[e]; t.p0 = p0; t.p1 = p1; t.p2 = p2; t.idx = -1;
+        return true;
+    }
+};
+
+__global__ void __launch_bounds__(R3_BX * R3_BY) lfb_remap3d_locate_smem(const Remap3Params P, const double *__restrict__ xi0,
+                                                                        const double *__restrict__ xi1, const double *__restrict__ xi2,
+                                                                        int64_t *__restrict__ tet, double *__restrict__ wgt,
+                                                                        int *__restrict__ too_small)
+{
+    extern __shared__ double r3_smem[];
+    const int r0 = P.ax[0].r, r1 = P.ax[1].r, r2 = P.ax[2].r;
+    const int e0 = R3_BX + 2 * r0, e1 = R3_BY + 2 * r1, e2 = 2 * r2 + 1, ne = e0 * e1 * e2;
+    double *px = r3_smem, *py = px + ne, *pz = py + ne;
+    const int n0 = blockIdx.x * R3_BX, n1 = blockIdx.y * R3_BY, i2 = blockIdx.z;
+    const int b0 = n0 - r0, b1 = n1 - r1, b2 = i2 - r2;
+    for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+        const int q0 = e % e0, q1 = (e / e0) % e1, q2 = e / (e0 * e1);
+        Cand3 t;
+        if (candidate3(P, xi0, xi1, xi2, b0 + q0, b1 + q1, b2 + q2, t)) { px[e] = t.x; py[e] = t.y; pz[e] = t.z; }
+        else { px[e] = INFINITY; py[e] = 0; pz[e] = 0; }
+    }
+    __syncthreads();
+    const int i0 = n0 + threadIdx.x % R3_BX, i1 = n1 + threadIdx.x / R3_BX;
+    if (i0 >= P.ax[0].n || i1 >= P.ax[1].n) return;
+    const Src3Shared src = {px, py, pz, b0, b1, b2, e0, e1};
+    remap3_locate_node(P, src, i0, i1, i2, tet, wgt, too_small);
 }
 
 __global__ void lfb_remap3d_apply(const Remap3Params P, const int64_t *__restrict__ tet, const double *__restrict__ wgt,
@@ -418,29 +494,62 @@ extern "C" void lfb_internal_set_error(const char *msg);      // lfb_api.cu: mes
 #define RCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) RFAIL(LFB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
 
 // normalisation extents of the reference's padded cloud along axis `a` (post:527-628) over the points of the index box
-// [lo, hi) and the largest displacement in cells
-static int cloud_extent(const lfb_remap_desc *D, const double *xi_a, int a, const int lo[3], const int hi[3], const int64_t st[3],
-                        double *mn_out, double *rg_out, double *md_out)
+// [lo, hi) and the largest displacement in cells: per-block partial results (min, max, max |xi| / delta)
+struct ExtentParams {
+    int     lo[3], n[3], H[3];      // box origin and extents (interior indices), halos
+    int64_t st[3];
+    int     a, periodic, has_map;
+    double  x0, dl, L, pad;
+};
+
+__global__ void lfb_remap_extent(const ExtentParams E, const double *__restrict__ xi_a, double *__restrict__ partial)
 {
-    const bool periodic = D->topology[a] == LFB_PERIODIC, has_map = D->has_map[a] && xi_a;
-    const double x0 = D->origin[a], dl = D->spacing[a], L = dl * D->size[a], xe = x0 + L, pad = D->npad * dl;
+    const int64_t total = (int64_t)E.n[0] * E.n[1] * E.n[2];
     double mn = INFINITY, mx = -INFINITY, md = 0;
-    for (int k = lo[2]; k < hi[2]; ++k)
-        for (int j = lo[1]; j < hi[1]; ++j)
-            for (int i = lo[0]; i < hi[0]; ++i) {
-                const int ii[3] = {i, j, k};
-                const int64_t idx = (int64_t)(i + D->halo[0]) * st[0] + (int64_t)(j + D->halo[1]) * st[1] + (int64_t)(k + D->halo[2]) * st[2];
-                const double d = has_map ? xi_a[idx] : 0.0;
-                double X = x0 + dl * (ii[a] + 0.5) + d;
-                if (fabs(d) / dl > md) md = fabs(d) / dl;
-                if (periodic && has_map) X -= floor((X - x0) / L) * L;
-                if (X < mn) mn = X;
-                if (X > mx) mx = X;
-                if (periodic) {
-                    if (X > xe - pad && X < xe) { if (X - L < mn) mn = X - L; }
-                    else if (X < x0 + pad && X > x0) { if (X + L > mx) mx = X + L; }
-                }
-            }
+    const double xe = E.x0 + E.L;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+        int ii[3];
+        ii[0] = E.lo[0] + (int)(q % E.n[0]); ii[1] = E.lo[1] + (int)((q / E.n[0]) % E.n[1]); ii[2] = E.lo[2] + (int)(q / ((int64_t)E.n[0] * E.n[1]));
+        const int64_t idx = (int64_t)(ii[0] + E.H[0]) * E.st[0] + (int64_t)(ii[1] + E.H[1]) * E.st[1] + (int64_t)(ii[2] + E.H[2]) * E.st[2];
+        const double d = E.has_map ? xi_a[idx] : 0.0;
+        double X = E.x0 + E.dl * (ii[E.a] + 0.5) + d;
+        md = fmax(md, fabs(d) / E.dl);
+        if (!(fabs(d) < 1e300)) md = INFINITY;                                  // NaN / inf displacement
+        if (E.periodic && E.has_map) X -= floor((X - E.x0) / E.L) * E.L;
+        mn = fmin(mn, X); mx = fmax(mx, X);
+        if (E.periodic) {
+            if (X > xe - E.pad && X < xe) mn = fmin(mn, X - E.L);
+            else if (X < E.x0 + E.pad && X > E.x0) mx = fmax(mx, X + E.L);
+        }
+    }
+    __shared__ double smn[256], smx[256], smd[256];
+    smn[threadIdx.x] = mn; smx[threadIdx.x] = mx; smd[threadIdx.x] = md;
+    __syncthreads();
+    for (int s2 = blockDim.x / 2; s2 > 0; s2 >>= 1) {
+        if ((int)threadIdx.x < s2) {
+            smn[threadIdx.x] = fmin(smn[threadIdx.x], smn[threadIdx.x + s2]);
+            smx[threadIdx.x] = fmax(smx[threadIdx.x], smx[threadIdx.x + s2]);
+            smd[threadIdx.x] = fmax(smd[threadIdx.x], smd[threadIdx.x + s2]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { partial[3 * blockIdx.x] = smn[0]; partial[3 * blockIdx.x + 1] = smx[0]; partial[3 * blockIdx.x + 2] = smd[0]; }
+}
+
+#define EXT_BLOCKS 592
+static int cloud_extent(const lfb_remap_desc *D, const double *d_xi_a, double *d_partial, int a, const int lo[3], const int hi[3],
+                        const int64_t st[3], double *mn_out, double *rg_out, double *md_out)
+{
+    ExtentParams E;
+    memset(&E, 0, sizeof(E));
+    for (int q = 0; q < 3; ++q) { E.lo[q] = lo[q]; E.n[q] = hi[q] - lo[q]; E.H[q] = D->halo[q]; E.st[q] = st[q]; }
+    E.a = a; E.periodic = D->topology[a] == LFB_PERIODIC; E.has_map = D->has_map[a] && d_xi_a;
+    E.x0 = D->origin[a]; E.dl = D->spacing[a]; E.L = E.dl * D->size[a]; E.pad = D->npad * E.dl;
+    lfb_remap_extent<<<EXT_BLOCKS, 256>>>(E, d_xi_a, d_partial);
+    static double hp[3 * EXT_BLOCKS];
+    if (cudaGetLastError() != cudaSuccess || cudaMemcpy(hp, d_partial, sizeof(hp), cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+    double mn = INFINITY, mx = -INFINITY, md = 0;
+    for (int b2 = 0; b2 < EXT_BLOCKS; ++b2) { mn = fmin(mn, hp[3 * b2]); mx = fmax(mx, hp[3 * b2 + 1]); md = fmax(md, hp[3 * b2 + 2]); }
     if (!(md < 1e300)) return -1;
     *mn_out = mn; *rg_out = mx - mn; *md_out = md;
     return 0;
@@ -449,8 +558,12 @@ static int cloud_extent(const lfb_remap_desc *D, const double *xi_a, int a, cons
 // grids with three non-Flat axes: 3-D walk for the bulk, then the reference's edge-plane interpolation on every
 // Bounded axis (a 2-D LinearNDInterpolator over the points of the first / last index plane, normalised by the extents
 // of that cut, post:678-745), halos zero
+static double now_s() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
 static int remap3(const lfb_remap_desc *D, const double *const *xi, int n_fields, const double *const *fields, double *const *out)
 {
+    const bool timing = getenv("LFB200_REMAP_TIMING") != nullptr;
+    const double t_start = now_s();
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) RFAIL(LFB_ERR_CUDA, "no CUDA device available; liblfb200 has no CPU fallback");
     RCU(cudaSetDevice(D->device));
@@ -461,26 +574,29 @@ static int remap3(const lfb_remap_desc *D, const double *const *xi, int n_fields
     Remap3Params P;
     memset(&P, 0, sizeof(P));
     const int lo[3] = {0, 0, 0}, hi[3] = {D->size[0], D->size[1], D->size[2]};
+    double *d_xi[3] = {nullptr, nullptr, nullptr}, *d_f = nullptr, *d_out = nullptr, *d_w = nullptr, *d_pw = nullptr, *d_part = nullptr;
+    int64_t *d_tet = nullptr, *d_ptri = nullptr;
+    int *d_flag = nullptr;
+    const int64_t nodes = (int64_t)D->size[0] * D->size[1] * D->size[2];
+    auto cleanup = [&]() {
+        for (int a = 0; a < 3; ++a) cudaFree(d_xi[a]);
+        cudaFree(d_f); cudaFree(d_out); cudaFree(d_w); cudaFree(d_tet); cudaFree(d_flag); cudaFree(d_pw); cudaFree(d_ptri); cudaFree(d_part);
+    };
+#define RCU3(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); RFAIL(LFB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    for (int a = 0; a < 3; ++a)
+        if (D->has_map[a] && xi[a]) {
+            RCU3(cudaMalloc(&d_xi[a], len * sizeof(double)));
+            RCU3(cudaMemcpy(d_xi[a], xi[a], len * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    RCU3(cudaMalloc(&d_part, 3 * EXT_BLOCKS * sizeof(double)));
     for (int a = 0; a < 3; ++a) {
         RemapAxis &A = P.ax[a];
         A.n = D->size[a]; A.H = D->halo[a]; A.periodic = D->topology[a] == LFB_PERIODIC; A.has_map = D->has_map[a] && xi[a];
         A.origin = D->origin[a]; A.delta = D->spacing[a]; A.L = A.delta * A.n; A.pad = D->npad * A.delta; A.stride = st[a];
-        if (cloud_extent(D, xi[a], a, lo, hi, st, &A.mn, &A.rg, &A.maxdisp)) RFAIL(LFB_ERR_ARG, "non-finite displacement");
+        const int ce = cloud_extent(D, d_xi[a], d_part, a, lo, hi, st, &A.mn, &A.rg, &A.maxdisp);
+        if (ce) { cleanup(); RFAIL(ce == -1 ? LFB_ERR_ARG : LFB_ERR_CUDA, ce == -1 ? "non-finite displacement" : "extent kernel failed"); }
     }
-    double *d_xi[3] = {nullptr, nullptr, nullptr}, *d_f = nullptr, *d_out = nullptr, *d_w = nullptr, *d_pw = nullptr;
-    int64_t *d_tet = nullptr, *d_ptri = nullptr;
-    int *d_flag = nullptr;
-    const int64_t nodes = (int64_t)P.ax[0].n * P.ax[1].n * P.ax[2].n;
-    auto cleanup = [&]() {
-        for (int a = 0; a < 3; ++a) cudaFree(d_xi[a]);
-        cudaFree(d_f); cudaFree(d_out); cudaFree(d_w); cudaFree(d_tet); cudaFree(d_flag); cudaFree(d_pw); cudaFree(d_ptri);
-    };
-#define RCU3(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); RFAIL(LFB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
-    for (int a = 0; a < 3; ++a)
-        if (P.ax[a].has_map) {
-            RCU3(cudaMalloc(&d_xi[a], len * sizeof(double)));
-            RCU3(cudaMemcpy(d_xi[a], xi[a], len * sizeof(double), cudaMemcpyHostToDevice));
-        }
+    const double t_ext = now_s();
     RCU3(cudaMalloc(&d_f, len * sizeof(double)));
     RCU3(cudaMalloc(&d_out, len * sizeof(double)));
     RCU3(cudaMalloc(&d_w, 4 * nodes * sizeof(double)));
@@ -501,12 +617,20 @@ static int remap3(const lfb_remap_desc *D, const double *const *xi, int n_fields
     for (int attempt = 0; attempt < 3 && flag; ++attempt) {
         for (int a = 0; a < 3; ++a) P.ax[a].r = r[a];
         RCU3(cudaMemset(d_flag, 0, sizeof(int)));
-        lfb_remap3d_locate<<<grid, block>>>(P, d_xi[0], d_xi[1], d_xi[2], d_tet, d_w, d_flag);
+        const size_t patch_bytes = (size_t)(R3_BX + 2 * r[0]) * (R3_BY + 2 * r[1]) * (2 * r[2] + 1) * 3 * sizeof(double);
+        if (patch_bytes <= 200 * 1024 && !getenv("LFB200_REMAP_GLOBAL")) {
+            RCU3(cudaFuncSetAttribute(lfb_remap3d_locate_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_bytes));
+            dim3 gs((P.ax[0].n + R3_BX - 1) / R3_BX, (P.ax[1].n + R3_BY - 1) / R3_BY, P.ax[2].n);
+            lfb_remap3d_locate_smem<<<gs, R3_BX * R3_BY, patch_bytes>>>(P, d_xi[0], d_xi[1], d_xi[2], d_tet, d_w, d_flag);
+        } else {
+            lfb_remap3d_locate<<<grid, block>>>(P, d_xi[0], d_xi[1], d_xi[2], d_tet, d_w, d_flag);
+        }
         RCU3(cudaGetLastError());
         RCU3(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
         if (flag) for (int a = 0; a < 3; ++a) { r[a] = r[a] * 2; if (r[a] > P.ax[a].n) r[a] = P.ax[a].n; }
     }
     if (flag) { cleanup(); RFAIL(LFB_ERR_STATE, "remap patch too small even at radius (%d, %d, %d): displacements too large for the local search", P.ax[0].r, P.ax[1].r, P.ax[2].r); }
+    const double t_loc = now_s();
 
     // edge planes of the Bounded axes: triangle + weights per plane, shared by all fields
     struct Plane { RemapParams P2; int64_t base; int64_t off; int n0, n1; };
@@ -528,7 +652,7 @@ static int remap3(const lfb_remap_desc *D, const double *const *xi, int n_fields
                 R.periodic[s2] = D->topology[a] == LFB_PERIODIC; R.has_map[s2] = P.ax[a].has_map;
                 R.origin[s2] = D->origin[a]; R.delta[s2] = D->spacing[a]; R.L[s2] = P.ax[a].L; R.stride[s2] = st[a];
                 R.pad[s2] = P.ax[a].pad;
-                if (cloud_extent(D, xi[a], a, plo, phi, st, &R.mn[s2], &R.rg[s2], &R.maxdisp[s2])) { cleanup(); RFAIL(LFB_ERR_ARG, "non-finite displacement"); }
+                if (cloud_extent(D, d_xi[a], d_part, a, plo, phi, st, &R.mn[s2], &R.rg[s2], &R.maxdisp[s2])) { cleanup(); RFAIL(LFB_ERR_ARG, "non-finite displacement"); }
             }
             pl.base = (int64_t)(edge + D->halo[q]) * st[q];
             pl.off = plane_nodes; pl.n0 = pl.P2.n[0]; pl.n1 = pl.P2.n[1];
@@ -579,6 +703,10 @@ static int remap3(const lfb_remap_desc *D, const double *const *xi, int n_fields
     }
     cleanup();
 #undef RCU3
+    if (timing)
+        fprintf(stderr, "lfb_remap_to_mean 3-D: %lld nodes, radius (%d, %d, %d): extents %.3f s, upload + tetrahedron search %.3f s, "
+                        "edge planes + %d fields %.3f s\n", (long long)nodes, P.ax[0].r, P.ax[1].r, P.ax[2].r, t_ext - t_start, t_loc - t_ext,
+                n_fields, now_s() - t_loc);
     return LFB_OK;
 }
 
