@@ -174,18 +174,24 @@ static int select_kernel(lfb_handle *h)
     P.relax = h->desc.relaxation;
     for (int ax = 0; ax < 3; ++ax) P.vel_present[ax] = (h->desc.velocity_mask >> ax) & 1;
     P.j0 = 0; P.j1 = h->L.N[1];
-    const int ok = lfb_zmarch_supported(&P) && !h->desc.strict;
-    if ((h->desc.kernel == LFB_KERNEL_ZMARCH || h->desc.kernel == LFB_KERNEL_ZSPLIT || h->desc.kernel == LFB_KERNEL_ZTMA) && !ok)
-        return fail(LFB_ERR_ARG, "the z-marching kernel needs a (Periodic|slab, Periodic|slab, Bounded) grid with Nx %% 32 == 0, "
-                                 "Ny %% 8 == 0, Nz >= 8, u,v,w all present, WENO advection, no relaxation and strict = 0");
-    // 0 generic, 1 z-march (cp.async), 2 role-split z-march, 3 TMA-staged z-march (what `auto` picks)
+    // 0 generic, 1 z-march (cp.async staging), 2 role-split z-march, 3 TMA-staged z-march (what `auto` picks)
+    const int ok_cp = lfb_zmarch_supported(&P) && !h->desc.strict;          // needs Nx % 32 == 0
+    const int ok_tma = lfb_ztma_supported(&P) && !h->desc.strict;
+    const char *need = "a (Periodic|slab, Periodic|slab, Bounded) grid with Nz >= 8, u,v,w all present, WENO advection, no relaxation and strict = 0";
     h->use_zmarch = 0;
-    if (h->desc.kernel != LFB_KERNEL_GENERIC && ok) {
-        if (h->desc.kernel == LFB_KERNEL_ZMARCH) h->use_zmarch = 1;
-        else if (h->desc.kernel == LFB_KERNEL_ZSPLIT) h->use_zmarch = 2;
-        else if (lfb_ztma_supported(&P)) h->use_zmarch = 3;
-        else if (h->desc.kernel == LFB_KERNEL_ZTMA) return fail(LFB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-        else h->use_zmarch = 1;
+    switch (h->desc.kernel) {
+    case LFB_KERNEL_GENERIC: break;
+    case LFB_KERNEL_ZMARCH:
+    case LFB_KERNEL_ZSPLIT:
+        if (!ok_cp) return fail(LFB_ERR_ARG, "the cp.async z-marching kernels need %s, and Nx %% 32 == 0", need);
+        h->use_zmarch = h->desc.kernel == LFB_KERNEL_ZMARCH ? 1 : 2;
+        break;
+    case LFB_KERNEL_ZTMA:
+        if (!ok_tma) return fail(LFB_ERR_ARG, "the TMA z-marching kernel needs %s (and cuTensorMapEncodeTiled from the driver)", need);
+        h->use_zmarch = 3;
+        break;
+    default:
+        h->use_zmarch = ok_tma ? 3 : (ok_cp ? 1 : 0);
     }
     return LFB_OK;
 }

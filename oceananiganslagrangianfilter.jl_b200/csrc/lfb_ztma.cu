@@ -358,9 +358,9 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     const unsigned a32 = sbase + 8u * t, a32s = a32 + sub * VT_B;
     const unsigned a40 = sbase + 8u * (ty * ZT_CW + tx + ZT_HX), a40s = a40 + 3 * ROW_B + sub * CTP_B;
     const int partner_off = NSUB == 2 ? (sub ? -(int)CTP_B : (int)CTP_B) : 0;
-    const bool active = j0 + ty < S.j1;                              // partial tiles at the end of the y range
+    const bool active = j0 + ty < S.j1 && i0 + tx < L.N[0];         // partial tiles at the end of the y range / of x
     const int64_t plane = L.plane;
-    // rows beyond j1 (partial tiles) compute like the others but store into the scratch field
+    // rows beyond j1 / columns beyond Nx (partial tiles) compute like the others but store into the scratch field
     const int64_t cell0 = L.at(i0 + tx, j0 + ty, 0);
     double *__restrict__ pUn = active ? S.U_new + cell0 + (int64_t)(item.tracer_c + sub) * L.len : P.scratch + cell0;
     const int64_t g_off = active ? (S.G - S.U_new) : 0;              // pG = pUn + g_off
@@ -589,7 +589,7 @@ extern "C" int lfb_ztma_supported(const LfbStageParams *P)
     if (L.topo[0] != LFB_PERIODIC || L.topo[2] != LFB_BOUNDED) return 0;
     if (L.topo[1] != LFB_PERIODIC && !(L.connected_lo[1] && L.connected_hi[1])) return 0;
     if (!(P->vel_present[0] && P->vel_present[1] && P->vel_present[2])) return 0;
-    if (L.N[0] % ZT_TX || L.N[1] < 4 || L.N[2] < 8) return 0;
+    if (L.N[0] < 8 || L.N[1] < 4 || L.N[2] < 8) return 0;
     if (L.H[0] < 3 || L.H[1] < 3 || L.H[2] < 3) return 0;
     if (!zt_encoder()) return 0;
     return 1;
@@ -631,7 +631,7 @@ static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
     for (int a = 0; a < 3; ++a) P.rd[a] = S->area[a] / S->volume;
     P.scratch = S->scratch;
     const int ytiles = (S->j1 - S->j0 + TY - 1) / TY;
-    dim3 grid(S->n_items * ytiles, L.N[0] / ZT_TX, 1);
+    dim3 grid(S->n_items * ytiles, (L.N[0] + ZT_TX - 1) / ZT_TX, 1);
     lfb_stage_ztma<NSUB, TY><<<grid, SM::THREADS, SM::BYTES, stream>>>(P);
     return cudaGetLastError();
 }
