@@ -73,29 +73,30 @@ __device__ __forceinline__ T weno3z_ref(T o, T n, T e)
 //   b2 = 13/4 (do - dp)^2 + 3/4 (3 do - dp)^2
 // Z weights a_s = C_s (1 + tau^2 / (b_s + eps)^2) brought to the common denominator
 // prod_s (b_s + eps)^2, so that face value = n + sum_s A_s X_s / sum_s A_s needs one division,
-// with X_s = q_s - n the candidate increments.
+// with X_s = q_s - n the candidate increments; written as X_1 - (A0 y0 / 2 + A2 y2 / 3) / sum C_s A_s.
 __device__ __forceinline__ double weno5z_increment(double dp, double do_, double dn, double de)
 {
-    const double eps = LFB_WENO_EPS;
-    double s0 = de - dn, s1 = dn - do_, s2 = do_ - dp;
-    double t0 = fma(-3.0, dn, de), t1 = dn + do_, t2 = fma(3.0, do_, -dp);
-    double b0 = fma(3.25 * s0, s0, (0.75 * t0) * t0);
-    double b1 = fma(3.25 * s1, s1, (0.75 * t1) * t1);
-    double b2 = fma(3.25 * s2, s2, (0.75 * t2) * t2);
-    double x0 = fma(2.0 / 3.0, dn, (-1.0 / 6.0) * de);
-    double x1 = fma(1.0 / 3.0, dn, (1.0 / 6.0) * do_);
-    double x2 = fma(5.0 / 6.0, do_, (-1.0 / 3.0) * dp);
-    double tau = b0 - b2;
-    double tt = tau * tau;
-    double g0 = b0 + eps, g1 = b1 + eps, g2 = b2 + eps;
-    double G0 = g0 * g0, G1 = g1 * g1, G2 = g2 * g2;
-    double A0 = (G0 + tt) * (G1 * G2);
-    double A1 = (G1 + tt) * (G0 * G2);
-    double A2 = (G2 + tt) * (G0 * G1);
-    // C = (3, 6, 1) / 10
-    double den = fma(3.0, A0, fma(6.0, A1, A2));
-    double num = fma(3.0, A0 * x0, fma(6.0, A1 * x1, A2 * x2));
-    return num / den;
+    // the short form of the TMA z-march kernel (lfb_ztma.cu, zt_inc / zt_blend): indicators scaled by 4/3 with eps
+    // folded into the curvature term, tau^2 folded into the products, one reciprocal (hardware seed + one cubic step)
+    const double k133 = 13.0 / 3.0, eps43 = LFB_WENO_EPS * (4.0 / 3.0);
+    const double s0 = de - dn, s1 = dn - do_, s2 = do_ - dp;
+    const double t0 = fma(-3.0, dn, de), t1 = dn + do_, t2 = fma(3.0, do_, -dp);
+    const double g0 = fma(t0, t0, fma(k133 * s0, s0, eps43));
+    const double g1 = fma(t1, t1, fma(k133 * s1, s1, eps43));
+    const double g2 = fma(t2, t2, fma(k133 * s2, s2, eps43));
+    const double tau = g0 - g2;
+    const double G0 = g0 * g0, G1 = g1 * g1, G2 = g2 * g2;
+    const double A0 = fma(tau, tau, G0) * (G1 * G2);
+    const double A1 = fma(tau, tau, G1) * (G0 * G2);
+    const double A2 = fma(tau, tau, G2) * (G0 * G1);
+    const double den = fma(3.0, A0, fma(6.0, A1, A2));
+    const double num = fma(0.5, A0 * (s0 - s1), (1.0 / 3.0) * (A2 * (s1 - s2)));
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+    const double e = fma(-den, r, 1.0);
+    const double t = fma(e, e, e);
+    r = fma(r, t, r);
+    return fma(-num, r, fma(1.0 / 3.0, dn, (1.0 / 6.0) * do_));
 }
 
 // Upwind face value at face m (1-based; between cells m-1 and m) along one axis.
