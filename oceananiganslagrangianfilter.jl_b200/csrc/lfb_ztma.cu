@@ -1,4 +1,5 @@
-// lfb_ztma.cu -- TMA-staged z-marching RK3 stage kernel (production path on 3-D (P|slab, P|slab, B) grids).
+// lfb_ztma.cu -- TMA-staged z-marching RK3 stage kernel (production path on 3-D grids that are Bounded in z and
+// Periodic, Bounded or slab-decomposed in x and y).
 //
 // Same fused work as lfb_stage_generic / lfb_stage_zmarch (WENO5-Z flux divergence, c div(U), forcing, RK3
 // substep, tendency caching, periodic halo images; reference call sites: compute_Gc! / tracer_tendency,
@@ -196,6 +197,33 @@ __device__ __forceinline__ double zt_face(unsigned a, double q, const ZtK &K)
     return n + zt_inc(o - p, n - o, e - n, f - e, K);
 }
 
+// Scheme of the face with 1-based global index m on an axis of N cells: 5 = WENO5, 3 = buffer
+// WENO3, 2 = Centered2, 1 / 0 = lower / upper wall face (the value next to the wall; the wall velocity is zero).
+// Periodic (or slab-connected) axes and everything outside 1 .. N+1 (surplus lanes of partial tiles): WENO5.
+__device__ __forceinline__ int zt_face_order(int m, int N, bool bounded)
+{
+    if (!bounded || m < 1 || m > N + 1) return 5;
+    if (m >= 4 && m <= N - 2) return 5;
+    if (m == 1) return 1;
+    if (m == N + 1) return 0;
+    if (m == 3 || m == N - 1) return 3;
+    return 2;
+}
+
+// in-plane face next to a wall of a Bounded axis: the same formulas as the generic kernel's production flavour
+// (weno3z_ref, lfb_math.cuh).  `a` = shared byte address of the cell on the high side of the face.
+template <int S>
+__device__ __noinline__ double zt_face_buffer(unsigned a, double q, int order)
+{
+    const double cm = lds(a), cm1 = lds(a - S);
+    if (order == 1) return cm;
+    if (order == 0) return cm1;
+    if (order == 2) return (cm1 + cm) / 2.0;
+    const bool left = q > 0.0;
+    const double o = left ? lds(a - 2 * S) : lds(a + S);
+    return weno3z_ref<double>(o, left ? cm1 : cm, left ? cm : cm1);
+}
+
 // top face of cell k next to the walls (1-based face index m = k + 2 outside 4 .. Nz - 2): WENO3-Z, Centered2, wall
 // 
 __device__ __noinline__ double zt_top_face_buffer(int m, int Nz, double cw, double d1, double d2, double d3, double ck, double ck1)
@@ -220,7 +248,9 @@ __device__ __noinline__ double zt_top_face_buffer(int m, int Nz, double cw, doub
 #define ZT_PB 2           // planes per block barrier
 #endif
 
-template <int NSUB, int TY>
+// WALLS: the grid has a Bounded x or y axis (buffer schemes next to those walls); compiled separately so that the
+// all-periodic form keeps its register allocation.
+template <int NSUB, int TY, bool WALLS>
 __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(const __grid_constant__ LfbZtParams P)
 {
     using SM = ZtSmem<NSUB, TY>;
@@ -319,6 +349,9 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         const unsigned aQ = sbase + (kind == 1 ? oV + 8u * (ty * 32 + tx) : oU + 8u * (ty * ZT_CW + tx + ZT_HX));
         const unsigned aF = sbase + (kind == 1 ? oFY + 8u * (sub * SM::VT + ty * 32 + tx)
                                                : oFX + 8u * (sub * SM::CTP + (ty + 3) * ZT_CW + tx + ZT_HX));
+        // scheme of this lane's face (lower order next to the walls of a Bounded axis)
+        const int h_order = kind == 1 ? zt_face_order(L.goff[1] + j0 + ty + 1, L.NG[1], L.topo[1] == LFB_BOUNDED)
+                                      : zt_face_order(L.goff[0] + i0 + tx + 1, L.NG[0], L.topo[0] == LFB_BOUNDED);
         if (face_lane) mbar_wait(barP, 0);
         __syncwarp();
         block_barrier();                 // prologue barrier: see the main warps
@@ -341,7 +374,8 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
                     mbar_wait(bar0 + 8u * (k & (ZT_RI - 1)), (k / ZT_RI) & 1);
                     const unsigned cs = (unsigned)((k + 2) & (ZT_RC - 1)) * CSLOT_B;
                     const double q = lds(aQ + (unsigned)(k & (ZT_RI - 1)) * ISLOT_B);
-                    const double cf = kind == 1 ? zt_face<ROW_B>(aT + cs, q, K) : zt_face<8>(aT + cs, q, K);
+                    double cf = kind == 1 ? zt_face<ROW_B>(aT + cs, q, K) : zt_face<8>(aT + cs, q, K);
+                    if (WALLS && h_order != 5) cf = kind == 1 ? zt_face_buffer<ROW_B>(aT + cs, q, h_order) : zt_face_buffer<8>(aT + cs, q, h_order);
                     sts(aF + (unsigned)(k & (ZT_RI - 1)) * FBUF_B, q * cf);
                 }
             }
@@ -373,6 +407,11 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             if (j < L.H[1]) ywrap = (int64_t)L.N[1] * L.pitch; else if (j >= L.N[1] - L.H[1]) ywrap = -(int64_t)L.N[1] * L.pitch;
         }
     }
+    // scheme of the west / south face of this column, and (block-uniform) whether any face of the tile is next to a wall
+    const int ox = zt_face_order(L.goff[0] + i0 + tx + 1, L.NG[0], L.topo[0] == LFB_BOUNDED);
+    const int oy = zt_face_order(L.goff[1] + j0 + ty + 1, L.NG[1], L.topo[1] == LFB_BOUNDED);
+    const bool tile_walls = (L.topo[0] == LFB_BOUNDED && (L.goff[0] + i0 < 3 || L.goff[0] + i0 + ZT_TX + 1 >= L.NG[0] - 1)) ||
+                            (L.topo[1] == LFB_BOUNDED && (L.goff[1] + j0 < 3 || L.goff[1] + j0 + TY + 1 >= L.NG[1] - 1));
     // block-uniform: does any column of this tile have a periodic image?
     const bool tile_wraps = (L.fuse_halo[0] && (i0 < L.H[0] || i0 + ZT_TX > L.N[0] - L.H[0])) ||
                             (L.fuse_halo[1] && (j0 < L.H[1] || j0 + TY > L.N[1] - L.H[1]));
@@ -439,8 +478,13 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         const double cu = lds(a40 + oU + is), cv = lds(a32 + oV + is);
         const double cw = lds(a32 + oW + NT_B + is);
         if (!FAST && k == 0) wb = lds(a32 + oW + is);
-        const double Fw = cu * zt_face<8>(aCk, cu, K);
-        const double Fs = cv * zt_face<ROW_B>(aCk, cv, K);
+        double fx = zt_face<8>(aCk, cu, K), fy = zt_face<ROW_B>(aCk, cv, K);
+        if (WALLS && tile_walls) {                        // buffer schemes next to the walls of Bounded x / y axes
+            if (ox != 5) fx = zt_face_buffer<8>(aCk, cu, ox);
+            if (oy != 5) fy = zt_face_buffer<ROW_B>(aCk, cv, oy);
+        }
+        const double Fw = cu * fx;
+        const double Fs = cv * fy;
         sts(a40s + oFX + fb, Fw);
         sts(a32s + oFY + fb, Fs);
         if (!FAST && k == 0) Fb = wb * ck;               // wall face m = 1: Centered2 on the mirrored halo
@@ -586,8 +630,7 @@ extern "C" int lfb_ztma_supported(const LfbStageParams *P)
 {
     const LfbLayout &L = P->L;
     if (!P->advect || P->relax) return 0;
-    if (L.topo[0] != LFB_PERIODIC || L.topo[2] != LFB_BOUNDED) return 0;
-    if (L.topo[1] != LFB_PERIODIC && !(L.connected_lo[1] && L.connected_hi[1])) return 0;
+    if (L.topo[0] == LFB_FLAT || L.topo[1] == LFB_FLAT || L.topo[2] != LFB_BOUNDED) return 0;
     if (!(P->vel_present[0] && P->vel_present[1] && P->vel_present[2])) return 0;
     if (L.N[0] < 8 || L.N[1] < 4 || L.N[2] < 8) return 0;
     if (L.H[0] < 3 || L.H[1] < 3 || L.H[2] < 3) return 0;
@@ -597,13 +640,13 @@ extern "C" int lfb_ztma_supported(const LfbStageParams *P)
 
 extern "C" int lfb_ztma_tile_rows(void) { return ZT_TY; }
 
-template <int NSUB, int TY>
+template <int NSUB, int TY, bool WALLS>
 static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
 {
     using SM = ZtSmem<NSUB, TY>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(lfb_stage_ztma<NSUB, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES);
+        cudaError_t e = cudaFuncSetAttribute(lfb_stage_ztma<NSUB, TY, WALLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -632,12 +675,14 @@ static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
     P.scratch = S->scratch;
     const int ytiles = (S->j1 - S->j0 + TY - 1) / TY;
     dim3 grid(S->n_items * ytiles, (L.N[0] + ZT_TX - 1) / ZT_TX, 1);
-    lfb_stage_ztma<NSUB, TY><<<grid, SM::THREADS, SM::BYTES, stream>>>(P);
+    lfb_stage_ztma<NSUB, TY, WALLS><<<grid, SM::THREADS, SM::BYTES, stream>>>(P);
     return cudaGetLastError();
 }
 
 extern "C" cudaError_t lfb_launch_stage_ztma(const LfbStageParams *P, cudaStream_t stream)
 {
     if (P->j1 <= P->j0) return cudaSuccess;
-    return P->single_exp ? zt_launch<1, ZT_TY>(P, stream) : zt_launch<2, ZT_TY>(P, stream);
+    const bool walls = P->L.topo[0] == LFB_BOUNDED || P->L.topo[1] == LFB_BOUNDED;
+    if (walls) return P->single_exp ? zt_launch<1, ZT_TY, true>(P, stream) : zt_launch<2, ZT_TY, true>(P, stream);
+    return P->single_exp ? zt_launch<1, ZT_TY, false>(P, stream) : zt_launch<2, ZT_TY, false>(P, stream);
 }

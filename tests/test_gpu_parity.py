@@ -302,6 +302,30 @@ def test_ztma_partial_tiles_in_x_and_y(size):
         assert rel_l2(b, a) < TOL_STEP
 
 
+@pytest.mark.parametrize("size,topology,N", [
+    ((40, 12, 10), ("Periodic", "Bounded", "Bounded"), 2),        # channel: walls in y
+    ((33, 9, 12), ("Bounded", "Bounded", "Bounded"), 2),          # box
+    ((36, 20, 9), ("Bounded", "Periodic", "Bounded"), 1),         # walls in x, single exponential
+    ((70, 17, 14), ("Periodic", "Bounded", "Bounded"), 4),        # several x tiles, partial tiles, two coefficient sets
+])
+def test_ztma_bounded_x_y_vs_oracle(size, topology, N):
+    """The TMA z-march kernel with Bounded x / y axes (buffer schemes WENO3 / Centered2 / wall next to the walls,
+    SURVEY App. A.5) against the CPU oracle: every tracer after several RK3 steps."""
+    g = lfb200.RectilinearGrid(size=size, extent=tuple(float(s) for s in size), topology=topology)
+    var_names, vel_names = ("T", "b"), ("u", "v", "w")
+    times = [0.0, 0.5, 1.0]
+    fields = make_series(g, times, var_names=var_names, velocity_names=vel_names, T_period=2.0)
+    fp = lfb200.set_offline_BW2_filter_params(N=N, freq_c=2 * np.pi / 2.0)
+    o, m = make_pair(g, var_names, vel_names, fp, times, fields, kernel="ztma")
+    assert m.kernel_name == "ztma"
+    names = oracle_names(var_names, vel_names, fp)
+    o.init_from_data(); m.init_from_data()
+    for dt in (0.1, 0.1, 0.05, 0.25, 0.2):
+        o.step(dt); m.step(dt)
+    compare_state(o, m, names, TOL_STEP)
+    m.close(); o.close()
+
+
 def test_zmarch_matches_generic_on_larger_grid():
     g = lfb200.RectilinearGrid(size=(128, 64, 40), extent=(128.0, 64.0, 40.0), topology=("Periodic", "Periodic", "Bounded"))
     var_names, vel_names = ("T", "b"), ("u", "v", "w")
