@@ -64,7 +64,7 @@ extern "C" {
 #define LFB_KERNEL_ZSPLIT  3      /* z-march with one thread per face direction (warp-specialised) */
 #define LFB_KERNEL_ZTMA    4      /* z-march with TMA-staged tiles; what LFB_KERNEL_AUTO selects on
                                    * 3-D grids Bounded in z (x, y Periodic or Bounded), u,v,w present,
-                                   * WENO advection, no relaxation, strict = 0                       */
+                                   * WENO advection (boundary relaxation included), strict = 0       */
 
 /* field ids for snapshots */
 #define LFB_FIELD_U 0

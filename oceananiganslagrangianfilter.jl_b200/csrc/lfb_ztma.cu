@@ -59,6 +59,7 @@ struct LfbZtParams {
     alignas(64) CUtensorMap mW;                  // w                               box 32 x TY x 2 (bottom and top faces)
     alignas(64) CUtensorMap mF[LFB_MAX_VARS];    // original variables, snapshot at or before the stage time, box 32 x TY
     alignas(64) CUtensorMap mF2[LFB_MAX_VARS];   // ... snapshot after it (linear interpolation in the forcing term)
+    alignas(64) CUtensorMap mM;                  // relaxation mask (boundary_relaxation), box 32 x TY
     double k133, k13, k16, eps43, rd[3];         // 13/3, 1/3, 1/6, 4/3 eps, area / volume per axis
     double *scratch;                             // one field: store target of the rows beyond j1 in partial tiles
 };
@@ -74,8 +75,9 @@ struct ZtSmem {
     static constexpr int UT = TY * ZT_CW;                        // [TY][40]
     static constexpr int VT = (TY + 1) * 32;                     // [TY+1][32]
     static constexpr int OFF_U = 0, OFF_V = UT, OFF_W = OFF_V + VT, OFF_G = OFF_W + 2 * NT, OFF_F = OFF_G + NSUB * VT,
-                         OFF_F2 = OFF_F + NT;                    // forcing variable: the two bracketing snapshots
-    static constexpr int ISLOT = OFF_F2 + NT;                    // doubles per input slot
+                         OFF_F2 = OFF_F + NT,                    // forcing variable: the two bracketing snapshots
+                         OFF_M = OFF_F2 + NT;                    // relaxation mask
+    static constexpr int ISLOT = OFF_M + NT;                     // doubles per input slot
     static constexpr int CSLOT = NSUB * CTP;
     static constexpr int FBUF = NSUB * (CTP + VT);               // Fx[NSUB] (tracer-tile geometry), Fy[NSUB][TY+1][32]
     static constexpr int O_C = 0;
@@ -248,8 +250,8 @@ __device__ __noinline__ double zt_top_face_buffer(int m, int Nz, double cw, doub
 #define ZT_PB 2           // planes per block barrier
 #endif
 
-// WALLS: the grid has a Bounded x or y axis (buffer schemes next to those walls); compiled separately so that the
-// all-periodic form keeps its register allocation.
+// WALLS: the general instantiation -- Bounded x or y axes (buffer schemes next to those walls) and boundary relaxation;
+// compiled separately so that the all-periodic form keeps its register allocation.
 template <int NSUB, int TY, bool WALLS>
 __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(const __grid_constant__ LfbZtParams P)
 {
@@ -261,7 +263,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
                        VT_B = 8u * SM::VT, NT_B = 8u * SM::NT;
     constexpr unsigned oC = 8u * SM::O_C, oIN = 8u * SM::O_IN, oFL = 8u * SM::O_FL, oBAR = 8u * SM::O_BAR;
     constexpr unsigned oU = oIN + 8u * SM::OFF_U, oV = oIN + 8u * SM::OFF_V, oW = oIN + 8u * SM::OFF_W,
-                       oG = oIN + 8u * SM::OFF_G, oF = oIN + 8u * SM::OFF_F, oF2 = oIN + 8u * SM::OFF_F2;
+                       oG = oIN + 8u * SM::OFF_G, oF = oIN + 8u * SM::OFF_F, oF2 = oIN + 8u * SM::OFF_F2, oM = oIN + 8u * SM::OFF_M;
     constexpr unsigned oFX = oFL, oFY = oFL + NSUB * CTP_B;
     const LfbStageParams &S = P.S;
     const LfbLayout &L = S.L;
@@ -274,6 +276,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     const int Nz = L.N[2];
     const bool use_G = !S.first_stage;
     const bool item_var = !item.is_map;
+    const bool relax = WALLS && S.relax;                  // boundary relaxation: only in the general instantiation
     const ZtK K = {P.k133, P.k13, P.k16, P.eps43};
     const unsigned bar0 = sbase + oBAR, barP = bar0 + 8u * ZT_RI;
 
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         // One loop for the whole warp (bar.sync is warp-aligned): the producer lane issues the TMA loads of the planes
         // ZT_D ahead, the face lanes compute their edge faces, idle lanes only keep the barrier count.
         const int cx = L.xoff + i0 - ZT_HX, cy = L.H[1] + j0 - 3, ix = L.xoff + i0, iy = L.H[1] + j0, z0 = L.H[2];
-        const unsigned in_bytes = 8u * (ZT_CW * TY + 32 * (TY + 1) + 2 * 32 * TY) + (use_G ? NSUB * NT_B : 0u) + (item_var ? 2 * NT_B : 0u);
+        const unsigned in_bytes = 8u * (ZT_CW * TY + 32 * (TY + 1) + 2 * 32 * TY) + (use_G ? NSUB * NT_B : 0u) + (item_var ? 2 * NT_B : 0u) + (relax ? NT_B : 0u);
         auto issue_C = [&](int pz, unsigned bar) {            // haloed tracer planes at z index pz (-2 .. Nz+2)
             const unsigned dst = sbase + oC + (unsigned)((pz + 2) & (ZT_RC - 1)) * CSLOT_B;
 #pragma unroll
@@ -320,6 +323,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
                 tma_load_3d(is + oF, &P.mF[item.src], ix, iy, z0 + g, bar);
                 tma_load_3d(is + oF2, &P.mF2[item.src], ix, iy, z0 + g, bar);
             }
+            if (relax) tma_load_3d(is + oM, &P.mM, ix, iy, z0 + g, bar);
         };
         // L2 prefetch of the tiles of group g (the shared-memory rings only allow the loads themselves to run one barrier
         // interval ahead; the prefetch runs ZT_PF planes ahead and costs no shared memory)
@@ -435,6 +439,17 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             aS1 = a32 + oF; aS2 = a32 + oF2;
         }
     }
+    // boundary relaxation (utils:584-699): forcing += (1 / tau_r) mask (g_eq - g), g_eq = kq * src with
+    // src = wA src1 + wB src2 the interpolated variable / the cell-centred velocity
+    double kq = 0.0, wA = 0.5, wB = 0.5, inv_tau = 0.0;
+    if (relax) {
+        const double c = item.c, d = item.d, n2 = c * c + d * d;
+        inv_tau = 1.0 / S.relax_timescale;
+        if (!item.is_map) { wA = S.var_w1; wB = S.var_w2; }
+        if (NSUB == 1)     kq = item.is_map ? -1.0 / (c * c) : 1.0 / c;
+        else if (sub == 0) kq = item.is_map ? (d * d - c * c) / (n2 * n2) : c / n2;
+        else               kq = item.is_map ? (-2.0 * c * d) / (n2 * n2) : d / n2;
+    }
     const double dtg = S.dt * S.gamma, dtz = S.dt * S.zeta;
     const double rdx = P.rd[0], rdy = P.rd[1], rdz = P.rd[2];
     const double nrdx = -rdx, nrdy = -rdy;
@@ -503,7 +518,9 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         const double Ft = cw * ct;
         // ---- own part of the tendency: c du - dF per axis in units of face velocity, forcing, G^- part of the substep ----
         const double ue = lds(a40 + oU + is + 8), vn = lds(a32 + oV + is + 8 * 32);
-        double forcing = fma(kA, lds(aS1 + is), fma(kB, lds(aS2 + is), k_own * ck));
+        const double sA = lds(aS1 + is), sB = lds(aS2 + is);
+        double forcing = fma(kA, sA, fma(kB, sB, k_own * ck));
+        if (relax) forcing = fma(lds(a32 + oM + is) * inv_tau, fma(kq, fma(wA, sA, wB * sB), -ck), forcing);
         if (NSUB == 2) forcing = fma(k_oth, lds(aCk + partner_off), forcing);
         const double az = fma(ck, cw - wb, Fb - Ft);
         part[p] = fma(rdx, fma(ck, ue - cu, Fw), fma(rdy, fma(ck, vn - cv, Fs), fma(rdz, az, forcing)));
@@ -629,7 +646,7 @@ static int zt_make_map(CUtensorMap *m, const LfbLayout &L, const void *base, int
 extern "C" int lfb_ztma_supported(const LfbStageParams *P)
 {
     const LfbLayout &L = P->L;
-    if (!P->advect || P->relax) return 0;
+    if (!P->advect || (P->relax && !P->mask)) return 0;
     if (L.topo[0] == LFB_FLAT || L.topo[1] == LFB_FLAT || L.topo[2] != LFB_BOUNDED) return 0;
     if (!(P->vel_present[0] && P->vel_present[1] && P->vel_present[2])) return 0;
     if (L.N[0] < 8 || L.N[1] < 4 || L.N[2] < 8) return 0;
@@ -669,6 +686,7 @@ static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
             bad |= zt_make_map(&P.mF[q], L, S->var[q], 0, 32, TY);
             bad |= zt_make_map(&P.mF2[q], L, S->var_fused ? S->var2[q] : S->var[q], 0, 32, TY);
         }
+    if (S->relax) bad |= zt_make_map(&P.mM, L, S->mask, 0, 32, TY);
     if (bad) return cudaErrorInvalidValue;
     P.k133 = 13.0 / 3.0; P.k13 = 1.0 / 3.0; P.k16 = 1.0 / 6.0; P.eps43 = LFB_WENO_EPS * (4.0 / 3.0);
     for (int a = 0; a < 3; ++a) P.rd[a] = S->area[a] / S->volume;
@@ -682,7 +700,7 @@ static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
 extern "C" cudaError_t lfb_launch_stage_ztma(const LfbStageParams *P, cudaStream_t stream)
 {
     if (P->j1 <= P->j0) return cudaSuccess;
-    const bool walls = P->L.topo[0] == LFB_BOUNDED || P->L.topo[1] == LFB_BOUNDED;
+    const bool walls = P->L.topo[0] == LFB_BOUNDED || P->L.topo[1] == LFB_BOUNDED || P->relax;       // the general instantiation
     if (walls) return P->single_exp ? zt_launch<1, ZT_TY, true>(P, stream) : zt_launch<2, ZT_TY, true>(P, stream);
     return P->single_exp ? zt_launch<1, ZT_TY, false>(P, stream) : zt_launch<2, ZT_TY, false>(P, stream);
 }

@@ -326,6 +326,33 @@ def test_ztma_bounded_x_y_vs_oracle(size, topology, N):
     m.close(); o.close()
 
 
+@pytest.mark.parametrize("size,topology,N", [
+    ((40, 12, 10), ("Periodic", "Bounded", "Bounded"), 2),
+    ((33, 10, 9), ("Bounded", "Bounded", "Bounded"), 1),
+    ((64, 16, 12), ("Periodic", "Periodic", "Bounded"), 2),
+])
+def test_ztma_boundary_relaxation_vs_oracle(size, topology, N):
+    """boundary_relaxation (reference utils:584-699: -(1/tau_r) (g - g_eq) mask) on the TMA z-march kernel: filtered
+    variables and maps, cosine and sine tracers, single exponential, against the CPU oracle."""
+    g = lfb200.RectilinearGrid(size=size, extent=tuple(float(s) for s in size), topology=topology)
+    var_names, vel_names = ("T", "b"), ("u", "v", "w")
+    times = [0.0, 0.5, 1.0]
+    fields = make_series(g, times, var_names=var_names, velocity_names=vel_names, T_period=2.0)
+    fp = lfb200.set_offline_BW2_filter_params(N=N, freq_c=2 * np.pi / 2.0)
+    y = g.nodes(1)[None, :, None]
+    z = g.nodes(2)[None, None, :]
+    mask = np.asfortranarray(np.exp(-((y - g.origin[1]) / 2.0) ** 2) + np.exp(-((y - g.origin[1] - g.L[1]) / 2.0) ** 2)
+                             + 0.1 * np.cos(z) ** 2 + 0 * g.nodes(0)[:, None, None])
+    o, m = make_pair(g, var_names, vel_names, fp, times, fields, kernel="ztma", relax_timescale=0.7, mask=mask)
+    assert m.kernel_name == "ztma"
+    names = oracle_names(var_names, vel_names, fp)
+    o.init_from_data(); m.init_from_data()
+    for dt in (0.1, 0.1, 0.05, 0.25, 0.2):
+        o.step(dt); m.step(dt)
+    compare_state(o, m, names, TOL_STEP)
+    m.close(); o.close()
+
+
 def test_zmarch_matches_generic_on_larger_grid():
     g = lfb200.RectilinearGrid(size=(128, 64, 40), extent=(128.0, 64.0, 40.0), topology=("Periodic", "Periodic", "Bounded"))
     var_names, vel_names = ("T", "b"), ("u", "v", "w")
