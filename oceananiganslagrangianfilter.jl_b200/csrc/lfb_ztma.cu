@@ -46,6 +46,9 @@
 #define ZT_RC 8           // ring of haloed tracer planes: k .. k+4 live, 2 in flight, 1 being released
 #define ZT_RI 4           // ring of per-plane input tiles, of flux buffers and of group mbarriers
 #define ZT_D  2           // planes the producer runs ahead
+#ifndef ZT_L2_PROMOTION
+#define ZT_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+#endif
 #ifndef ZT_PF
 #define ZT_PF 0           // planes an L2 prefetch (cp.async.bulk.prefetch.tensor) runs ahead; 0 = off: measured slower (6: +2 %, 10: +7 %)
 #endif
@@ -639,7 +642,7 @@ static int zt_make_map(CUtensorMap *m, const LfbLayout &L, const void *base, int
     cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, const_cast<void *>(base), dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_NONE, ZT_L2_PROMOTION, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 
