@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     const unsigned a40 = sbase + 8u * (ty * ZT_CW + tx + ZT_HX), a40s = a40 + 3 * ROW_B + sub * CTP_B;
     const int partner_off = NSUB == 2 ? (sub ? -(int)CTP_B : (int)CTP_B) : 0;
     const bool active = j0 + ty < S.j1 && i0 + tx < L.N[0];         // partial tiles at the end of the y range / of x
-    const int64_t plane = L.plane;
+    const int64_t plane_b = L.plane * 8;                             // byte stride between planes
     // rows beyond j1 / columns beyond Nx (partial tiles) compute like the others but store into the scratch field
     const int64_t cell0 = L.at(i0 + tx, j0 + ty, 0);
     double *__restrict__ pUn = active ? S.U_new + cell0 + (int64_t)(item.tracer_c + sub) * L.len : P.scratch + cell0;
@@ -511,10 +511,9 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             // the window is used by a warp-uniform branch per direction (both only in warps that straddle w = 0)
             const bool left = zt_positive(cw);
             const unsigned ml = __ballot_sync(0xffffffffu, left);
-            double ctL = ck, ctR = ck1;
-            if (ml != 0u) ctL = ck + zt_inc_q(d0, d1, d2, d3, Qa, Qb, Qc, K);
-            if (ml != 0xffffffffu) ctR = ck1 - zt_inc_q(d4, d3, d2, d1, Qd, Qc, Qb, K);
-            ct = left ? ctL : ctR;
+            ct = ck1;
+            if (ml != 0xffffffffu) ct = ck1 - zt_inc_q(d4, d3, d2, d1, Qd, Qc, Qb, K);
+            if (ml != 0u) { const double ctL = ck + zt_inc_q(d0, d1, d2, d3, Qa, Qb, Qc, K); ct = left ? ctL : ct; }
         } else {
             ct = zt_top_face_buffer(k + 2, Nz, cw, d1, d2, d3, ck, ck1);
         }
@@ -563,7 +562,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             if (xwrap) pUn[xwrap] = unew;
             if (ywrap) { pUn[ywrap] = unew; if (xwrap) pUn[xwrap + ywrap] = unew; }
         }
-        pUn += plane;
+        pUn = reinterpret_cast<double *>(reinterpret_cast<char *>(pUn) + plane_b);
     };
     using Dyn = std::integral_constant<int, -1>;
     // generic planes [ka, kb), ZT_PB per barrier
