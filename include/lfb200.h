@@ -63,7 +63,7 @@ extern "C" {
 #define LFB_KERNEL_ZMARCH  2      /* shared-memory x-y tiles marching in z, faces computed once  */
 #define LFB_KERNEL_ZSPLIT  3      /* z-march with one thread per face direction (warp-specialised) */
 #define LFB_KERNEL_ZTMA    4      /* z-march with TMA-staged tiles; what LFB_KERNEL_AUTO selects on
-                                   * 3-D grids Bounded in z (x, y Periodic or Bounded), u,v,w present,
+                                   * 3-D grids (x, y, z Periodic or Bounded), u,v,w present,
                                    * WENO advection (boundary relaxation included), strict = 0       */
 
 /* field ids for snapshots */

@@ -178,13 +178,13 @@ static int select_kernel(lfb_handle *h)
     // 0 generic, 1 z-march (cp.async staging), 2 role-split z-march, 3 TMA-staged z-march (what `auto` picks)
     const int ok_cp = lfb_zmarch_supported(&P) && !h->desc.strict;          // needs Nx % 32 == 0
     const int ok_tma = lfb_ztma_supported(&P) && !h->desc.strict;
-    const char *need = "a 3-D grid Bounded in z (x, y Periodic, Bounded or slab-decomposed) with Nz >= 8, u,v,w all present, WENO advection and strict = 0";
+    const char *need = "a 3-D grid (no Flat axis) with Nz >= 8, u,v,w all present, WENO advection and strict = 0";
     h->use_zmarch = 0;
     switch (h->desc.kernel) {
     case LFB_KERNEL_GENERIC: break;
     case LFB_KERNEL_ZMARCH:
     case LFB_KERNEL_ZSPLIT:
-        if (!ok_cp) return fail(LFB_ERR_ARG, "the cp.async z-marching kernels need %s, Periodic x and y, no relaxation and Nx %% 32 == 0", need);
+        if (!ok_cp) return fail(LFB_ERR_ARG, "the cp.async z-marching kernels need %s, Periodic x and y, Bounded z, no relaxation and Nx %% 32 == 0", need);
         h->use_zmarch = h->desc.kernel == LFB_KERNEL_ZMARCH ? 1 : 2;
         break;
     case LFB_KERNEL_ZTMA:

@@ -1,5 +1,5 @@
-// lfb_ztma.cu -- TMA-staged z-marching RK3 stage kernel (production path on 3-D grids that are Bounded in z and
-// Periodic, Bounded or slab-decomposed in x and y).
+// lfb_ztma.cu -- TMA-staged z-marching RK3 stage kernel (production path on 3-D grids: Periodic, Bounded or
+// slab-decomposed in x and y, Bounded or Periodic in z).
 //
 // Same fused work as lfb_stage_generic / lfb_stage_zmarch (WENO5-Z flux divergence, c div(U), forcing, RK3
 // substep, tendency caching, periodic halo images; reference call sites: compute_Gc! / tracer_tendency,
@@ -253,7 +253,7 @@ __device__ __noinline__ double zt_top_face_buffer(int m, int Nz, double cw, doub
 #define ZT_PB 2           // planes per block barrier
 #endif
 
-// WALLS: the general instantiation -- Bounded x or y axes (buffer schemes next to those walls) and boundary relaxation;
+// WALLS: the general instantiation -- Bounded x or y axes (buffer schemes next to those walls), Periodic z and boundary relaxation;
 // compiled separately so that the all-periodic form keeps its register allocation.
 template <int NSUB, int TY, bool WALLS>
 __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(const __grid_constant__ LfbZtParams P)
@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     const bool use_G = !S.first_stage;
     const bool item_var = !item.is_map;
     const bool relax = WALLS && S.relax;                  // boundary relaxation: only in the general instantiation
+    const bool zper = WALLS && L.topo[2] == LFB_PERIODIC; // Periodic z: likewise
     const ZtK K = {P.k133, P.k13, P.k16, P.eps43};
     const unsigned bar0 = sbase + oBAR, barP = bar0 + 8u * ZT_RI;
 
@@ -462,10 +463,12 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     double Qa, Qb, Qc, Qd;                       // Q[k-1..k+2], Q[m] = 13/3 (d[m] - d[m-1])^2 + 4/3 eps
     double ck, ck1, ck3;                         // c[k], c[k+1], c[k+3]
     double Fb = 0.0, wb = 0.0;                   // flux through / w at the bottom face of cell k
+    double dm3 = 0.0;                            // Periodic z: d[-3], for the bottom face of cell 0
     mbar_wait(barP, 0);
     {
         const unsigned aC = a40s + oC;
         const double cm2 = lds(aC + 0 * CSLOT_B), cm1 = lds(aC + 1 * CSLOT_B);
+        if (zper) dm3 = cm2 - S.U_old[(int64_t)(item.tracer_c + sub) * L.len + L.at(i0 + tx, j0 + ty, -3)];
         ck = lds(aC + 2 * CSLOT_B); ck1 = lds(aC + 3 * CSLOT_B);
         const double ck2 = lds(aC + 4 * CSLOT_B);
         ck3 = lds(aC + 5 * CSLOT_B);
@@ -505,9 +508,16 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         const double Fs = cv * fy;
         sts(a40s + oFX + fb, Fw);
         sts(a32s + oFY + fb, Fs);
-        if (!FAST && k == 0) Fb = wb * ck;               // wall face m = 1: Centered2 on the mirrored halo
+        if (!FAST && k == 0) {
+            if (zper) {
+                // Periodic z: the bottom face of cell 0 is a WENO5 face between cells -1 and 0 (c[-1] = c[0] - d[-1])
+                Fb = wb * (zt_positive(wb) ? (ck - d1) + zt_inc(dm3, d0, d1, d2, K) : ck - zt_inc(d3, d2, d1, d0, K));
+            } else {
+                Fb = wb * ck;                            // wall face m = 1: Centered2 on the mirrored halo
+            }
+        }
         double ct;
-        if (FAST || (k >= 2 && k <= Nz - 4)) {
+        if (FAST || zper || (k >= 2 && k <= Nz - 4)) {
             // the window is used by a warp-uniform branch per direction (both only in warps that straddle w = 0)
             const bool left = zt_positive(cw);
             const unsigned ml = __ballot_sync(0xffffffffu, left);
@@ -561,6 +571,14 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             // periodic halo images of the new state (the tracer halo fill of update_state!, fused)
             if (xwrap) pUn[xwrap] = unew;
             if (ywrap) { pUn[ywrap] = unew; if (xwrap) pUn[xwrap + ywrap] = unew; }
+        }
+        if (zper && L.fuse_halo[2] && (k < L.H[2] || k >= Nz - L.H[2])) {
+            double *pz = reinterpret_cast<double *>(reinterpret_cast<char *>(pUn) + (k < L.H[2] ? Nz : -Nz) * plane_b);
+            pz[0] = unew;
+            if (tile_wraps) {
+                if (xwrap) pz[xwrap] = unew;
+                if (ywrap) { pz[ywrap] = unew; if (xwrap) pz[xwrap + ywrap] = unew; }
+            }
         }
         pUn = reinterpret_cast<double *>(reinterpret_cast<char *>(pUn) + plane_b);
     };
@@ -649,7 +667,8 @@ extern "C" int lfb_ztma_supported(const LfbStageParams *P)
 {
     const LfbLayout &L = P->L;
     if (!P->advect || (P->relax && !P->mask)) return 0;
-    if (L.topo[0] == LFB_FLAT || L.topo[1] == LFB_FLAT || L.topo[2] != LFB_BOUNDED) return 0;
+    if (L.topo[0] == LFB_FLAT || L.topo[1] == LFB_FLAT || L.topo[2] == LFB_FLAT) return 0;
+    if (L.topo[2] == LFB_PERIODIC && L.N[2] < 2 * L.H[2]) return 0;
     if (!(P->vel_present[0] && P->vel_present[1] && P->vel_present[2])) return 0;
     if (L.N[0] < 8 || L.N[1] < 4 || L.N[2] < 8) return 0;
     if (L.H[0] < 3 || L.H[1] < 3 || L.H[2] < 3) return 0;
@@ -702,7 +721,7 @@ static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
 extern "C" cudaError_t lfb_launch_stage_ztma(const LfbStageParams *P, cudaStream_t stream)
 {
     if (P->j1 <= P->j0) return cudaSuccess;
-    const bool walls = P->L.topo[0] == LFB_BOUNDED || P->L.topo[1] == LFB_BOUNDED || P->relax;       // the general instantiation
+    const bool walls = P->L.topo[0] == LFB_BOUNDED || P->L.topo[1] == LFB_BOUNDED || P->L.topo[2] == LFB_PERIODIC || P->relax;   // the general instantiation
     if (walls) return P->single_exp ? zt_launch<1, ZT_TY, true>(P, stream) : zt_launch<2, ZT_TY, true>(P, stream);
     return P->single_exp ? zt_launch<1, ZT_TY, false>(P, stream) : zt_launch<2, ZT_TY, false>(P, stream);
 }

@@ -307,6 +307,9 @@ def test_ztma_partial_tiles_in_x_and_y(size):
     ((33, 9, 12), ("Bounded", "Bounded", "Bounded"), 2),          # box
     ((36, 20, 9), ("Bounded", "Periodic", "Bounded"), 1),         # walls in x, single exponential
     ((70, 17, 14), ("Periodic", "Bounded", "Bounded"), 4),        # several x tiles, partial tiles, two coefficient sets
+    ((40, 12, 16), ("Periodic", "Periodic", "Periodic"), 2),      # Periodic z: WENO5 on every z face, z halo images
+    ((33, 10, 9), ("Bounded", "Periodic", "Periodic"), 2),
+    ((36, 9, 13), ("Periodic", "Bounded", "Periodic"), 1),
 ])
 def test_ztma_bounded_x_y_vs_oracle(size, topology, N):
     """The TMA z-march kernel with Bounded x / y axes (buffer schemes WENO3 / Centered2 / wall next to the walls,
