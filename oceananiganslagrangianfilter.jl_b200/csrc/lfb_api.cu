@@ -85,6 +85,7 @@ struct lfb_handle {
     double    *G;
     double    *scratch;                    // one field
     double    *mask;
+    double    *zero_field;                 // velocity components that are not in velocity_names (TMA z-march path)
     double    *cur_in[N_FIELD_IDS];           // inputs at the current stage time (update_input_data!)
     void      *staging;                    // dense parent array, device side
     size_t     staging_bytes;
@@ -260,6 +261,7 @@ extern "C" int lfb_create(const lfb_desc *desc, lfb_handle **out)
     const LfbLayout &L = h->L;
     const size_t fbytes = (size_t)L.len * sizeof(double);
     h->U[0] = h->U[1] = h->G = h->scratch = h->mask = nullptr;
+    h->zero_field = nullptr;
     h->staging = nullptr;
     h->comm = nullptr; h->rank = 0; h->nranks = 1; h->comm_stream = nullptr; h->halos_valid = 0;
     h->send_lo = h->send_hi = h->recv_lo = h->recv_hi = nullptr;
@@ -325,6 +327,7 @@ extern "C" int lfb_destroy(lfb_handle *h)
     for (auto &pr : h->timing) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaFree(h->U[0]); cudaFree(h->U[1]); cudaFree(h->G); cudaFree(h->scratch);
     if (h->mask) cudaFree(h->mask);
+    if (h->zero_field) cudaFree(h->zero_field);
     for (int f = 0; f < N_FIELD_IDS; ++f) if (h->cur_in[f]) cudaFree(h->cur_in[f]);
     cudaFree(h->staging);
     if (h->send_lo) { cudaFree(h->send_lo); cudaFree(h->send_hi); cudaFree(h->recv_lo); cudaFree(h->recv_hi); }
@@ -725,6 +728,15 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
         if (I.n_fields) { CU(lfb_launch_interp_inputs(&I, h->compute)); h->launches++; }
     }
     for (int ax = 0; ax < 3; ++ax) P.vel_present[ax] = (h->desc.velocity_mask >> ax) & 1;
+    if (h->use_zmarch == 3 && update)
+        for (int ax = 0; ax < 3; ++ax)
+            if (!P.vel_present[ax]) {                  // a component that is not advected with: zero face velocity
+                if (!h->zero_field) {
+                    CU(cudaMalloc(&h->zero_field, (size_t)h->L.len * sizeof(double)));
+                    CU(cudaMemsetAsync(h->zero_field, 0, (size_t)h->L.len * sizeof(double), h->compute));
+                }
+                P.vel[ax] = h->zero_field;
+            }
     P.mask = h->mask;
     const double dx = h->desc.spacing[0], dy = h->desc.spacing[1], dz = h->desc.spacing[2];
     P.area[0] = dy * dz; P.area[1] = dx * dz; P.area[2] = dx * dy; P.volume = dx * dy * dz;

@@ -669,7 +669,7 @@ extern "C" int lfb_ztma_supported(const LfbStageParams *P)
     if (!P->advect || (P->relax && !P->mask)) return 0;
     if (L.topo[0] == LFB_FLAT || L.topo[1] == LFB_FLAT || L.topo[2] == LFB_FLAT) return 0;
     if (L.topo[2] == LFB_PERIODIC && L.N[2] < 2 * L.H[2]) return 0;
-    if (!(P->vel_present[0] && P->vel_present[1] && P->vel_present[2])) return 0;
+    if (!(P->vel_present[0] || P->vel_present[1] || P->vel_present[2])) return 0;     // absent components: a zero field
     if (L.N[0] < 8 || L.N[1] < 4 || L.N[2] < 8) return 0;
     if (L.H[0] < 3 || L.H[1] < 3 || L.H[2] < 3) return 0;
     if (!zt_encoder()) return 0;

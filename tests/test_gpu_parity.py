@@ -356,6 +356,25 @@ def test_ztma_boundary_relaxation_vs_oracle(size, topology, N):
     m.close(); o.close()
 
 
+@pytest.mark.parametrize("vel_names", [("u", "w"), ("v", "w"), ("u", "v")])
+def test_ztma_with_absent_velocity_component(vel_names):
+    """A 3-D grid filtered with two of the three velocity components (the third is not advected with and has no
+    map): the TMA kernel substitutes a zero field; against the CPU oracle."""
+    g = lfb200.RectilinearGrid(size=(40, 12, 10), extent=(40.0, 12.0, 10.0), topology=("Periodic", "Periodic", "Bounded"))
+    var_names = ("T", "b")
+    times = [0.0, 0.5, 1.0]
+    fields = make_series(g, times, var_names=var_names, velocity_names=vel_names, T_period=2.0)
+    fp = lfb200.set_offline_BW2_filter_params(N=2, freq_c=2 * np.pi / 2.0)
+    o, m = make_pair(g, var_names, vel_names, fp, times, fields, kernel="auto")
+    assert m.kernel_name == "ztma"
+    names = oracle_names(var_names, vel_names, fp)
+    o.init_from_data(); m.init_from_data()
+    for dt in (0.1, 0.1, 0.05, 0.25, 0.2):
+        o.step(dt); m.step(dt)
+    compare_state(o, m, names, TOL_STEP)
+    m.close(); o.close()
+
+
 def test_zmarch_matches_generic_on_larger_grid():
     g = lfb200.RectilinearGrid(size=(128, 64, 40), extent=(128.0, 64.0, 40.0), topology=("Periodic", "Periodic", "Bounded"))
     var_names, vel_names = ("T", "b"), ("u", "v", "w")
