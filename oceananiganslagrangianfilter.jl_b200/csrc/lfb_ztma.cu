@@ -87,7 +87,7 @@ struct ZtSmem {
     static constexpr int O_IN = O_C + ZT_RC * CSLOT;
     static constexpr int O_FL = O_IN + ZT_RI * ISLOT;
     static constexpr int O_BAR = O_FL + ZT_RI * FBUF;            // ZT_RI group barriers + the prologue barrier
-    static constexpr int DOUBLES = O_BAR + 8;
+    static constexpr int DOUBLES = O_BAR + 8 + 8;                // + 2 x 4 relaxation coefficients
     static constexpr int BYTES = DOUBLES * 8;
     static constexpr int NMAIN = NSUB * NT;
     static constexpr int THREADS = NMAIN + NSUB * 32 + 32;
@@ -444,15 +444,19 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         }
     }
     // boundary relaxation (utils:584-699): forcing += (1 / tau_r) mask (g_eq - g), g_eq = kq * src with
-    // src = wA src1 + wB src2 the interpolated variable / the cell-centred velocity
-    double kq = 0.0, wA = 0.5, wB = 0.5, inv_tau = 0.0;
-    if (relax) {
+    // src = wA src1 + wB src2 the interpolated variable / the cell-centred velocity.  The four coefficients of a tracer
+    // sit in shared memory (behind the mbarriers), so that they cost no registers in the march.
+    const unsigned aRX = sbase + oBAR + 64u + 32u * sub;
+    if (relax && t == 0) {
         const double c = item.c, d = item.d, n2 = c * c + d * d;
-        inv_tau = 1.0 / S.relax_timescale;
-        if (!item.is_map) { wA = S.var_w1; wB = S.var_w2; }
+        double kq;
         if (NSUB == 1)     kq = item.is_map ? -1.0 / (c * c) : 1.0 / c;
         else if (sub == 0) kq = item.is_map ? (d * d - c * c) / (n2 * n2) : c / n2;
         else               kq = item.is_map ? (-2.0 * c * d) / (n2 * n2) : d / n2;
+        sts(aRX, kq);
+        sts(aRX + 8, item.is_map ? 0.5 : S.var_w1);
+        sts(aRX + 16, item.is_map ? 0.5 : S.var_w2);
+        sts(aRX + 24, 1.0 / S.relax_timescale);
     }
     const double dtg = S.dt * S.gamma, dtz = S.dt * S.zeta;
     const double rdx = P.rd[0], rdy = P.rd[1], rdz = P.rd[2];
@@ -532,7 +536,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         const double ue = lds(a40 + oU + is + 8), vn = lds(a32 + oV + is + 8 * 32);
         const double sA = lds(aS1 + is), sB = lds(aS2 + is);
         double forcing = fma(kA, sA, fma(kB, sB, k_own * ck));
-        if (relax) forcing = fma(lds(a32 + oM + is) * inv_tau, fma(kq, fma(wA, sA, wB * sB), -ck), forcing);
+        if (relax) forcing = fma(lds(a32 + oM + is) * lds(aRX + 24), fma(lds(aRX), fma(lds(aRX + 8), sA, lds(aRX + 16) * sB), -ck), forcing);
         if (NSUB == 2) forcing = fma(k_oth, lds(aCk + partner_off), forcing);
         const double az = fma(ck, cw - wb, Fb - Ft);
         part[p] = fma(rdx, fma(ck, ue - cu, Fw), fma(rdy, fma(ck, vn - cv, Fs), fma(rdz, az, forcing)));
