@@ -60,8 +60,7 @@ extern "C" {
 /* kernel selection (lfb_desc.kernel) */
 #define LFB_KERNEL_AUTO    0
 #define LFB_KERNEL_GENERIC 1      /* one thread per cell and coefficient pair, any topology      */
-#define LFB_KERNEL_ZMARCH  2      /* shared-memory x-y tiles marching in z, faces computed once  */
-#define LFB_KERNEL_ZSPLIT  3      /* z-march with one thread per face direction (warp-specialised) */
+                                  /* ids 2, 3: the retired cp.async z-march kernels (rejected)   */
 #define LFB_KERNEL_ZTMA    4      /* z-march with TMA-staged tiles; what LFB_KERNEL_AUTO selects on
                                    * 3-D grids (x, y, z Periodic or Bounded), u,v,w present,
                                    * WENO advection (boundary relaxation included), strict = 0       */
@@ -219,7 +218,7 @@ int lfb_stage_time_ms(lfb_handle *h, int reset, double *ms, int64_t *launches);
  * the device time between the two in milliseconds. */
 int lfb_timer_start(lfb_handle *h);
 int lfb_timer_stop(lfb_handle *h, double *ms);
-/* name of the stage kernel in use: "generic" | "generic-strict" | "zmarch" | "zsplit" | "ztma" */
+/* name of the stage kernel in use: "generic" | "generic-strict" | "ztma" */
 const char *lfb_kernel_name(const lfb_handle *h);
 /* raw device pointers for zero-copy hosts (torch): what = 0 tracer (current), 1 tendency,
  * 2 snapshot slot (idx = slot * 16 + field_id); internal padded layout, see lfb_layout */

@@ -17,7 +17,7 @@ MAX_COEFFS, MAX_VARS = 8, 8
 PERIODIC, BOUNDED, FLAT = 0, 1, 2
 TOPOLOGY = {"Periodic": PERIODIC, "Bounded": BOUNDED, "Flat": FLAT}
 ADVECTION_NONE, ADVECTION_WENO5 = 0, 1
-KERNEL_AUTO, KERNEL_GENERIC, KERNEL_ZMARCH, KERNEL_ZSPLIT, KERNEL_ZTMA = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_GENERIC, KERNEL_ZTMA = 0, 1, 4
 FIELD_U, FIELD_V, FIELD_W, FIELD_VAR0 = 0, 1, 2, 3
 OUT_FILTERED_VAR, OUT_XI, OUT_MEAN_VEL = 0, 1, 2
 ERR_NAMES = {-1: "LFB_ERR_ARG", -2: "LFB_ERR_CUDA", -3: "LFB_ERR_STATE", -4: "LFB_ERR_NO_DATA", -5: "LFB_ERR_COMM"}

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "liblfb200.so")
-SOURCES = ["lfb_api.cu", "lfb_generic.cu", "lfb_zmarch.cu", "lfb_zsplit.cu", "lfb_ztma.cu", "lfb_remap.cu"]
+SOURCES = ["lfb_api.cu", "lfb_generic.cu", "lfb_ztma.cu", "lfb_remap.cu"]
 HEADERS = ["lfb_internal.h", "lfb_math.cuh", "lfb_zm_common.cuh", os.path.join(ROOT, "include", "lfb200.h")]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

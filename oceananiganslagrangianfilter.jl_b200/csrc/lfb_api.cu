@@ -1,7 +1,7 @@
 // lfb_api.cu -- host side of liblfb200.so: the C ABI declared in include/lfb200.h.
 //
 // Owns device memory, streams and the RK3 / snapshot bookkeeping; all arithmetic on field data is
-// done by the kernels in lfb_generic.cu / lfb_zmarch.cu.  No CPU fallback exists: every entry point
+// done by the kernels in lfb_generic.cu / lfb_ztma.cu.  No CPU fallback exists: every entry point
 // that touches field data requires a CUDA device.
 #include <cuda_runtime.h>
 #include <nccl.h>
@@ -16,12 +16,9 @@
 
 #include "lfb_internal.h"
 
-// ---- kernel launchers (lfb_generic.cu, lfb_zmarch.cu) -------------------------------------------
+// ---- kernel launchers (lfb_generic.cu, lfb_ztma.cu) ---------------------------------------------
 extern "C" {
 cudaError_t lfb_launch_stage_generic(const LfbStageParams *P, int strict, cudaStream_t stream);
-cudaError_t lfb_launch_stage_zmarch(const LfbStageParams *P, cudaStream_t stream);
-cudaError_t lfb_launch_stage_zsplit(const LfbStageParams *P, cudaStream_t stream);
-int         lfb_zmarch_supported(const LfbStageParams *P);
 cudaError_t lfb_launch_stage_ztma(const LfbStageParams *P, cudaStream_t stream);
 int         lfb_ztma_supported(const LfbStageParams *P);
 int         lfb_ztma_tile_rows(void);
@@ -176,24 +173,20 @@ static int select_kernel(lfb_handle *h)
     P.mask = h->mask;
     for (int ax = 0; ax < 3; ++ax) P.vel_present[ax] = (h->desc.velocity_mask >> ax) & 1;
     P.j0 = 0; P.j1 = h->L.N[1];
-    // 0 generic, 1 z-march (cp.async staging), 2 role-split z-march, 3 TMA-staged z-march (what `auto` picks)
-    const int ok_cp = lfb_zmarch_supported(&P) && !h->desc.strict;          // needs Nx % 32 == 0
+    // 0 generic, 3 TMA-staged z-march (what `auto` picks when the grid allows it)
     const int ok_tma = lfb_ztma_supported(&P) && !h->desc.strict;
-    const char *need = "a 3-D grid (no Flat axis) with Nz >= 8, u,v,w all present, WENO advection and strict = 0";
+    const char *need = "a 3-D grid (no Flat axis) with Nx >= 8, Ny >= 4, Nz >= 8, halos >= 3, at least one velocity component, "
+                       "WENO(order=5) advection, RK3, no immersed boundary and strict = 0";
     h->use_zmarch = 0;
     switch (h->desc.kernel) {
+    case LFB_KERNEL_AUTO: h->use_zmarch = ok_tma ? 3 : 0; break;
     case LFB_KERNEL_GENERIC: break;
-    case LFB_KERNEL_ZMARCH:
-    case LFB_KERNEL_ZSPLIT:
-        if (!ok_cp) return fail(LFB_ERR_ARG, "the cp.async z-marching kernels need %s, Periodic x and y, Bounded z, no relaxation and Nx %% 32 == 0", need);
-        h->use_zmarch = h->desc.kernel == LFB_KERNEL_ZMARCH ? 1 : 2;
-        break;
     case LFB_KERNEL_ZTMA:
         if (!ok_tma) return fail(LFB_ERR_ARG, "the TMA z-marching kernel needs %s (and cuTensorMapEncodeTiled from the driver)", need);
         h->use_zmarch = 3;
         break;
     default:
-        h->use_zmarch = ok_tma ? 3 : (ok_cp ? 1 : 0);
+        return fail(LFB_ERR_ARG, "kernel id %d: the cp.async z-march kernels (ids 2, 3) were retired; use AUTO, GENERIC or ZTMA", h->desc.kernel);
     }
     return LFB_OK;
 }
@@ -752,13 +745,11 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
     CU(cudaEventRecord(e0, h->compute));
     const int Ny = h->L.N[1];
     // rows per edge strip: one z-march tile row / the halo width
-    const int strip = h->use_zmarch == 3 ? lfb_ztma_tile_rows() : (h->use_zmarch == 2 ? 4 : (h->use_zmarch ? 6 : h->L.H[1]));
+    const int strip = h->use_zmarch == 3 ? lfb_ztma_tile_rows() : h->L.H[1];
     const bool overlap = update && h->nranks > 1 && Ny >= 4 * strip;
     auto launch = [&](int j0, int j1) -> int {
         P.j0 = j0; P.j1 = j1;
         if (h->use_zmarch == 3 && update) CU(lfb_launch_stage_ztma(&P, h->compute));
-        else if (h->use_zmarch == 2 && update) CU(lfb_launch_stage_zsplit(&P, h->compute));
-        else if (h->use_zmarch && update) CU(lfb_launch_stage_zmarch(&P, h->compute));
         else                         CU(lfb_launch_stage_generic(&P, h->desc.strict, h->compute));
         h->launches++;
         return LFB_OK;
@@ -1065,8 +1056,6 @@ extern "C" const char *lfb_kernel_name(const lfb_handle *h)
 {
     if (!h) return "";
     if (h->use_zmarch == 3) return "ztma";
-    if (h->use_zmarch == 2) return "zsplit";
-    if (h->use_zmarch) return "zmarch";
     return h->desc.strict ? "generic-strict" : "generic";
 }
 

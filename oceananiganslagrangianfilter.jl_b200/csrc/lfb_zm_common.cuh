@@ -1,4 +1,4 @@
-// lfb_zm_common.cuh -- device helpers shared by the z-marching stage kernels (lfb_zmarch.cu, lfb_zsplit.cu):
+// lfb_zm_common.cuh -- device helpers of the z-marching stage kernel (lfb_ztma.cu):
 // 32-bit shared-window loads/stores, cp.async, the block barrier, the branch-free division and the
 // difference-form WENO5-Z / WENO3-Z face values.
 #pragma once

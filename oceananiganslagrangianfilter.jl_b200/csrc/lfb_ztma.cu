@@ -1,7 +1,7 @@
 // lfb_ztma.cu -- TMA-staged z-marching RK3 stage kernel (production path on 3-D grids: Periodic, Bounded or
 // slab-decomposed in x and y, Bounded or Periodic in z).
 //
-// Same fused work as lfb_stage_generic / lfb_stage_zmarch (WENO5-Z flux divergence, c div(U), forcing, RK3
+// Same fused work as lfb_stage_generic (WENO5-Z flux divergence, c div(U), forcing, RK3
 // substep, tendency caching, periodic halo images; reference call sites: compute_Gc! / tracer_tendency,
 // lagrangian_filter_tendency_kernel_functions.jl:36-61, lagrangian_filter_rk3_substep.jl:31-61,
 // cache_lagrangian_filter_tendencies.jl:8-31, update_lagrangian_filter_state.jl:33-34).

@@ -17,8 +17,7 @@ from ._lib import check
 from .filter_utils import FilterParams, create_filtered_vars, tracer_layout
 from .grids import RectilinearGrid
 
-_KERNELS = {"auto": _lib.KERNEL_AUTO, "generic": _lib.KERNEL_GENERIC, "zmarch": _lib.KERNEL_ZMARCH,
-            "zsplit": _lib.KERNEL_ZSPLIT, "ztma": _lib.KERNEL_ZTMA}
+_KERNELS = {"auto": _lib.KERNEL_AUTO, "generic": _lib.KERNEL_GENERIC, "ztma": _lib.KERNEL_ZTMA}
 
 
 class LagrangianFilter:

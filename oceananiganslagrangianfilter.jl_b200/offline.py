@@ -198,7 +198,7 @@ def evaluate_mask(config) -> np.ndarray:
 
 
 def run_offline_Lagrangian_filter(config: OfflineFilterConfig, output_dtype=np.float32, save: bool = True,
-                                  model: Optional[LagrangianFilter] = None) -> FilterOutput:
+                                  model: Optional[LagrangianFilter] = None, regrid: bool = True) -> FilterOutput:
     """Runs the offline Lagrangian filter configured by `config` on the GPU and returns the combined
     output (also written to `config.output_filename` unless save=False).
 
@@ -229,7 +229,7 @@ def run_offline_Lagrangian_filter(config: OfflineFilterConfig, output_dtype=np.f
         out = sum_forward_backward_contributions(config, fwd, bwd, iterations, model=model)
         if config.output_original_data:
             out.add_original_data(config, source, indices, file_times)
-        if config.map_to_mean:
+        if config.map_to_mean and regrid:
             regrid_to_mean_position(config, out)
         if config.compute_Eulerian_filter:
             compute_Eulerian_filter(config, out)

@@ -26,6 +26,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define LFO_MAXP 8      /* max coefficient sets (N/2)            */
 #define LFO_MAXV 8      /* max variables to filter               */
@@ -189,6 +192,18 @@ void lfo_destroy(lfo_state *S)
     for (int v = 0; v < S->P.n_vars; ++v) free(S->var[v].p);
     free(S->mask.p);
     free(S);
+}
+
+/* OpenMP thread control for the timed CPU baseline (bench.py): launchers such as torchrun export
+ * OMP_NUM_THREADS=1, which must not silently shrink the baseline. */
+int lfo_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n; return 1;
+#endif
 }
 
 int  lfo_n_tracers(const lfo_state *S) { return S->n_T; }

@@ -74,8 +74,14 @@ def lib():
         L.lfo_get_tendency.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.lfo_output.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.lfo_bw2_params.argtypes = [C.c_int, C.c_double] + [C.POINTER(C.c_double)] * 4
+        L.lfo_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
+
+
+def set_threads(n: int = 0) -> int:
+    """Set the OpenMP thread count of the oracle (n <= 0: leave it); returns the count in effect."""
+    return int(lib().lfo_set_threads(int(n)))
 
 
 def bw2_params(N: int, freq_c: float) -> Dict[str, float]:

@@ -106,3 +106,32 @@ def test_eulerian_filter_matches_golden(golden_offline):
                                 [fp["a1"]], [fp["b1"]], [fp["c1"]], [fp["d1"]])
         ref = golden_offline[nm + "_Eulerian_filtered"]
         assert np.linalg.norm(np.stack(ef) - ref) <= 1e-13 * np.linalg.norm(ref)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The golden case extruded into 3-D (tests/golden_extrude.py): pins the oracle's y-direction / 3-D code, which no
+# reference test exercises, to the reference's own vectors.
+@pytest.mark.parametrize("mode", ["y-replicated", "x-to-y"])
+@pytest.mark.parametrize("halo", [3, 4])
+def test_extruded_golden_case_matches_golden(golden_sim, golden_offline, mode, halo):
+    import golden_extrude as ge
+    grid, times, fields, vel_names, rename = ge.extrude(golden_sim, mode, n_rep=6, halo=halo)
+    N = grid["size"]
+    delta = (1000.0, 1000.0, 10.0)
+    fp = lo.bw2_params(GOLDEN_RUN["N_filter"], GOLDEN_RUN["freq_c"])
+    vel = {k: [a.astype(np.float64) for a in fields[k]] for k in vel_names}
+    vars_ = [[a.astype(np.float64) for a in fields["b"]]]
+    res = lo.run_offline(times, vel, vars_, ["b"], N=N, H=(halo,) * 3, topology=grid["topology"], delta=delta,
+                         filter_params=fp, dt=GOLDEN_RUN["dt"], T_out=GOLDEN_RUN["T_out"], velocities="".join(vel_names))
+    checked = 0
+    for name, series in res.items():
+        if name == "t":
+            continue
+        gname = rename.get(name, name)
+        for n in (0, 7, 12, 24):
+            ref = ge.golden_rehaloed(golden_offline[gname][n], gname, halo)
+            for col in ge.columns_of(series[n], mode, halo):
+                assert col.shape == ref.shape
+                assert np.linalg.norm(col - ref) <= 1e-12 * np.linalg.norm(ref), (name, n)
+                checked += 1
+    assert checked == 5 * 4 * 6
