@@ -84,6 +84,11 @@ struct lfb_handle {
     double    *mask;
     double    *zero_field;                 // velocity components that are not in velocity_names (TMA z-march path)
     double    *cur_in[N_FIELD_IDS];           // inputs at the current stage time (update_input_data!)
+    // TMA z-march path: two sets of stage-time velocity fields; while a stage reads one, its helper warps fill the
+    // other with the velocities of the next stage time (set 0 = cur_in[0..2], set 1 = vin_alt)
+    double    *vin_alt[3];
+    struct VinTag { int valid; double tau; int dir, s1, s2; uint64_t g1, g2; double t1, t2; } vin_tag[2];
+    std::vector<uint64_t> slot_gen;        // bumped by every upload into the slot
     void      *staging;                    // dense parent array, device side
     size_t     staging_bytes;
     std::vector<double *> slot_field;      // [slot * N_FIELD_IDS + field_id]
@@ -101,7 +106,8 @@ struct lfb_handle {
     std::vector<cudaEvent_t> ev_export, ev_fetched;
     std::vector<int> ring_used;
     int        export_next;
-    cudaEvent_t  ev_tmp, ev_t0, ev_t1;
+    cudaEvent_t  ev_tmp, ev_t0, ev_t1, ev_pre;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_free;   // recycled stage-timing event pairs
     // statistics
     int64_t    launches;
     double     stage_ms;
@@ -191,6 +197,79 @@ static int select_kernel(lfb_handle *h)
     return LFB_OK;
 }
 
+static int create_impl(lfb_handle *h)
+{
+    const lfb_desc *desc = &h->desc;
+    build_layout(h);
+    h->single_exp = desc->n_coeffs == 0;
+    h->n_pairs = h->single_exp ? 1 : desc->n_coeffs;
+    h->sub = h->single_exp ? 1 : 2;
+    h->n_maps = 0;
+    if (desc->with_maps)
+        for (int ax = 0; ax < 3; ++ax) if ((desc->velocity_mask >> ax) & 1) h->map_axis[h->n_maps++] = ax;
+    h->n_fields = desc->n_vars + h->n_maps;
+    h->n_items = h->n_fields * h->n_pairs;
+    if (h->n_items > LFB_MAX_ITEMS) return fail(LFB_ERR_ARG, "too many tracers (%d items > %d)", h->n_items, LFB_MAX_ITEMS);
+    h->n_tracers = h->n_items * h->sub;
+    for (int f = 0; f < h->n_fields; ++f)
+        for (int p = 0; p < h->n_pairs; ++p) {
+            LfbItem &it = h->items[f * h->n_pairs + p];
+            it.is_map = f >= desc->n_vars;
+            it.src = it.is_map ? h->map_axis[f - desc->n_vars] : f;
+            it.tracer_c = (f * h->n_pairs + p) * h->sub;
+            it.pad = 0;
+            it.c = desc->c[p];
+            it.d = h->single_exp ? 0.0 : desc->d[p];
+        }
+    const LfbLayout &L = h->L;
+    const size_t fbytes = (size_t)L.len * sizeof(double);
+    const int nt = h->n_tracers > 0 ? h->n_tracers : 1;
+    CU(cudaMalloc(&h->U[0], fbytes * nt));
+    CU(cudaMalloc(&h->U[1], fbytes * nt));
+    CU(cudaMalloc(&h->G, fbytes * nt));
+    CU(cudaMalloc(&h->scratch, fbytes));
+    CU(cudaMemset(h->U[0], 0, fbytes * nt));
+    CU(cudaMemset(h->U[1], 0, fbytes * nt));
+    CU(cudaMemset(h->G, 0, fbytes * nt));
+    CU(cudaMemset(h->scratch, 0, fbytes));
+    if (desc->relaxation) { CU(cudaMalloc(&h->mask, fbytes)); CU(cudaMemset(h->mask, 0, fbytes)); }
+    for (int f = 0; f < N_FIELD_IDS; ++f)
+        if (field_present(h, f)) { CU(cudaMalloc(&h->cur_in[f], fbytes)); CU(cudaMemset(h->cur_in[f], 0, fbytes)); }
+    h->staging_bytes = fbytes;     // dense parent arrays are never larger than the padded layout
+    CU(cudaMalloc(&h->staging, h->staging_bytes));
+    const int ns = desc->n_slots;
+    h->slot_field.assign((size_t)ns * N_FIELD_IDS, nullptr);
+    h->slot_time.assign(ns, 0.0);
+    h->slot_valid.assign(ns, 0u);
+    h->slot_pending.assign(ns, 0);
+    h->slot_gen.assign(ns, 0);
+    h->slot_ready.assign(ns, nullptr);
+    h->slot_used.assign(ns, nullptr);
+    for (int s = 0; s < ns; ++s) {
+        CU(cudaEventCreateWithFlags(&h->slot_ready[s], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->slot_used[s], cudaEventDisableTiming));
+        for (int f = 0; f < N_FIELD_IDS; ++f)
+            if (field_present(h, f)) {
+                CU(cudaMalloc(&h->slot_field[(size_t)s * N_FIELD_IDS + f], fbytes));
+                CU(cudaMemset(h->slot_field[(size_t)s * N_FIELD_IDS + f], 0, fbytes));
+            }
+    }
+    CU(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&h->d2h, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_tmp, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming));
+    CU(cudaEventCreate(&h->ev_t0));
+    CU(cudaEventCreate(&h->ev_t1));
+    CU(cudaDeviceSynchronize());
+    int rc = select_kernel(h);
+    if (rc) return rc;
+    if (h->use_zmarch == 3)
+        for (int f = 0; f < 3; ++f)
+            if (field_present(h, f)) { CU(cudaMalloc(&h->vin_alt[f], fbytes)); CU(cudaMemset(h->vin_alt[f], 0, fbytes)); }
+    return LFB_OK;
+}
+
 extern "C" int lfb_create(const lfb_desc *desc, lfb_handle **out)
 {
     if (!desc || !out) return fail(LFB_ERR_ARG, "null argument");
@@ -228,80 +307,24 @@ extern "C" int lfb_create(const lfb_desc *desc, lfb_handle **out)
     CU(cudaSetDevice(desc->device));
 
     lfb_handle *h = new lfb_handle();
+    // every member that lfb_destroy looks at is null / empty from here on, so a failure anywhere below can be
+    // routed through lfb_destroy without touching garbage or leaking what was already allocated
     h->desc = *desc;
     h->device = desc->device;
-    build_layout(h);
-    h->single_exp = desc->n_coeffs == 0;
-    h->n_pairs = h->single_exp ? 1 : desc->n_coeffs;
-    h->sub = h->single_exp ? 1 : 2;
-    h->n_maps = 0;
-    if (desc->with_maps)
-        for (int ax = 0; ax < 3; ++ax) if ((desc->velocity_mask >> ax) & 1) h->map_axis[h->n_maps++] = ax;
-    h->n_fields = desc->n_vars + h->n_maps;
-    h->n_items = h->n_fields * h->n_pairs;
-    if (h->n_items > LFB_MAX_ITEMS) { delete h; return fail(LFB_ERR_ARG, "too many tracers (%d items > %d)", h->n_items, LFB_MAX_ITEMS); }
-    h->n_tracers = h->n_items * h->sub;
-    for (int f = 0; f < h->n_fields; ++f)
-        for (int p = 0; p < h->n_pairs; ++p) {
-            LfbItem &it = h->items[f * h->n_pairs + p];
-            it.is_map = f >= desc->n_vars;
-            it.src = it.is_map ? h->map_axis[f - desc->n_vars] : f;
-            it.tracer_c = (f * h->n_pairs + p) * h->sub;
-            it.pad = 0;
-            it.c = desc->c[p];
-            it.d = h->single_exp ? 0.0 : desc->d[p];
-        }
-    const LfbLayout &L = h->L;
-    const size_t fbytes = (size_t)L.len * sizeof(double);
-    h->U[0] = h->U[1] = h->G = h->scratch = h->mask = nullptr;
-    h->zero_field = nullptr;
-    h->staging = nullptr;
-    h->comm = nullptr; h->rank = 0; h->nranks = 1; h->comm_stream = nullptr; h->halos_valid = 0;
-    h->send_lo = h->send_hi = h->recv_lo = h->recv_hi = nullptr;
-    const int nt = h->n_tracers > 0 ? h->n_tracers : 1;
-    CU(cudaMalloc(&h->U[0], fbytes * nt));
-    CU(cudaMalloc(&h->U[1], fbytes * nt));
-    CU(cudaMalloc(&h->G, fbytes * nt));
-    CU(cudaMalloc(&h->scratch, fbytes));
-    CU(cudaMemset(h->U[0], 0, fbytes * nt));
-    CU(cudaMemset(h->U[1], 0, fbytes * nt));
-    CU(cudaMemset(h->G, 0, fbytes * nt));
-    CU(cudaMemset(h->scratch, 0, fbytes));
-    if (desc->relaxation) { CU(cudaMalloc(&h->mask, fbytes)); CU(cudaMemset(h->mask, 0, fbytes)); }
-    for (int f = 0; f < N_FIELD_IDS; ++f) {
-        h->cur_in[f] = nullptr;
-        if (field_present(h, f)) { CU(cudaMalloc(&h->cur_in[f], fbytes)); CU(cudaMemset(h->cur_in[f], 0, fbytes)); }
-    }
-    h->staging_bytes = fbytes;     // dense parent arrays are never larger than the padded layout
-    CU(cudaMalloc(&h->staging, h->staging_bytes));
-    const int ns = desc->n_slots;
-    h->slot_field.assign((size_t)ns * N_FIELD_IDS, nullptr);
-    h->slot_time.assign(ns, 0.0);
-    h->slot_valid.assign(ns, 0u);
-    h->slot_pending.assign(ns, 0);
-    h->slot_ready.resize(ns);
-    h->slot_used.resize(ns);
-    for (int s = 0; s < ns; ++s) {
-        CU(cudaEventCreateWithFlags(&h->slot_ready[s], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&h->slot_used[s], cudaEventDisableTiming));
-        for (int f = 0; f < N_FIELD_IDS; ++f)
-            if (field_present(h, f)) {
-                CU(cudaMalloc(&h->slot_field[(size_t)s * N_FIELD_IDS + f], fbytes));
-                CU(cudaMemset(h->slot_field[(size_t)s * N_FIELD_IDS + f], 0, fbytes));
-            }
-    }
-    CU(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h->d2h, cudaStreamNonBlocking));
+    h->U[0] = h->U[1] = h->G = h->scratch = h->mask = h->zero_field = nullptr;
+    h->staging = nullptr; h->staging_bytes = 0;
+    for (int f = 0; f < N_FIELD_IDS; ++f) h->cur_in[f] = nullptr;
+    for (int f = 0; f < 3; ++f) h->vin_alt[f] = nullptr;
+    memset(h->vin_tag, 0, sizeof(h->vin_tag));
+    h->compute = h->copy = h->d2h = h->comm_stream = nullptr;
+    h->ev_tmp = h->ev_t0 = h->ev_t1 = h->ev_pre = h->ev_strips = h->ev_halo = nullptr;
+    h->comm = nullptr; h->rank = 0; h->nranks = 1; h->halos_valid = 0;
+    h->send_lo = h->send_hi = h->recv_lo = h->recv_hi = nullptr; h->halo_elems = 0;
     h->export_next = 0;
-    CU(cudaEventCreateWithFlags(&h->ev_tmp, cudaEventDisableTiming));
-    CU(cudaEventCreate(&h->ev_t0));
-    CU(cudaEventCreate(&h->ev_t1));
     h->cur = 0; h->time = 0; h->iteration = 0; h->direction = 1;
     h->launches = 0; h->stage_ms = 0; h->stage_launches = 0;
     h->use_zmarch = 0;
-    CU(cudaDeviceSynchronize());
-    int rc = select_kernel(h);
+    int rc = create_impl(h);
     if (rc) { lfb_destroy(h); return rc; }
     *out = h;
     return LFB_OK;
@@ -312,23 +335,24 @@ extern "C" int lfb_destroy(lfb_handle *h)
     if (!h) return LFB_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    // tolerates partially built handles (lfb_create routes its failures through here)
     if (h->comm) ncclCommDestroy(h->comm);
-    if (h->comm_stream) { cudaStreamDestroy(h->comm_stream); cudaEventDestroy(h->ev_strips); cudaEventDestroy(h->ev_halo); }
+    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+    for (cudaEvent_t e : {h->ev_strips, h->ev_halo, h->ev_tmp, h->ev_t0, h->ev_t1, h->ev_pre}) if (e) cudaEventDestroy(e);
     for (double *p : h->slot_field) if (p) cudaFree(p);
-    for (cudaEvent_t e : h->slot_ready) cudaEventDestroy(e);
-    for (cudaEvent_t e : h->slot_used) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->slot_ready) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->slot_used) if (e) cudaEventDestroy(e);
     for (auto &pr : h->timing) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-    cudaFree(h->U[0]); cudaFree(h->U[1]); cudaFree(h->G); cudaFree(h->scratch);
-    if (h->mask) cudaFree(h->mask);
-    if (h->zero_field) cudaFree(h->zero_field);
+    for (auto &pr : h->timing_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (double *p : {h->U[0], h->U[1], h->G, h->scratch, h->mask, h->zero_field, h->send_lo, h->send_hi, h->recv_lo, h->recv_hi})
+        if (p) cudaFree(p);
     for (int f = 0; f < N_FIELD_IDS; ++f) if (h->cur_in[f]) cudaFree(h->cur_in[f]);
-    cudaFree(h->staging);
-    if (h->send_lo) { cudaFree(h->send_lo); cudaFree(h->send_hi); cudaFree(h->recv_lo); cudaFree(h->recv_hi); }
-    for (void *p : h->export_ring) cudaFree(p);
-    for (cudaEvent_t e : h->ev_export) cudaEventDestroy(e);
-    for (cudaEvent_t e : h->ev_fetched) cudaEventDestroy(e);
-    cudaStreamDestroy(h->compute); cudaStreamDestroy(h->copy); cudaStreamDestroy(h->d2h);
-    cudaEventDestroy(h->ev_tmp); cudaEventDestroy(h->ev_t0); cudaEventDestroy(h->ev_t1);
+    for (int f = 0; f < 3; ++f) if (h->vin_alt[f]) cudaFree(h->vin_alt[f]);
+    if (h->staging) cudaFree(h->staging);
+    for (void *p : h->export_ring) if (p) cudaFree(p);
+    for (cudaEvent_t e : h->ev_export) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_fetched) if (e) cudaEventDestroy(e);
+    for (cudaStream_t st : {h->compute, h->copy, h->d2h}) if (st) cudaStreamDestroy(st);
     delete h;
     return LFB_OK;
 }
@@ -405,6 +429,7 @@ static int upload_impl(lfb_handle *h, int slot, int field_id, const void *parent
     if (h->slot_valid[slot] && h->slot_time[slot] != time) h->slot_valid[slot] = 0;
     h->slot_time[slot] = time;
     h->slot_valid[slot] |= 1u << field_id;
+    h->slot_gen[slot]++;
     // the host buffer is only borrowed: wait for the H2D copy (not for the import kernel)
     if (wait) CU(cudaEventSynchronize(h->ev_tmp));
     return LFB_OK;
@@ -454,7 +479,7 @@ static uint32_t required_mask(const lfb_handle *h)
 }
 
 // slots bracketing pass time tau: s1 = latest slot with time <= tau, s2 = earliest slot with time > tau
-static int bracket(const lfb_handle *h, double tau, int *s1, int *s2, double *w1, double *w2, int *interp)
+static int bracket(const lfb_handle *h, double tau, int *s1, int *s2, double *w1, double *w2, int *interp, bool quiet = false)
 {
     const uint32_t need = required_mask(h);
     int a = -1, b = -1;
@@ -464,10 +489,10 @@ static int bracket(const lfb_handle *h, double tau, int *s1, int *s2, double *w1
         if (t <= tau) { if (a < 0 || t > h->slot_time[a]) a = s; }
         else          { if (b < 0 || t < h->slot_time[b]) b = s; }
     }
-    if (a < 0) return fail(LFB_ERR_NO_DATA, "no resident snapshot at or before pass time %.17g", tau);
+    if (a < 0) return quiet ? LFB_ERR_NO_DATA : fail(LFB_ERR_NO_DATA, "no resident snapshot at or before pass time %.17g", tau);
     *s1 = a;
     if (h->slot_time[a] == tau) { *s2 = a; *w1 = 1; *w2 = 0; *interp = 0; return LFB_OK; }
-    if (b < 0) return fail(LFB_ERR_NO_DATA, "no resident snapshot after pass time %.17g", tau);
+    if (b < 0) return quiet ? LFB_ERR_NO_DATA : fail(LFB_ERR_NO_DATA, "no resident snapshot after pass time %.17g", tau);
     const double t1 = h->slot_time[a], t2 = h->slot_time[b];
     const double n = (tau - t1) / (t2 - t1);
     *s2 = b; *w2 = n; *w1 = 1 - n; *interp = 1;
@@ -675,7 +700,24 @@ extern "C" int lfb_set_tracer(lfb_handle *h, int tracer, const double *parent)
 }
 
 // ---- time stepping -------------------------------------------------------------------------------
-static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, double zeta, int first, int store_G, int update)
+static lfb_handle::VinTag make_tag(const lfb_handle *h, double tau, int s1, int s2)
+{
+    lfb_handle::VinTag t;
+    t.valid = 1; t.tau = tau; t.dir = h->direction; t.s1 = s1; t.s2 = s2;
+    t.g1 = h->slot_gen[s1]; t.g2 = h->slot_gen[s2]; t.t1 = h->slot_time[s1]; t.t2 = h->slot_time[s2];
+    return t;
+}
+
+static bool same_tag(const lfb_handle::VinTag &a, const lfb_handle::VinTag &b)
+{
+    return a.valid && b.valid && a.tau == b.tau && a.dir == b.dir && a.s1 == b.s1 && a.s2 == b.s2 && a.g1 == b.g1 &&
+           a.g2 == b.g2 && a.t1 == b.t1 && a.t2 == b.t2;
+}
+
+// One fused RK3 stage at pass time tau.  tau_next (NaN: unknown) is the time of the stage that follows: the TMA
+// z-march kernel interpolates that stage's velocities on the side.
+static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, double zeta, int first, int store_G, int update,
+                        double tau_next = NAN)
 {
     LfbStageParams P;
     memset(&P, 0, sizeof(P));
@@ -691,37 +733,57 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
     int s1, s2, interp; double w1, w2;
     int rc = bracket(h, tau, &s1, &s2, &w1, &w2, &interp);
     if (rc) return rc;
-    for (int s : {s1, s2})
+    const bool ztma = h->use_zmarch == 3 && update;
+    const bool backward = h->direction < 0;
+    // the next stage's bracketing snapshots, if they are resident already (the side job reads them)
+    int n1 = -1, n2 = -1, ninterp = 0; double nw1 = 1, nw2 = 0;
+    static const bool no_prefetch = getenv("LFB_NO_PREFETCH") != nullptr;      // A/B measurements only
+    bool prefetch = ztma && !no_prefetch && h->L.N[0] % 2 == 0 /* 128-bit accesses up to column Nx */ && tau_next == tau_next && bracket(h, tau_next, &n1, &n2, &nw1, &nw2, &ninterp, true) == LFB_OK &&
+                    (ninterp || backward);
+    for (int s : {s1, s2, prefetch ? n1 : s1, prefetch ? n2 : s1})
         if (h->slot_pending[s]) { CU(cudaStreamWaitEvent(h->compute, h->slot_ready[s], 0)); h->slot_pending[s] = 0; }
     // update_input_data!: inputs at the stage time (aliased to the slot when no arithmetic is needed)
+    int vset = -1;                     // velocity set read by this stage (TMA path), -1: aliased to a slot
     {
         LfbInterpParams I;
         memset(&I, 0, sizeof(I));
         I.len = h->L.len; I.interp = interp; I.w1 = w1; I.w2 = w2;
-        const bool backward = h->direction < 0;
+        const lfb_handle::VinTag want = make_tag(h, tau, s1, s2);
+        const bool need_vel = interp || backward;
+        if (ztma && need_vel) {
+            for (int b = 0; b < 2; ++b) if (same_tag(h->vin_tag[b], want)) vset = b;
+            if (vset < 0) {            // not prefetched (first stage after a start, re-tagged slots, ...): interpolate now
+                vset = h->vin_tag[0].valid && !h->vin_tag[1].valid ? 1 : 0;
+                h->vin_tag[vset] = want;
+            } else I.interp = -1;      // marks "velocities already there"
+        } else if (!ztma && need_vel) h->vin_tag[0].valid = 0;     // the generic path overwrites set 0
         for (int f = 0; f < N_FIELD_IDS; ++f) {
             if (!field_present(h, f)) continue;
             const double *a = h->slot_field[(size_t)s1 * N_FIELD_IDS + f];
             const double *b = h->slot_field[(size_t)s2 * N_FIELD_IDS + f];
             const bool neg = backward && f < 3;
             const double *use = a;
-            if (f >= 3 && h->use_zmarch == 3 && update) {
+            if (f >= 3 && ztma) {
                 // the TMA z-march kernel reads both snapshots of a variable and interpolates in its forcing term
                 P.var_fused = 1; P.var_w1 = w1; P.var_w2 = w2;
                 P.var[f - 3] = a; P.var2[f - 3] = interp ? b : a;
                 continue;
             }
             if (interp || neg) {
-                const int q = I.n_fields++;
-                I.s1[q] = a; I.s2[q] = b; I.dst[q] = h->cur_in[f]; I.negate[q] = neg;
-                use = h->cur_in[f];
+                double *dst = (f < 3 && vset == 1) ? h->vin_alt[f] : h->cur_in[f];
+                if (!(f < 3 && I.interp < 0)) {
+                    const int q = I.n_fields++;
+                    I.s1[q] = a; I.s2[q] = b; I.dst[q] = dst; I.negate[q] = neg;
+                }
+                use = dst;
             }
             if (f < 3) P.vel[f] = use; else P.var[f - 3] = use;
         }
+        if (I.interp < 0) I.interp = interp;
         if (I.n_fields) { CU(lfb_launch_interp_inputs(&I, h->compute)); h->launches++; }
     }
     for (int ax = 0; ax < 3; ++ax) P.vel_present[ax] = (h->desc.velocity_mask >> ax) & 1;
-    if (h->use_zmarch == 3 && update)
+    if (ztma)
         for (int ax = 0; ax < 3; ++ax)
             if (!P.vel_present[ax]) {                  // a component that is not advected with: zero face velocity
                 if (!h->zero_field) {
@@ -730,6 +792,23 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
                 }
                 P.vel[ax] = h->zero_field;
             }
+    int pset = -1;
+    if (prefetch) {
+        // the set this stage does not read receives the next stage's velocities
+        pset = vset == 0 ? 1 : 0;
+        const lfb_handle::VinTag next = make_tag(h, tau_next, n1, n2);
+        if (same_tag(h->vin_tag[pset], next)) pset = -1;           // already there
+        else {
+            P.pf.on = 1; P.pf.negate = backward; P.pf.w1 = ninterp ? nw1 : 1.0; P.pf.w2 = ninterp ? nw2 : 0.0;
+            for (int f = 0; f < 3; ++f) {
+                if (!field_present(h, f)) continue;
+                P.pf.s1[f] = h->slot_field[(size_t)n1 * N_FIELD_IDS + f];
+                P.pf.s2[f] = h->slot_field[(size_t)(ninterp ? n2 : n1) * N_FIELD_IDS + f];
+                P.pf.dst[f] = pset == 1 ? h->vin_alt[f] : h->cur_in[f];
+            }
+            h->vin_tag[pset].valid = 0;
+        }
+    }
     P.mask = h->mask;
     const double dx = h->desc.spacing[0], dy = h->desc.spacing[1], dz = h->desc.spacing[2];
     P.area[0] = dy * dz; P.area[1] = dx * dz; P.area[2] = dx * dy; P.volume = dx * dy * dz;
@@ -739,46 +818,49 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
     P.j0 = 0; P.j1 = h->L.N[1];
     P.scratch = h->scratch;
 
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
-    CU(cudaEventRecord(e0, h->compute));
+    std::pair<cudaEvent_t, cudaEvent_t> ev;
+    if (!h->timing_free.empty()) { ev = h->timing_free.back(); h->timing_free.pop_back(); }
+    else { CU(cudaEventCreate(&ev.first)); CU(cudaEventCreate(&ev.second)); }
+    CU(cudaEventRecord(ev.first, h->compute));
     const int Ny = h->L.N[1];
     // rows per edge strip: one z-march tile row / the halo width
     const int strip = h->use_zmarch == 3 ? lfb_ztma_tile_rows() : h->L.H[1];
     const bool overlap = update && h->nranks > 1 && Ny >= 4 * strip;
-    auto launch = [&](int j0, int j1) -> int {
-        P.j0 = j0; P.j1 = j1;
-        if (h->use_zmarch == 3 && update) CU(lfb_launch_stage_ztma(&P, h->compute));
-        else                         CU(lfb_launch_stage_generic(&P, h->desc.strict, h->compute));
+    auto launch = [&](int j0, int j1, int jb0, int jb1, cudaStream_t st) -> int {
+        P.j0 = j0; P.j1 = j1; P.jb0 = jb0; P.jb1 = jb1;
+        if (ztma) CU(lfb_launch_stage_ztma(&P, st));
+        else {
+            CU(lfb_launch_stage_generic(&P, h->desc.strict, st));
+            if (jb1 > jb0) { P.j0 = jb0; P.j1 = jb1; CU(lfb_launch_stage_generic(&P, h->desc.strict, st)); h->launches++; }
+        }
         h->launches++;
         return LFB_OK;
     };
     if (!overlap) {
-        rc = launch(0, Ny);
+        rc = launch(0, Ny, 0, 0, h->compute);
         if (rc) return rc;
         if (update && h->nranks > 1) { rc = exchange_y(h, P.U_new, h->n_tracers); if (rc) return rc; }
     } else {
-        // slab decomposition: edge strips first, then their halo exchange on the communication stream
-        // while the interior is computed (stands in for Oceananigans' async halo fill +
-        // compute_buffer_tendencies!, compute_lagrangian_filter_buffer_tendencies.jl:8-38)
-        rc = launch(0, strip);
+        // Slab decomposition (stands in for Oceananigans' async halo fill + compute_buffer_tendencies!,
+        // compute_lagrangian_filter_buffer_tendencies.jl:8-38).  The two edge strips are ONE grid on the
+        // high-priority communication stream, followed there by their halo exchange; the interior is a second
+        // grid on the compute stream.  Nothing orders the two grids of a stage, so the strip blocks are placed
+        // first and the interior blocks fill the SMs behind them without a wave boundary in between.
+        CU(cudaEventRecord(h->ev_pre, h->compute));               // the previous stage's interior + this stage's inputs
+        CU(cudaStreamWaitEvent(h->comm_stream, h->ev_pre, 0));
+        rc = launch(0, strip, Ny - strip, Ny, h->comm_stream);
         if (rc) return rc;
-        rc = launch(Ny - strip, Ny);
-        if (rc) return rc;
-        CU(cudaEventRecord(h->ev_strips, h->compute));
-        CU(cudaStreamWaitEvent(h->comm_stream, h->ev_strips, 0));
         rc = exchange_y(h, P.U_new, h->n_tracers, h->comm_stream);
         if (rc) return rc;
         CU(cudaEventRecord(h->ev_halo, h->comm_stream));
-        rc = launch(strip, Ny - strip);
+        rc = launch(strip, Ny - strip, 0, 0, h->compute);
         if (rc) return rc;
-        CU(cudaStreamWaitEvent(h->compute, h->ev_halo, 0));   // the next stage reads the received halo rows
+        CU(cudaStreamWaitEvent(h->compute, h->ev_halo, 0));   // the next stage reads the strips and the received halo rows
     }
-    CU(cudaEventRecord(e1, h->compute));
-    h->timing.push_back({e0, e1});
-    CU(cudaEventRecord(h->slot_used[s1], h->compute));
-    if (s2 != s1) CU(cudaEventRecord(h->slot_used[s2], h->compute));
+    CU(cudaEventRecord(ev.second, h->compute));
+    h->timing.push_back(ev);
+    if (pset >= 0) h->vin_tag[pset] = make_tag(h, tau_next, n1, n2);
+    for (int s : {s1, s2, prefetch ? n1 : s1, prefetch ? n2 : s1}) CU(cudaEventRecord(h->slot_used[s], h->compute));
     return LFB_OK;
 }
 
@@ -792,8 +874,7 @@ static int drain_timings(lfb_handle *h, bool wait)
         CU(cudaEventElapsedTime(&ms, pr.first, pr.second));
         h->stage_ms += ms;
         h->stage_launches++;
-        cudaEventDestroy(pr.first);
-        cudaEventDestroy(pr.second);
+        h->timing_free.push_back(pr);
         ++done;
     }
     h->timing.erase(h->timing.begin(), h->timing.begin() + done);
@@ -812,11 +893,12 @@ extern "C" int lfb_step(lfb_handle *h, double dt)
     const double tau2 = tau1 + (g2 + z2) * dt;
     const double taus[3] = {t0, tau1, tau2};
     const double gam[3] = {g1, g2, g3}, zet[3] = {0.0, z2, z3};
+    const double next_tau[3] = {tau1, tau2, t1};       // the stage that follows (the next step starts at t1)
     if (h->timing.size() > 64) drain_timings(h, false);
     for (int s = 0; s < 3; ++s) {
         int rc = refresh_halos(h, h->U[h->cur], h->n_tracers);
         if (rc) return rc;
-        rc = launch_stage(h, taus[s], dt, gam[s], zet[s], s == 0, s < 2, 1);
+        rc = launch_stage(h, taus[s], dt, gam[s], zet[s], s == 0, s < 2, 1, next_tau[s]);
         if (rc) return rc;
         h->cur ^= 1;          // the stage kernels (and the slab exchange) leave the halos of the new state valid
     }

@@ -81,6 +81,18 @@ struct LfbStageParams {
     int     var_fused;
     const double *var2[LFB_MAX_VARS];
     double  var_w1, var_w2;
+    // second row range [jb0, jb1) of the same launch (the two edge strips of a slab in ONE grid); empty if jb1 <= jb0
+    int     jb0, jb1;
+    // side job of the TMA z-march kernel: while it computes this stage, its helper warps interpolate the velocities of
+    // the NEXT stage time from the two bracketing snapshots (update_input_data!, utils:1036-1058) for the rows /
+    // columns / planes the next stage's tiles will read: dst = +-(s2 * w2 + s1 * w1).  Replaces the separate
+    // lfb_interp_inputs launch for every stage but the first after a (re)start.
+    struct {
+        int           on, negate;
+        const double *s1[3], *s2[3];
+        double       *dst[3];            // null: component absent / aliased to a snapshot
+        double        w1, w2;
+    } pf;
 };
 
 // Output combinations (create_output_fields, utils:898-1012): out = sum_i wc[i] U[tc[i]] + ws[i] U[tc[i]+1]

@@ -137,6 +137,19 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *map, int x, i
     asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(x), "r"(y), "r"(z), "r"(t) : "memory");
 }
 
+// streaming (evict-first) global accesses of the side job: its data is touched once per stage and must not push the
+// velocity tiles the sibling blocks of a tile share out of L2
+__device__ __forceinline__ double2 ldg_stream(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream(double2 *p, double2 v)
+{
+    asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
 // ---- arithmetic ---------------------------------------------------------------------------------------------------
 struct ZtK { double k133, k13, k16, eps43; };
 
@@ -274,7 +287,11 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     const int item_id = blockIdx.x % S.n_items;
     const int ytile = blockIdx.x / S.n_items;
     const int i0 = blockIdx.y * ZT_TX;
-    const int j0 = S.j0 + ytile * TY;
+    // rows of this tile: range [S.j0, S.j1) first, then (the second edge strip of a slab) [S.jb0, S.jb1)
+    const int ytiles_a = (S.j1 - S.j0 + TY - 1) / TY;
+    const bool range_b = ytile >= ytiles_a;
+    const int j0 = range_b ? S.jb0 + (ytile - ytiles_a) * TY : S.j0 + ytile * TY;
+    const int j1 = range_b ? S.jb1 : S.j1;
     const LfbItem item = S.items[item_id];
     const int Nz = L.N[2];
     const bool use_G = !S.first_stage;
@@ -360,6 +377,60 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         // scheme of this lane's face (lower order next to the walls of a Bounded axis)
         const int h_order = kind == 1 ? zt_face_order(L.goff[1] + j0 + ty + 1, L.NG[1], L.topo[1] == LFB_BOUNDED)
                                       : zt_face_order(L.goff[0] + i0 + tx + 1, L.NG[0], L.topo[0] == LFB_BOUNDED);
+        // ---- side job: the velocities of the NEXT stage time (S.pf), for the elements the next stage's tiles read ----
+        // Work units of a tile plane, one 128-bit access per lane (two doubles), two rows per warp instruction:
+        //   units 0 .. 3 TY/2 - 1   rows (2r, 2r + 1) of the tile in u, v, w
+        //   unit 3 TY/2             the v row behind the last row of this launch's row range (north face of that row)
+        //   unit 3 TY/2 + 1         the u column behind the last column of the grid (east face / periodic image)
+        // and one more plane of w (top faces of the last plane).  The units of a tile are dealt round-robin to the helper
+        // warps of the blocks (items) of the tile.  The first unit of a warp is software-pipelined by one barrier interval
+        // (an HBM round trip is about as long as an interval); further units (few items per tile) follow serially.
+        static_assert(TY % 2 == 0, "two rows per side-job unit");
+        constexpr int NHW = NSUB + 1, UPA = TY / 2, NUNIT = 3 * UPA + 2;
+        const int lane = hl & 31, hw = hl >> 5;
+        const bool pf_on = S.pf.on != 0;
+        const int unit_step = S.n_items * NHW, unit0 = item_id + S.n_items * hw;
+        // the two elements of unit u owned by this lane: axis (-1: none) and offset in plane 0
+        auto pf_elem = [&](int u, int &ax, int64_t &off) {
+            int i = i0 + 2 * (lane & 15), j;
+            bool ok;
+            if (u < 3 * UPA)       { ax = u / UPA; j = j0 + 2 * (u % UPA) + (lane >> 4); ok = j < j1 && (ax == 0 ? i <= L.N[0] : i < L.N[0]); }
+            else if (u == 3 * UPA) { ax = 1; j = j1; ok = lane < 16 && j0 + TY >= j1 && i < L.N[0]; }
+            else                   { ax = 0; i = L.N[0]; j = j0 + lane; ok = lane < TY && j < j1 && i0 + ZT_TX == L.N[0]; }
+            if (!ok || u >= NUNIT || !S.pf.dst[ax]) ax = -1;
+            off = L.at(i, j, 0);
+        };
+        auto pf_value = [&](double2 a, double2 b) {
+            double2 r;
+            r.x = __dadd_rn(__dmul_rn(b.x, S.pf.w2), __dmul_rn(a.x, S.pf.w1));
+            r.y = __dadd_rn(__dmul_rn(b.y, S.pf.w2), __dmul_rn(a.y, S.pf.w1));
+            if (S.pf.negate) { r.x = -r.x; r.y = -r.y; }
+            return r;
+        };
+        const double2 *pa = nullptr, *pb = nullptr;       // running pointers of the pipelined unit (plane k0)
+        double2 *pd = nullptr, *pdl = nullptr;            // ... pdl trails pd by one interval
+        if (pf_on) {
+            int ax; int64_t off;
+            pf_elem(unit0, ax, off);
+            if (ax >= 0) {
+                pa = reinterpret_cast<const double2 *>(S.pf.s1[ax] + off); pb = reinterpret_cast<const double2 *>(S.pf.s2[ax] + off);
+                pd = reinterpret_cast<double2 *>(S.pf.dst[ax] + off);
+            }
+        }
+        const int64_t plane2 = L.plane / 2;                // plane stride in double2 (the pitch is a multiple of 16)
+        // units beyond the first of this warp, and the extra w plane: load, combine, store
+        auto pf_rest = [&](int k, int u_from, bool w_only) {
+            for (int u = u_from; u < NUNIT; u += unit_step) {
+                int ax; int64_t off;
+                pf_elem(u, ax, off);
+                if (ax < 0 || (w_only && ax != 2)) continue;
+                off += (int64_t)k * L.plane;
+                stg_stream(reinterpret_cast<double2 *>(S.pf.dst[ax] + off),
+                           pf_value(ldg_stream(reinterpret_cast<const double2 *>(S.pf.s1[ax] + off)),
+                                    ldg_stream(reinterpret_cast<const double2 *>(S.pf.s2[ax] + off))));
+            }
+        };
+        double2 va[ZT_PB], vb[ZT_PB];
         if (face_lane) mbar_wait(barP, 0);
         __syncwarp();
         block_barrier();                 // prologue barrier: see the main warps
@@ -373,6 +444,16 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
 #pragma unroll
                 for (int p = 0; p < ZT_PB; ++p) if (k0 + ZT_PF + p < Nz) prefetch_group(k0 + ZT_PF + p);
 #endif
+            }
+            // side job: store what was loaded during the previous interval, then issue this interval's loads
+            if (pf_on && pa) {
+#pragma unroll
+                for (int p = 0; p < ZT_PB; ++p) {
+                    if (k0 > 0) stg_stream(pdl + p * plane2, pf_value(va[p], vb[p]));
+                    if (k0 + p < Nz) { va[p] = ldg_stream(pa + p * plane2); vb[p] = ldg_stream(pb + p * plane2); }
+                }
+                pdl = pd;
+                pa += ZT_PB * plane2; pb += ZT_PB * plane2; pd += ZT_PB * plane2;
             }
 #pragma unroll
             for (int p = 0; p < ZT_PB; ++p) {
@@ -388,7 +469,17 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
                 }
             }
             __syncwarp();
+            if (pf_on && unit0 + unit_step < NUNIT)
+                for (int p = 0; p < ZT_PB; ++p) if (k0 + p < Nz) pf_rest(k0 + p, unit0 + unit_step, false);
             block_barrier();
+        }
+        if (pf_on) {
+            const int kl = (Nz - 1) / ZT_PB * ZT_PB;     // first plane of the last interval
+            if (pa) {
+#pragma unroll
+                for (int p = 0; p < ZT_PB; ++p) if (kl + p < Nz) stg_stream(pdl + p * plane2, pf_value(va[p], vb[p]));
+            }
+            pf_rest(Nz, unit0, true);                     // top faces of the last plane
         }
         return;
     }
@@ -400,7 +491,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     const unsigned a32 = sbase + 8u * t, a32s = a32 + sub * VT_B;
     const unsigned a40 = sbase + 8u * (ty * ZT_CW + tx + ZT_HX), a40s = a40 + 3 * ROW_B + sub * CTP_B;
     const int partner_off = NSUB == 2 ? (sub ? -(int)CTP_B : (int)CTP_B) : 0;
-    const bool active = j0 + ty < S.j1 && i0 + tx < L.N[0];         // partial tiles at the end of the y range / of x
+    const bool active = j0 + ty < j1 && i0 + tx < L.N[0];         // partial tiles at the end of the y range / of x
     const int64_t plane_b = L.plane * 8;                             // byte stride between planes
     // rows beyond j1 / columns beyond Nx (partial tiles) compute like the others but store into the scratch field
     const int64_t cell0 = L.at(i0 + tx, j0 + ty, 0);
@@ -686,11 +777,14 @@ template <int NSUB, int TY, bool WALLS>
 static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
 {
     using SM = ZtSmem<NSUB, TY>;
-    static bool configured = false;
-    if (!configured) {
+    // the attribute is per device (a process may hold handles on several GPUs)
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(lfb_stage_ztma<NSUB, TY, WALLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     LfbZtParams P;
     memset(&P, 0, sizeof(P));
@@ -716,7 +810,7 @@ static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
     P.k133 = 13.0 / 3.0; P.k13 = 1.0 / 3.0; P.k16 = 1.0 / 6.0; P.eps43 = LFB_WENO_EPS * (4.0 / 3.0);
     for (int a = 0; a < 3; ++a) P.rd[a] = S->area[a] / S->volume;
     P.scratch = S->scratch;
-    const int ytiles = (S->j1 - S->j0 + TY - 1) / TY;
+    const int ytiles = (S->j1 - S->j0 + TY - 1) / TY + (S->jb1 > S->jb0 ? (S->jb1 - S->jb0 + TY - 1) / TY : 0);
     dim3 grid(S->n_items * ytiles, (L.N[0] + ZT_TX - 1) / ZT_TX, 1);
     lfb_stage_ztma<NSUB, TY, WALLS><<<grid, SM::THREADS, SM::BYTES, stream>>>(P);
     return cudaGetLastError();

@@ -51,7 +51,23 @@ typedef struct {
     /* optional boundary relaxation (utils:584-699): mask pre-evaluated at cell centres */
     int    relax;         /* boundary_relaxation                                     */
     double relax_timescale;
+    /* numerics options beyond the reference's defaults */
+    int    timestepper;   /* 0 = RungeKutta3 (default, lagrangian_filter.jl:85), 1 = QuasiAdamsBashforth2 */
+    double chi;           /* AB2 parameter (Oceananigans default 0.1)                */
+    int    immersed;      /* 1: an immersed-cell flag field was set (lfo_set_immersed) */
+    int    weights_f32;   /* experiment only: WENO5-Z nonlinear weights evaluated in Float32 */
 } lfo_problem;
+
+/* advection scheme ids carried by lfo_problem.advect (OfflineFilterConfig.advection,
+ * OfflineLagrangianFilter.jl:139,246): 0 = nothing, 1 = WENO(order=5) (the default) */
+#define ADV_NONE 0
+#define ADV_WENO5 1
+#define ADV_CENTERED2 2
+#define ADV_CENTERED4 3
+#define ADV_UPWIND1 4
+#define ADV_UPWIND3 5
+#define ADV_UPWIND5 6
+#define ADV_WENO3 7
 
 typedef struct {
     double *p;            /* parent array                                            */
@@ -68,6 +84,8 @@ typedef struct {
     lfo_field vel[3];             /* current (time-interpolated) u,v,w               */
     lfo_field var[LFO_MAXV];      /* current original variables (aux fields)         */
     lfo_field mask;               /* relaxation mask at centres (optional)           */
+    lfo_field imm;                /* 1.0 in immersed cells (ImmersedBoundaryGrid), else 0; halos too */
+    double  last_dt;              /* AB2: the previous step's dt (Euler step when it changes) */
     /* input series */
     int     n_snap;
     double *snap_t;               /* times as seen by the pass (after shift/reversal) */
@@ -166,6 +184,8 @@ lfo_state *lfo_create(const lfo_problem *P)
     for (int ax = 0; ax < 3; ++ax) field_alloc(&S->vel[ax], P, ax);
     for (int v = 0; v < P->n_vars; ++v) field_alloc(&S->var[v], P, -1);
     field_alloc(&S->mask, P, -1);
+    field_alloc(&S->imm, P, -1);
+    S->last_dt = INFINITY;        /* Oceananigans Clock: last_dt = Inf */
     return S;
 }
 
@@ -191,6 +211,7 @@ void lfo_destroy(lfo_state *S)
     for (int ax = 0; ax < 3; ++ax) free(S->vel[ax].p);
     for (int v = 0; v < S->P.n_vars; ++v) free(S->var[v].p);
     free(S->mask.p);
+    free(S->imm.p);
     free(S);
 }
 
@@ -210,7 +231,7 @@ int  lfo_n_tracers(const lfo_state *S) { return S->n_T; }
 long lfo_center_len(const lfo_state *S) { return S->U[0].len; }
 long lfo_vel_len(const lfo_state *S, int ax) { return S->vel[ax].len; }
 double lfo_time(const lfo_state *S) { return S->time; }
-void lfo_reset_clock(lfo_state *S) { S->time = 0; S->iteration = 0; }   /* run_offline...jl:93 */
+void lfo_reset_clock(lfo_state *S) { S->time = 0; S->iteration = 0; S->last_dt = INFINITY; }   /* run_offline...jl:93 */
 
 /* a14: create_input_data_on_disk, utils:97-180.  `times` are the ORIGINAL file times of the
  * snapshots in [T_start,T_end] in file order.  forward: t <- t - T_start, order kept.
@@ -257,6 +278,22 @@ void lfo_set_mask(lfo_state *S, const double *mask_parent)
 /* a7: update_input_data!, utils:1036-1058: parent(field) .= parent(fts[Time(t)]) with
  * Oceananigans' linear time interpolation psi2*n + psi1*(1-n), n=(t-t1)/(t2-t1); a time that
  * sits on a snapshot returns that snapshot. */
+/* Immersed cells of an ImmersedBoundaryGrid (GridFittedBottom-style: whole cells), as a parent array of 0 / 1 flags
+ * evaluated by the host from the bottom height (immersed_cell: z_centre <= bottom_height). */
+void lfo_set_immersed(lfo_state *S, const double *imm_parent)
+{
+    memcpy(S->imm.p, imm_parent, sizeof(double) * S->imm.len);
+    S->P.immersed = 1;
+}
+
+/* mask_immersed_field!: tracers are zero inside the immersed boundary (update_lagrangian_filter_state.jl:22-24) */
+static void mask_immersed(lfo_state *S)
+{
+    if (!S->P.immersed) return;
+    for (int t = 0; t < S->n_T; ++t)
+        for (long q = 0; q < S->U[t].len; ++q) if (S->imm.p[q] != 0.0) S->U[t].p[q] = 0.0;
+}
+
 static void time_interp(double *dst, long len, double *const *series, const double *ts, int ns, double t)
 {
     int n1 = 0;
@@ -312,26 +349,82 @@ static inline double weno3z(double o, double n, double e)
     return (a0 * q0 + a1 * q1) / (a0 + a1);
 }
 
-/* Upwind face value at face m (1-based: between cells m-1 and m) along one axis.
- * cm points at cell m, s is the stride along the axis, N the cell count, q the advecting
- * face velocity.  Bounded axes degrade WENO5 -> WENO3 -> Centered2 by face index
- * (printed scheme chain at OfflineLagrangianFilter.jl:212-214). */
-static inline double face_value(const double *cm, long s, int m, int N, int topo, double q)
+/* WENO5-Z with the nonlinear weights evaluated in Float32 (EXPERIMENT, lfo_problem.weights_f32): the
+ * candidates and the final combination stay FP64.  Used only to measure what Float32 weights would cost
+ * in parity; never a product path. */
+static inline double weno5z_w32(double p, double o, double n, double e, double f)
 {
-    int order = 5;
-    if (topo == TOPO_BOUNDED) {
-        if (m >= 4 && m <= N - 2) order = 5;
-        else if (m >= 3 && m <= N - 1) order = 3;
-        else order = 2;      /* m = 2, N, and the walls m = 1, N+1 (halo cell mirrors the interior) */
+    const float eps = 1e-8f;
+    float pf = (float)p, of = (float)o, nf = (float)n, ef = (float)e, ff = (float)f;
+    float b0 = nf * (10 * nf - 31 * ef + 11 * ff) + ef * (25 * ef - 19 * ff) + ff * (4 * ff);
+    float b1 = of * (4 * of - 13 * nf + 5 * ef) + nf * (13 * nf - 13 * ef) + ef * (4 * ef);
+    float b2 = pf * (4 * pf - 19 * of + 11 * nf) + of * (25 * of - 31 * nf) + nf * (10 * nf);
+    float tau = fabsf(b0 - b2);
+    float r0 = tau / (b0 + eps), r1 = tau / (b1 + eps), r2 = tau / (b2 + eps);
+    double a0 = 0.3f * (1 + r0 * r0), a1 = 0.6f * (1 + r1 * r1), a2 = 0.1f * (1 + r2 * r2);
+    double q0 = n / 3 + 5 * e / 6 - f / 6;
+    double q1 = -o / 6 + 5 * n / 6 + e / 3;
+    double q2 = p / 3 - 7 * o / 6 + 11 * n / 6;
+    return (a0 * q0 + a1 * q1 + a2 * q2) / (a0 + a1 + a2);
+}
+
+/* Reconstruction kinds of a scheme chain.  Every Oceananigans scheme carries a `buffer_scheme` that takes over
+ * where its own stencil would reach outside the domain or into the immersed boundary; the chains (highest
+ * order first) follow the constructors' defaults, e.g. the one printed at OfflineLagrangianFilter.jl:212-214:
+ *   WENO(order=5) -> WENO(order=3) -> Centered(order=2)
+ *   UpwindBiased(order=5) -> UpwindBiased(order=3) -> UpwindBiased(order=1)
+ *   Centered(order=4) -> Centered(order=2)
+ * Only the WENO(order=5) chain is pinned by the reference's golden file. */
+enum { K_C2, K_C4, K_U1, K_U3, K_U5, K_W3, K_W5 };
+
+static int scheme_chain(int scheme, int kinds[3], int bufs[3])
+{
+    switch (scheme) {
+    case ADV_WENO5:     kinds[0] = K_W5; bufs[0] = 3; kinds[1] = K_W3; bufs[1] = 2; kinds[2] = K_C2; bufs[2] = 1; return 3;
+    case ADV_WENO3:     kinds[0] = K_W3; bufs[0] = 2; kinds[1] = K_C2; bufs[1] = 1; return 2;
+    case ADV_CENTERED4: kinds[0] = K_C4; bufs[0] = 2; kinds[1] = K_C2; bufs[1] = 1; return 2;
+    case ADV_CENTERED2: kinds[0] = K_C2; bufs[0] = 1; return 1;
+    case ADV_UPWIND5:   kinds[0] = K_U5; bufs[0] = 3; kinds[1] = K_U3; bufs[1] = 2; kinds[2] = K_U1; bufs[2] = 1; return 3;
+    case ADV_UPWIND3:   kinds[0] = K_U3; bufs[0] = 2; kinds[1] = K_U1; bufs[1] = 1; return 2;
+    case ADV_UPWIND1:   kinds[0] = K_U1; bufs[0] = 1; return 1;
     }
-    if (order == 2) return (cm[-s] + cm[0]) / 2;
-    if (q > 0) {
-        if (order == 5) return weno5z(cm[-3 * s], cm[-2 * s], cm[-s], cm[0], cm[s]);
-        return weno3z(cm[-2 * s], cm[-s], cm[0]);
-    } else {
-        if (order == 5) return weno5z(cm[2 * s], cm[s], cm[0], cm[-s], cm[-2 * s]);
-        return weno3z(cm[s], cm[0], cm[-s]);
+    return 0;
+}
+
+/* Face value at face m (1-based: between cells m-1 and m) along one axis.
+ * cm points at cell m, s is the stride along the axis, N the cell count, q the advecting face velocity, imm
+ * (or NULL) points at the immersed flag of cell m.  The first scheme of the chain whose symmetric stencil of
+ * `buffer` cells on each side of the face (cells m-b .. m+b-1) lies inside a Bounded domain and outside the
+ * immersed boundary is used (Oceananigans near_*_boundary / near_*_immersed_boundary; for WENO(order=5) this is
+ * the face-index rule of SURVEY.md App. A.5).  Where not even the two adjacent cells are active the face is a
+ * wall (velocity zero / flux masked) and the centred average is returned. */
+static inline double face_value(const lfo_problem *P, const double *cm, const double *imm, long s, int m, int N, int topo, double q)
+{
+    int kinds[3], bufs[3];
+    const int nk = scheme_chain(P->advect, kinds, bufs);
+    int kind = K_C2;
+    for (int c = 0; c < nk; ++c) {
+        const int b = bufs[c];
+        int ok = 1;
+        if (topo == TOPO_BOUNDED && (m - b < 1 || m + b - 1 > N)) ok = 0;
+        if (ok && imm) for (int r = -b; r < b; ++r) if (imm[r * s] != 0.0) { ok = 0; break; }
+        if (ok) { kind = kinds[c]; break; }
     }
+    const int left = q > 0;
+    /* upwind-ordered stencil (p, o, n | e, f): n is the upwind cell */
+    #define CELL(r) (left ? cm[((r) - 1) * s] : cm[-(r) * s])      /* r = -2..2 relative to n */
+    switch (kind) {
+    case K_W5: return P->weights_f32 ? weno5z_w32(CELL(-2), CELL(-1), CELL(0), CELL(1), CELL(2))
+                                     : weno5z(CELL(-2), CELL(-1), CELL(0), CELL(1), CELL(2));
+    case K_W3: return weno3z(CELL(-1), CELL(0), CELL(1));
+    case K_U1: return CELL(0);
+    case K_U3: return (-1.0 / 6.0) * CELL(-1) + (5.0 / 6.0) * CELL(0) + (1.0 / 3.0) * CELL(1);
+    case K_U5: return (2.0 / 60.0) * CELL(-2) + (-13.0 / 60.0) * CELL(-1) + (47.0 / 60.0) * CELL(0)
+                      + (27.0 / 60.0) * CELL(1) + (-3.0 / 60.0) * CELL(2);
+    case K_C4: return (-1.0 / 12.0) * cm[-2 * s] + (7.0 / 12.0) * cm[-s] + (7.0 / 12.0) * cm[0] + (-1.0 / 12.0) * cm[s];
+    default:   return (cm[-s] + cm[0]) / 2;
+    }
+    #undef CELL
 }
 
 /* a9 + a3 (+ a4): compute_tendencies! -> compute_Gc! -> tracer_tendency
@@ -376,9 +469,13 @@ static void compute_tendencies(lfo_state *S)
                     long iv = fidx(vf, P, i, j, k);
                     double q_lo = vf->p[iv], q_hi = vf->p[iv + sv[ax]];
                     int m = ijk[ax] + 1;  /* 1-based face index of the low face */
-                    double c_lo = face_value(cp, sc[ax], m, P->N[ax], P->topo[ax], q_lo);
-                    double c_hi = face_value(cp + sc[ax], sc[ax], m + 1, P->N[ax], P->topo[ax], q_hi);
+                    const double *ip = P->immersed ? S->imm.p + ic : NULL;
+                    double c_lo = face_value(P, cp, ip, sc[ax], m, P->N[ax], P->topo[ax], q_lo);
+                    double c_hi = face_value(P, cp + sc[ax], ip ? ip + sc[ax] : NULL, sc[ax], m + 1, P->N[ax], P->topo[ax], q_hi);
                     double F_lo = area[ax] * q_lo * c_lo, F_hi = area[ax] * q_hi * c_hi;
+                    /* conditional_flux: no advective flux through a face of the immersed boundary */
+                    if (ip && (ip[-sc[ax]] != 0.0 || ip[0] != 0.0)) F_lo = 0;
+                    if (ip && (ip[0] != 0.0 || ip[sc[ax]] != 0.0)) F_hi = 0;
                     div_flux += (F_hi - F_lo);
                     div_u += (area[ax] * q_hi - area[ax] * q_lo);
                 }
@@ -422,6 +519,7 @@ static void compute_tendencies(lfo_state *S)
 /* a8: update_state!, update_lagrangian_filter_state.jl:19-53 */
 void lfo_update_state(lfo_state *S)
 {
+    mask_immersed(S);
     for (int t = 0; t < S->n_T; ++t) fill_halos(&S->U[t], &S->P);
     update_input_data(S, S->time);
     compute_tendencies(S);
@@ -508,8 +606,33 @@ static void cache_tendencies(lfo_state *S)
 /* One RK3 step of size dt (Oceananigans time_step!(::RungeKutta3) driving the LagrangianFilter
  * method extensions).  Requires lfo_update_state() to have been called once
  * at iteration 0 (as Oceananigans does). */
+/* QuasiAdamsBashforth2 step (lagrangian_filter_ab2_step.jl:24-51 + Oceananigans time_step!/_ab2_step_field!):
+ * U += dt ((3/2 + chi) G - (1/2 + chi) G^-), an Euler step (chi = -1/2) at iteration 0 and whenever dt differs
+ * from the previous step's. */
+static void ab2_time_step(lfo_state *S, double dt)
+{
+    const lfo_problem *P = &S->P;
+    if (S->iteration == 0) lfo_update_state(S);
+    const int euler = dt != S->last_dt;
+    const double chi = euler ? -0.5 : P->chi;
+    for (int t = 0; t < S->n_T; ++t) {
+        lfo_field *U = &S->U[t], *G = &S->G[t], *Gm = &S->Gm[t];
+        for (int k = 0; k < P->N[2]; ++k) for (int j = 0; j < P->N[1]; ++j) for (int i = 0; i < P->N[0]; ++i) {
+            long q = fidx(U, P, i, j, k);
+            double Gu = (1.5 + chi) * G->p[q] - (euler ? 0.0 : (0.5 + chi) * Gm->p[q]);
+            U->p[q] += dt * Gu;
+        }
+    }
+    S->time = S->time + dt;
+    S->last_dt = dt;
+    for (int t = 0; t < S->n_T; ++t) memcpy(S->Gm[t].p, S->G[t].p, sizeof(double) * S->G[t].len);
+    lfo_update_state(S);
+    S->iteration += 1;
+}
+
 void lfo_time_step(lfo_state *S, double dt)
 {
+    if (S->P.timestepper == 1) { ab2_time_step(S, dt); return; }
     const double g1 = 8.0 / 15, g2 = 5.0 / 12, g3 = 3.0 / 4, z2 = -17.0 / 60, z3 = -5.0 / 12;
     double t0 = S->time, t1 = t0 + dt;
     if (S->iteration == 0) lfo_update_state(S);

@@ -40,7 +40,12 @@ class _Problem(C.Structure):
                 ("n_vars", C.c_int), ("vel_present", C.c_int * 3), ("n_pairs", C.c_int), ("single_exp", C.c_int),
                 ("with_maps", C.c_int), ("advect", C.c_int),
                 ("a", C.c_double * MAXP), ("b", C.c_double * MAXP), ("c", C.c_double * MAXP), ("d", C.c_double * MAXP),
-                ("relax", C.c_int), ("relax_timescale", C.c_double)]
+                ("relax", C.c_int), ("relax_timescale", C.c_double),
+                ("timestepper", C.c_int), ("chi", C.c_double), ("immersed", C.c_int), ("weights_f32", C.c_int)]
+
+
+ADVECTION = {None: 0, "WENO5": 1, "Centered2": 2, "Centered4": 3, "UpwindBiased1": 4, "UpwindBiased3": 5,
+             "UpwindBiased5": 6, "WENO3": 7}
 
 
 _lib = None
@@ -65,6 +70,7 @@ def lib():
         L.lfo_load_series.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_int,
                                       PP, PP, PP, C.POINTER(PP)]
         L.lfo_set_mask.argtypes = [C.c_void_p, C.c_void_p]
+        L.lfo_set_immersed.argtypes = [C.c_void_p, C.c_void_p]
         L.lfo_update_state.argtypes = [C.c_void_p]
         L.lfo_init_from_data.argtypes = [C.c_void_p]
         L.lfo_negate_maps.argtypes = [C.c_void_p]
@@ -119,7 +125,10 @@ class Oracle:
     """One LagrangianFilter model + its input series, CPU reference numerics."""
 
     def __init__(self, N, H, topology, delta, n_vars, velocities="uvw", filter_params=None, with_maps=True,
-                 advect=True, relax_timescale=None, mask=None):
+                 advect=True, relax_timescale=None, mask=None, timestepper="RungeKutta3", chi=0.1, immersed=None,
+                 weights_f32=False):
+        """advect: True (the default WENO(order=5)), False / None (advection = nothing) or a scheme name from
+        ADVECTION; timestepper: "RungeKutta3" | "QuasiAdamsBashforth2"; immersed: parent array of 0 / 1 flags."""
         P = _Problem()
         nc = filter_params["N_coeffs"]
         single = nc == 0.5
@@ -130,7 +139,11 @@ class Oracle:
             P.delta[ax] = float(delta[ax])
             P.vel_present[ax] = int("uvw"[ax] in velocities)
         P.n_vars, P.n_pairs, P.single_exp = n_vars, npairs, int(single)
-        P.with_maps, P.advect = int(with_maps), int(advect)
+        P.with_maps = int(with_maps)
+        P.advect = ADVECTION[advect] if (advect is None or isinstance(advect, str)) else int(bool(advect))
+        P.timestepper = {"RungeKutta3": 0, "QuasiAdamsBashforth2": 1}[timestepper]
+        P.chi = float(chi)
+        P.weights_f32 = int(bool(weights_f32))
         for i in range(npairs):
             P.a[i] = filter_params[f"a{i + 1}"]
             P.c[i] = filter_params[f"c{i + 1}"]
@@ -150,6 +163,10 @@ class Oracle:
             m = np.asfortranarray(mask, dtype=np.float64)
             assert m.shape == self.center_shape
             self.L.lfo_set_mask(self.h, m.ctypes.data)
+        if immersed is not None:
+            m = np.asfortranarray(immersed, dtype=np.float64)
+            assert m.shape == self.center_shape
+            self.L.lfo_set_immersed(self.h, m.ctypes.data)
 
     def close(self):
         if self.h:
@@ -239,7 +256,8 @@ class Oracle:
 
 def run_offline(times, vel, vars_, var_names, N, H, topology, delta, filter_params, dt, T_out,
                 T_start=None, T_end=None, velocities="uw", map_to_mean=True, compute_mean_velocities=True,
-                advect=True, float32_outputs=True, relax_timescale=None, mask=None, return_state=False):
+                advect=True, float32_outputs=True, relax_timescale=None, mask=None, return_state=False,
+                immersed=None, weights_f32=False):
     """Oracle restatement of run_offline_Lagrangian_filter up to and including
     sum_forward_backward_contributions! (reference run_offline_lagrangian_filter.jl:25-105).
 
@@ -256,7 +274,7 @@ def run_offline(times, vel, vars_, var_names, N, H, topology, delta, filter_para
     vars_s = [[v[i] for i in sel] for v in vars_]
     with_maps = map_to_mean or compute_mean_velocities
     o = Oracle(N, H, topology, delta, len(var_names), velocities, filter_params, with_maps, advect,
-               relax_timescale, mask)
+               relax_timescale, mask, immersed=immersed, weights_f32=weights_f32)
     vel_names = [n for n in "uvw" if n in velocities]
 
     def collect():
