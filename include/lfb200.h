@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define LFB_VERSION 100           /* 0.1.0 */
+#define LFB_VERSION 110           /* 0.1.1 */
 
 #define LFB_MAX_COEFFS 8          /* coefficient sets (a,b,c,d), i.e. Butterworth order up to 16 */
 #define LFB_MAX_VARS   8          /* variables to filter                                         */
@@ -54,8 +54,20 @@ extern "C" {
 #define LFB_FLAT     2
 
 /* advection (OfflineFilterConfig.advection, OfflineLagrangianFilter.jl:139,246) */
-#define LFB_ADVECTION_NONE  0     /* advection = nothing: Eulerian filter through the same path  */
-#define LFB_ADVECTION_WENO5 1     /* WENO() default: WENO5-Z, buffers WENO3-Z and Centered2      */
+#define LFB_ADVECTION_NONE      0 /* advection = nothing: Eulerian filter through the same path  */
+#define LFB_ADVECTION_WENO5     1 /* WENO() default: WENO5-Z, buffers WENO3-Z and Centered2      */
+/* the other schemes OfflineFilterConfig.advection admits, each with Oceananigans' buffer-scheme chain
+ * (the scheme whose stencil fits between the walls / outside the immersed boundary is used) */
+#define LFB_ADVECTION_CENTERED2 2 /* Centered(order=2)                                           */
+#define LFB_ADVECTION_CENTERED4 3 /* Centered(order=4) -> Centered2                              */
+#define LFB_ADVECTION_UPWIND1   4 /* UpwindBiased(order=1)                                       */
+#define LFB_ADVECTION_UPWIND3   5 /* UpwindBiased(order=3) -> UpwindBiased1                      */
+#define LFB_ADVECTION_UPWIND5   6 /* UpwindBiased(order=5) -> UpwindBiased3 -> UpwindBiased1     */
+#define LFB_ADVECTION_WENO3     7 /* WENO(order=3) -> Centered2                                  */
+
+/* time stepper (LagrangianFilter(...; timestepper), lagrangian_filter.jl:48,85) */
+#define LFB_TIMESTEPPER_RK3 0     /* :RungeKutta3 (default), lagrangian_filter_rk3_substep.jl:11-61 */
+#define LFB_TIMESTEPPER_AB2 1     /* :QuasiAdamsBashforth2, lagrangian_filter_ab2_step.jl:24-51  */
 
 /* kernel selection (lfb_desc.kernel) */
 #define LFB_KERNEL_AUTO    0
@@ -97,7 +109,10 @@ typedef struct lfb_desc {
     int32_t kernel;               /* LFB_KERNEL_*                                                */
     int32_t relaxation;           /* boundary_relaxation (OfflineLagrangianFilter.jl:108-111)    */
     double  relax_timescale;
-    int32_t reserved[8];          /* must be zero                                                */
+    int32_t timestepper;          /* LFB_TIMESTEPPER_*                                           */
+    int32_t immersed;             /* 1: ImmersedBoundaryGrid; the cell flags follow with lfb_set_immersed */
+    double  chi;                  /* AB2 parameter (Oceananigans default 0.1); ignored by RK3   */
+    int32_t reserved[4];          /* must be zero                                                */
 } lfb_desc;
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
@@ -136,6 +151,17 @@ int lfb_set_slot_time(lfb_handle *h, int slot, double time);
 int lfb_set_direction(lfb_handle *h, int direction);
 /* relaxation mask evaluated at cell centres (mask_func, utils:584-699); parent layout */
 int lfb_set_mask(lfb_handle *h, const double *parent);
+/* Immersed cells of an ImmersedBoundaryGrid (lee-wave example, examples/offline_filter_lee_wave.jl:49-53):
+ * parent array of 0 / 1 flags at cell centres, halos included (periodic halos filled like the data), evaluated
+ * by the host from the bottom height.  Tracers are kept at zero inside the boundary (mask_immersed_field!,
+ * update_lagrangian_filter_state.jl:22-24), no advective flux crosses a face that touches an immersed cell and
+ * the reconstruction drops to the buffer scheme whose stencil stays outside the boundary (Oceananigans'
+ * conditional fluxes / near-boundary interpolation reached through div_Uc,
+ * lagrangian_filter_tendency_kernel_functions.jl:56).  Needs desc.immersed = 1.
+ * cell_heights (or NULL: whole cells, GridFittedBottom): parent array of the cell heights dz(i,j,k) of a
+ * PartialCellBottom (the lee-wave example's choice); they enter the flux divergence through Oceananigans'
+ * partial-cell metrics Ax = dy min(dz[i-1], dz[i]), Ay = dx min(dz[j-1], dz[j]), Az = dx dy, V = dx dy dz. */
+int lfb_set_immersed(lfb_handle *h, const double *parent, const double *cell_heights);
 
 /* ---- state ----------------------------------------------------------------------------------- */
 /* initialise_filtered_vars_from_data, utils:1086-1137 (uses the snapshot at pass time 0) */
@@ -179,6 +205,29 @@ int lfb_host_free(void *ptr);
 int lfb_combine(lfb_handle *h, int64_t n, const double *fwd, const double *bwd_lo, const double *bwd_hi,
                 double w_hi, double sign, double *out);
 
+/* ---- device-resident pass outputs -----------------------------------------------------------------
+ * The reference writes each pass's outputs to forward_output.jld2 / backward_output.jld2 (JLD2Writer,
+ * run_offline_lagrangian_filter.jl:77-80), reads them back, sums them (post:45-170) and reads the sum again for
+ * the remap (post:327-762).  Here the outputs of both passes can stay on the device as dense parent arrays
+ * ("kept" outputs, addressed by small integer ids), are combined there, gathered across the y-slabs of a multi-GPU
+ * run, handed to lfb_remap_to_mean as device pointers and fetched once at the end. */
+/* evaluate an output now (like lfb_output) and keep it: FP64, or rounded to FP32 as the reference's writer does */
+int lfb_output_keep(lfb_handle *h, int kind, int field, int is_f32, int *id);
+/* new FP64 kept array = fwd + sign * (w_hi * bwd_hi + (1 - w_hi) * bwd_lo)  (lfb_combine on kept arrays;
+ * bwd_hi is ignored when w_hi == 0) */
+int lfb_kept_combine(lfb_handle *h, int fwd, int bwd_lo, int bwd_hi, double w_hi, double sign, int *id);
+/* copy a kept array to the host in its own precision (parent layout) */
+int lfb_kept_fetch(lfb_handle *h, int id, void *parent);
+/* precision, parent extents and raw device pointer of a kept array (any of the outputs may be NULL) */
+int lfb_kept_info(lfb_handle *h, int id, int *is_f32, int *extents3, void **device_ptr);
+int lfb_kept_release(lfb_handle *h, int id);
+/* COLLECTIVE over the communicator of lfb_comm_init: assemble the GLOBAL parent array of a kept output on rank
+ * `root` from every rank's y-slab (interior rows from their owners, outer halo rows from the first / last rank).
+ * *gid is the new kept id on `root`, -1 elsewhere; with one rank *gid = id. */
+int lfb_kept_gather(lfb_handle *h, int id, int root, int *gid);
+/* free / total device memory (the host decides whether the pass outputs fit on the device) */
+int lfb_mem_info(lfb_handle *h, size_t *free_bytes, size_t *total_bytes);
+
 /* ---- remap to the mean position (regrid_to_mean_position!, post:327-762) ------------------------ */
 typedef struct lfb_remap_desc {
     int32_t size[3], halo[3], topology[3];   /* grid: two or three axes must be non-Flat                 */
@@ -194,11 +243,17 @@ typedef struct lfb_remap_desc {
  * Piecewise-linear interpolation on the Delaunay triangulation of the normalised, periodically padded
  * cloud (scipy LinearNDInterpolator in the reference; tetrahedra on grids with three non-Flat axes), the
  * reference's edge fix on Bounded axes (numpy.interp along edge rows in 2-D, a 2-D interpolation on the
- * edge planes in 3-D), halos zero, NaN outside the hull.  The simplex search is shared by all fields. */
+ * edge planes in 3-D), halos zero, NaN outside the hull.  The simplex search is shared by all fields.
+ * xi / fields / out may be host pointers or device pointers of desc.device (e.g. from lfb_kept_info): the copies
+ * use unified addressing. */
 int lfb_remap_to_mean(const lfb_remap_desc *desc, const double *const *xi, int n_fields, const double *const *fields,
                       double *const *out);
 
-/* ---- multi-GPU: y-slab decomposition, one process per GPU ------------------------------------- */
+/* ---- multi-GPU: y-slab decomposition, one process per GPU -------------------------------------
+ * With nranks > 1 every call that produces exported arrays or (re)initialises the state exchanges y-halo rows with
+ * the neighbour ranks and is therefore COLLECTIVE: lfb_init_from_data, lfb_step / lfb_run_until, lfb_get_tracer,
+ * lfb_get_tendency, lfb_output, lfb_output_f32, lfb_output_async, lfb_output_keep and lfb_kept_gather must be called
+ * by all ranks in the same order (a rank that reads a diagnostic on its own deadlocks the others). */
 /* NCCL unique id (128 bytes) created on rank 0 and broadcast by the host (torch.distributed / MPI). */
 int lfb_comm_unique_id(void *id128);
 /* Join the communicator.  Rank r owns rows [r*Ny/R, (r+1)*Ny/R) of the global grid; tracer y-halos

@@ -5,10 +5,11 @@ the shim module at the repository root.  The exported names mirror the reference
 (reference src/OceananigansLagrangianFilter.jl:23-30, src/Utils/Utils.jl:17-21); everything that
 touches field data runs in liblfb200.so (hand-written CUDA for sm_100a) -- there is no CPU fallback.
 """
-from .config import InputData, OfflineFilterConfig, OnlineFilterConfig, WENO
+from .config import Centered, InputData, OfflineFilterConfig, OnlineFilterConfig, UpwindBiased, WENO
 from .filter_utils import (FilterParams, create_filtered_vars, create_forcing, set_offline_BW2_filter_params,
                            set_online_BW_filter_params)
-from .grids import Bounded, Flat, Periodic, RectilinearGrid
+from .grids import (Bounded, Flat, GridFittedBottom, ImmersedBoundaryGrid, PartialCellBottom, Periodic,
+                    RectilinearGrid)
 from .jld2 import JLD2File
 from .offline import aligned_time_steps, run_offline_Lagrangian_filter
 from .post import (FilterOutput, compute_Eulerian_filter, compute_time_shift, get_offline_frequency_response,
@@ -18,7 +19,8 @@ from .post import (FilterOutput, compute_Eulerian_filter, compute_time_shift, ge
 __version__ = "0.1.0"
 
 __all__ = [
-    "OfflineFilterConfig", "OnlineFilterConfig", "InputData", "WENO", "RectilinearGrid", "Periodic", "Bounded", "Flat",
+    "OfflineFilterConfig", "OnlineFilterConfig", "InputData", "WENO", "Centered", "UpwindBiased", "RectilinearGrid", "ImmersedBoundaryGrid", "GridFittedBottom",
+    "PartialCellBottom", "Periodic", "Bounded", "Flat",
     "run_offline_Lagrangian_filter", "aligned_time_steps", "set_offline_BW2_filter_params",
     "set_online_BW_filter_params", "create_filtered_vars", "create_forcing", "FilterParams", "FilterOutput",
     "sum_forward_backward_contributions", "regrid_to_mean_position", "compute_Eulerian_filter", "compute_time_shift",

@@ -28,17 +28,58 @@ from .grids import Flat, RectilinearGrid
 log = logging.getLogger("lfb200")
 
 
-class WENO:
-    """Marker for Oceananigans' `WENO()` default: order 5, buffer schemes WENO3 -> Centered2."""
+class _Scheme:
+    """Marker for an Oceananigans advection scheme (`OfflineFilterConfig.advection`, OfflineLagrangianFilter.jl:139,246).
+    `scheme_name` selects the reconstruction and its buffer-scheme chain in liblfb200 (LFB_ADVECTION_*)."""
+    _orders: Tuple[int, ...] = ()
+    _prefix = ""
 
-    def __init__(self, order: int = 5):
-        if order != 5:
-            raise NotImplementedError("liblfb200 implements the reference default WENO(order=5); "
-                                      f"order={order} is not built yet")
-        self.order = order
+    def __init__(self, order: int):
+        if order not in self._orders:
+            raise ValueError(f"{type(self).__name__}(order={order}) is not available; liblfb200 builds orders {self._orders}")
+        self.order = int(order)
+
+    @property
+    def scheme_name(self) -> str:
+        return f"{self._prefix}{self.order}"
+
+    @property
+    def required_halo(self) -> int:
+        """Cells the stencil reaches on each side of a face (Oceananigans' required_halo_size)."""
+        return (self.order + 1) // 2
 
     def __repr__(self):
-        return "WENO(order=5)"
+        return f"{type(self).__name__}(order={self.order})"
+
+    def __eq__(self, other):
+        return type(self) is type(other) and self.order == other.order
+
+    def __hash__(self):
+        return hash((type(self).__name__, self.order))
+
+
+class WENO(_Scheme):
+    """`WENO(order=5)` (the reference's default: WENO5-Z with buffer schemes WENO3-Z -> Centered2) or `WENO(order=3)`."""
+    _orders, _prefix = (3, 5), "WENO"
+
+    def __init__(self, order: int = 5):
+        super().__init__(order)
+
+
+class Centered(_Scheme):
+    """`Centered(order=2)` / `Centered(order=4)` (buffer scheme Centered2)."""
+    _orders, _prefix = (2, 4), "Centered"
+
+    def __init__(self, order: int = 2):
+        super().__init__(order)
+
+
+class UpwindBiased(_Scheme):
+    """`UpwindBiased(order=1 | 3 | 5)` (buffer schemes of the next lower odd order)."""
+    _orders, _prefix = (1, 3, 5), "UpwindBiased"
+
+    def __init__(self, order: int = 3):
+        super().__init__(order)
 
 
 @dataclass
@@ -124,7 +165,7 @@ class OfflineFilterConfig:
     compute_Eulerian_filter: bool
     output_netcdf: bool
     output_original_data: bool
-    advection: Optional[WENO]
+    advection: Optional[_Scheme]
     grid: RectilinearGrid
     label: str
     boundary_relaxation: bool
@@ -136,6 +177,7 @@ class OfflineFilterConfig:
     n_slots: int = 4
     strict: bool = False
     kernel: str = "auto"
+    timestepper: str = "RungeKutta3"       # LagrangianFilter(...; timestepper) (lagrangian_filter.jl:48,85)
     data: Optional[InputData] = field(default=None, repr=False)
 
     def __init__(self, *, var_names_to_filter, velocity_names, original_data_filename=None, data=None,
@@ -145,11 +187,15 @@ class OfflineFilterConfig:
                  compute_mean_velocities=True, delete_intermediate_files=True, compute_Eulerian_filter=False,
                  output_netcdf=False, output_original_data=True, advection="default", grid=None, label="",
                  boundary_relaxation=False, relax_timescale=None, mask_params=None, mask_func=None,
-                 device=0, n_slots=4, strict=False, kernel="auto"):
+                 device=0, n_slots=4, strict=False, kernel="auto", timestepper="RungeKutta3"):
+        if timestepper not in ("RungeKutta3", "QuasiAdamsBashforth2"):
+            raise ValueError("timestepper must be 'RungeKutta3' or 'QuasiAdamsBashforth2'")
         if Δt is None:
             Δt = dt
-        if advection == "default":
+        if isinstance(advection, str) and advection == "default":
             advection = WENO()
+        if advection is not None and not isinstance(advection, _Scheme):
+            raise ValueError("advection must be WENO(...), Centered(...), UpwindBiased(...) or None")
         var_names_to_filter = tuple(var_names_to_filter)
         velocity_names = tuple(velocity_names)
         if data is None:
@@ -269,6 +315,7 @@ class OfflineFilterConfig:
         self.mask_params = mask_params
         self.mask_func = mask_func
         self.device, self.n_slots, self.strict, self.kernel = int(device), int(n_slots), bool(strict), kernel
+        self.timestepper = timestepper
         self.data = data
         self._source = source
 

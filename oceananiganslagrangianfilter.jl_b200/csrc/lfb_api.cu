@@ -32,9 +32,12 @@ cudaError_t lfb_launch_export(void *dst, int is_f32, const double *src, const Lf
 cudaError_t lfb_launch_centre_velocity(double *dst, const double *vel, const LfbLayout *L, int ax, double sign,
                                        cudaStream_t stream);
 cudaError_t lfb_launch_scale(double *dst, const double *src, double factor, int64_t n, cudaStream_t stream);
+cudaError_t lfb_launch_mask_immersed(double *U, const double *imm, int64_t len, int n_fields, cudaStream_t stream);
 cudaError_t lfb_launch_output(double *out, const LfbOutputParams *P, cudaStream_t stream);
 cudaError_t lfb_launch_combine(double *out, const double *fwd, const double *lo, const double *hi, double w,
                                double sign, int64_t n, cudaStream_t stream);
+cudaError_t lfb_launch_combine_mixed(double *out, const void *fwd, int fwd_f32, const void *lo, int lo_f32, const void *hi, int hi_f32,
+                                     double w, double sign, int64_t n, cudaStream_t stream);
 cudaError_t lfb_launch_pack_y(double *buf, double *base, int64_t field_stride, int n_fields, const LfbLayout *L,
                               int side, int unpack, cudaStream_t stream);
 }
@@ -82,6 +85,10 @@ struct lfb_handle {
     double    *G;
     double    *scratch;                    // one field
     double    *mask;
+    double    *imm;                        // immersed-cell flags (desc.immersed), set by lfb_set_immersed
+    double    *dzc;                        // partial-cell heights (optional)
+    int        imm_set;
+    double     last_dt;                    // AB2: the previous step's dt (an Euler step whenever it changes)
     double    *zero_field;                 // velocity components that are not in velocity_names (TMA z-march path)
     double    *cur_in[N_FIELD_IDS];           // inputs at the current stage time (update_input_data!)
     // TMA z-march path: two sets of stage-time velocity fields; while a stage reads one, its helper warps fill the
@@ -122,6 +129,9 @@ struct lfb_handle {
     int        rank, nranks;
     double    *send_lo, *send_hi, *recv_lo, *recv_hi;
     size_t     halo_elems;
+    // device-resident outputs (lfb_output_keep ...): dense parent arrays
+    struct Kept { void *p; int is_f32; int e[3]; };
+    std::vector<Kept> kept;
 };
 
 static inline int field_present(const lfb_handle *h, int field_id)
@@ -174,15 +184,16 @@ static int select_kernel(lfb_handle *h)
     LfbStageParams P;
     memset(&P, 0, sizeof(P));
     P.L = h->L;
-    P.advect = h->desc.advection != LFB_ADVECTION_NONE;
+    P.advect = h->desc.advection;
     P.relax = h->desc.relaxation;
     P.mask = h->mask;
+    P.imm = h->imm;
     for (int ax = 0; ax < 3; ++ax) P.vel_present[ax] = (h->desc.velocity_mask >> ax) & 1;
     P.j0 = 0; P.j1 = h->L.N[1];
     // 0 generic, 3 TMA-staged z-march (what `auto` picks when the grid allows it)
     const int ok_tma = lfb_ztma_supported(&P) && !h->desc.strict;
     const char *need = "a 3-D grid (no Flat axis) with Nx >= 8, Ny >= 4, Nz >= 8, halos >= 3, at least one velocity component, "
-                       "WENO(order=5) advection, RK3, no immersed boundary and strict = 0";
+                       "WENO(order=5) advection, no immersed boundary and strict = 0";
     h->use_zmarch = 0;
     switch (h->desc.kernel) {
     case LFB_KERNEL_AUTO: h->use_zmarch = ok_tma ? 3 : 0; break;
@@ -233,6 +244,7 @@ static int create_impl(lfb_handle *h)
     CU(cudaMemset(h->G, 0, fbytes * nt));
     CU(cudaMemset(h->scratch, 0, fbytes));
     if (desc->relaxation) { CU(cudaMalloc(&h->mask, fbytes)); CU(cudaMemset(h->mask, 0, fbytes)); }
+    if (desc->immersed) { CU(cudaMalloc(&h->imm, fbytes)); CU(cudaMemset(h->imm, 0, fbytes)); }
     for (int f = 0; f < N_FIELD_IDS; ++f)
         if (field_present(h, f)) { CU(cudaMalloc(&h->cur_in[f], fbytes)); CU(cudaMemset(h->cur_in[f], 0, fbytes)); }
     h->staging_bytes = fbytes;     // dense parent arrays are never larger than the padded layout
@@ -279,8 +291,14 @@ extern "C" int lfb_create(const lfb_desc *desc, lfb_handle **out)
         if (desc->topology[ax] < 0 || desc->topology[ax] > 2) return fail(LFB_ERR_ARG, "topology[%d] invalid", ax);
         if (desc->topology[ax] == LFB_FLAT && (desc->size[ax] != 1 || desc->halo[ax] != 0))
             return fail(LFB_ERR_ARG, "Flat axis %d must have size 1 and halo 0", ax);
-        if (desc->topology[ax] != LFB_FLAT && desc->advection == LFB_ADVECTION_WENO5 && desc->halo[ax] < 3)
-            return fail(LFB_ERR_ARG, "WENO5 needs halo >= 3 on axis %d (got %d)", ax, desc->halo[ax]);
+        {
+            // halo the scheme's stencil (and, on an immersed grid, its boundary test) reaches into
+            const int adv = desc->advection;
+            const int need_halo = adv == LFB_ADVECTION_NONE ? 0 : (adv == LFB_ADVECTION_WENO5 || adv == LFB_ADVECTION_UPWIND5) ? 3 :
+                                  (adv == LFB_ADVECTION_CENTERED2 || adv == LFB_ADVECTION_UPWIND1) ? 1 : 2;
+            if (desc->topology[ax] != LFB_FLAT && desc->halo[ax] < need_halo)
+                return fail(LFB_ERR_ARG, "advection scheme %d needs halo >= %d on axis %d (got %d)", adv, need_halo, ax, desc->halo[ax]);
+        }
         if (desc->halo[ax] < 0 || desc->halo[ax] > 8) return fail(LFB_ERR_ARG, "halo[%d] out of range", ax);
         if (!(desc->spacing[ax] > 0)) return fail(LFB_ERR_ARG, "spacing[%d] must be positive", ax);
         if (desc->topology[ax] == LFB_PERIODIC && desc->size[ax] < desc->halo[ax])
@@ -289,10 +307,13 @@ extern "C" int lfb_create(const lfb_desc *desc, lfb_handle **out)
     if (desc->n_vars < 0 || desc->n_vars > LFB_MAX_VARS) return fail(LFB_ERR_ARG, "n_vars out of range");
     if (desc->n_coeffs < 0 || desc->n_coeffs > LFB_MAX_COEFFS) return fail(LFB_ERR_ARG, "n_coeffs out of range");
     if (desc->n_slots < 2 || desc->n_slots > 4096) return fail(LFB_ERR_ARG, "n_slots must be in [2, 4096]");
-    if (desc->advection != LFB_ADVECTION_NONE && desc->advection != LFB_ADVECTION_WENO5)
+    if (desc->advection < LFB_ADVECTION_NONE || desc->advection > LFB_ADVECTION_WENO3)
         return fail(LFB_ERR_ARG, "unknown advection id %d", desc->advection);
+    if (desc->timestepper != LFB_TIMESTEPPER_RK3 && desc->timestepper != LFB_TIMESTEPPER_AB2)
+        return fail(LFB_ERR_ARG, "unknown timestepper id %d", desc->timestepper);
+    if (desc->immersed != 0 && desc->immersed != 1) return fail(LFB_ERR_ARG, "immersed must be 0 or 1");
     if (desc->relaxation && !(desc->relax_timescale > 0)) return fail(LFB_ERR_ARG, "relax_timescale must be set");
-    for (int q = 0; q < 8; ++q) if (desc->reserved[q]) return fail(LFB_ERR_ARG, "reserved fields must be zero");
+    for (int q = 0; q < 4; ++q) if (desc->reserved[q]) return fail(LFB_ERR_ARG, "reserved fields must be zero");
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -311,7 +332,8 @@ extern "C" int lfb_create(const lfb_desc *desc, lfb_handle **out)
     // routed through lfb_destroy without touching garbage or leaking what was already allocated
     h->desc = *desc;
     h->device = desc->device;
-    h->U[0] = h->U[1] = h->G = h->scratch = h->mask = h->zero_field = nullptr;
+    h->U[0] = h->U[1] = h->G = h->scratch = h->mask = h->zero_field = h->imm = h->dzc = nullptr;
+    h->imm_set = 0; h->last_dt = INFINITY;
     h->staging = nullptr; h->staging_bytes = 0;
     for (int f = 0; f < N_FIELD_IDS; ++f) h->cur_in[f] = nullptr;
     for (int f = 0; f < 3; ++f) h->vin_alt[f] = nullptr;
@@ -344,12 +366,13 @@ extern "C" int lfb_destroy(lfb_handle *h)
     for (cudaEvent_t e : h->slot_used) if (e) cudaEventDestroy(e);
     for (auto &pr : h->timing) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto &pr : h->timing_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-    for (double *p : {h->U[0], h->U[1], h->G, h->scratch, h->mask, h->zero_field, h->send_lo, h->send_hi, h->recv_lo, h->recv_hi})
+    for (double *p : {h->U[0], h->U[1], h->G, h->scratch, h->mask, h->imm, h->dzc, h->zero_field, h->send_lo, h->send_hi, h->recv_lo, h->recv_hi})
         if (p) cudaFree(p);
     for (int f = 0; f < N_FIELD_IDS; ++f) if (h->cur_in[f]) cudaFree(h->cur_in[f]);
     for (int f = 0; f < 3; ++f) if (h->vin_alt[f]) cudaFree(h->vin_alt[f]);
     if (h->staging) cudaFree(h->staging);
     for (void *p : h->export_ring) if (p) cudaFree(p);
+    for (auto &k : h->kept) if (k.p) cudaFree(k.p);
     for (cudaEvent_t e : h->ev_export) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_fetched) if (e) cudaEventDestroy(e);
     for (cudaStream_t st : {h->compute, h->copy, h->d2h}) if (st) cudaStreamDestroy(st);
@@ -514,6 +537,32 @@ extern "C" int lfb_set_mask(lfb_handle *h, const double *parent)
     return LFB_OK;
 }
 
+extern "C" int lfb_set_immersed(lfb_handle *h, const double *parent, const double *cell_heights)
+{
+    if (!h || !parent) return fail(LFB_ERR_ARG, "null argument");
+    if (!h->imm) return fail(LFB_ERR_STATE, "handle was created with desc.immersed = 0");
+    CU(cudaSetDevice(h->device));
+    int e[3];
+    parent_extents(h, -1, e);
+    CU(cudaStreamSynchronize(h->copy));
+    CU(cudaMemcpyAsync(h->staging, parent, (size_t)e[0] * e[1] * e[2] * sizeof(double), cudaMemcpyHostToDevice, h->compute));
+    CU(lfb_launch_import(h->imm, h->staging, 0, &h->L, e[0], e[1], e[2], h->compute));
+    h->launches++;
+    CU(cudaStreamSynchronize(h->compute));
+    if (cell_heights) {
+        const size_t fbytes = (size_t)h->L.len * sizeof(double);
+        if (!h->dzc) { CU(cudaMalloc(&h->dzc, fbytes)); }
+        CU(cudaMemset(h->dzc, 0, fbytes));
+        CU(cudaMemcpyAsync(h->staging, cell_heights, (size_t)e[0] * e[1] * e[2] * sizeof(double), cudaMemcpyHostToDevice, h->compute));
+        CU(lfb_launch_import(h->dzc, h->staging, 0, &h->L, e[0], e[1], e[2], h->compute));
+        h->launches++;
+        CU(cudaStreamSynchronize(h->compute));
+    } else if (h->dzc) { cudaFree(h->dzc); h->dzc = nullptr; }
+    h->imm_set = 1;
+    h->halos_valid = 0;
+    return LFB_OK;
+}
+
 // ---- halo handling -------------------------------------------------------------------------------
 // Periodic halos of the current tracer buffer (what the stencils read).  Bounded-axis halos are never
 // read by the stencils and are only produced for exported arrays.  Axes whose images
@@ -572,6 +621,13 @@ static int exchange_y(lfb_handle *h, double *base, int n_fields, cudaStream_t st
 static int refresh_halos(lfb_handle *h, double *base, int n_fields)
 {
     const int force = !h->halos_valid;
+    if (force && h->imm) {
+        // mask_immersed_field! of update_state!: the stage kernels keep immersed cells at zero themselves, so this is
+        // only needed after the state was set from outside (initialisation, lfb_set_tracer)
+        if (!h->imm_set) return fail(LFB_ERR_STATE, "desc.immersed = 1 but lfb_set_immersed was not called");
+        CU(lfb_launch_mask_immersed(base, h->imm, h->L.len, n_fields, h->compute));
+        h->launches++;
+    }
     int rc = fill_periodic_halos(h, base, n_fields, force);
     if (rc) return rc;
     if (h->nranks > 1 && force) { rc = exchange_y(h, base, n_fields); if (rc) return rc; }
@@ -648,7 +704,7 @@ extern "C" int lfb_negate_maps(lfb_handle *h)
 extern "C" int lfb_reset_clock(lfb_handle *h)
 {
     if (!h) return fail(LFB_ERR_ARG, "null handle");
-    h->time = 0; h->iteration = 0;
+    h->time = 0; h->iteration = 0; h->last_dt = INFINITY;      // Oceananigans' reset!(clock): last_dt = Inf
     return LFB_OK;
 }
 
@@ -727,8 +783,10 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
     P.G = h->G;
     P.n_items = h->n_items;
     P.single_exp = h->single_exp;
-    P.advect = h->desc.advection != LFB_ADVECTION_NONE;
+    P.advect = h->desc.advection;
     P.relax = h->desc.relaxation;
+    P.imm = h->imm;
+    P.dzc = h->dzc;
     memcpy(P.items, h->items, sizeof(LfbItem) * h->n_items);
     int s1, s2, interp; double w1, w2;
     int rc = bracket(h, tau, &s1, &s2, &w1, &w2, &interp);
@@ -812,6 +870,7 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
     P.mask = h->mask;
     const double dx = h->desc.spacing[0], dy = h->desc.spacing[1], dz = h->desc.spacing[2];
     P.area[0] = dy * dz; P.area[1] = dx * dz; P.area[2] = dx * dy; P.volume = dx * dy * dz;
+    P.spacing[0] = dx; P.spacing[1] = dy; P.spacing[2] = dz;
     P.relax_timescale = h->desc.relax_timescale;
     P.dt = dt; P.gamma = gamma; P.zeta = zeta;
     P.first_stage = first; P.store_G = store_G; P.update = update;
@@ -886,6 +945,24 @@ extern "C" int lfb_step(lfb_handle *h, double dt)
     if (!h) return fail(LFB_ERR_ARG, "null handle");
     if (!(dt > 0)) return fail(LFB_ERR_ARG, "dt must be positive");
     CU(cudaSetDevice(h->device));
+    if (h->timing.size() > 64) drain_timings(h, false);
+    if (h->desc.timestepper == LFB_TIMESTEPPER_AB2) {
+        // QuasiAdamsBashforth2 (lagrangian_filter_ab2_step.jl:24-51 -> Oceananigans _ab2_step_field!):
+        // U += dt ((3/2 + chi) G^n - (1/2 + chi) G^-), an Euler step (chi = -1/2) at the first step after a clock reset
+        // and whenever dt differs from the previous step's.  One fused stage: G^n of the current state at the current
+        // time, the update, and G^n kept as the next step's G^-.
+        const bool euler = dt != h->last_dt;
+        const double chi = euler ? -0.5 : h->desc.chi;
+        int rc = refresh_halos(h, h->U[h->cur], h->n_tracers);
+        if (rc) return rc;
+        rc = launch_stage(h, h->time, dt, 1.5 + chi, -(0.5 + chi), euler, 1, 1, h->time + dt);
+        if (rc) return rc;
+        h->cur ^= 1;
+        h->time = h->time + dt;
+        h->last_dt = dt;
+        h->iteration += 1;
+        return LFB_OK;
+    }
     // Oceananigans RungeKutta3 (Le & Moin 1991) coefficients and stage times
     const double g1 = 8.0 / 15, g2 = 5.0 / 12, g3 = 3.0 / 4, z2 = -17.0 / 60, z3 = -5.0 / 12;
     const double t0 = h->time, t1 = t0 + dt;
@@ -894,7 +971,6 @@ extern "C" int lfb_step(lfb_handle *h, double dt)
     const double taus[3] = {t0, tau1, tau2};
     const double gam[3] = {g1, g2, g3}, zet[3] = {0.0, z2, z3};
     const double next_tau[3] = {tau1, tau2, t1};       // the stage that follows (the next step starts at t1)
-    if (h->timing.size() > 64) drain_timings(h, false);
     for (int s = 0; s < 3; ++s) {
         int rc = refresh_halos(h, h->U[h->cur], h->n_tracers);
         if (rc) return rc;
@@ -942,9 +1018,21 @@ extern "C" int lfb_get_tendency(lfb_handle *h, int tracer, double *parent)
     CU(cudaSetDevice(h->device));
     int rc = refresh_halos(h, h->U[h->cur], h->n_tracers);
     if (rc) return rc;
+    // AB2 keeps G^- of the previous step in G between steps: set it aside while the diagnostic overwrites G
+    double *keep = nullptr;
+    const size_t gbytes = (size_t)h->L.len * sizeof(double) * h->n_tracers;
+    if (h->desc.timestepper == LFB_TIMESTEPPER_AB2) {
+        CU(cudaMalloc(&keep, gbytes));
+        CU(cudaMemcpyAsync(keep, h->G, gbytes, cudaMemcpyDeviceToDevice, h->compute));
+    }
     rc = launch_stage(h, h->time, 0.0, 0.0, 0.0, 1, 1, 0);
-    if (rc) return rc;
-    return download(h, h->G + (int64_t)tracer * h->L.len, parent, 0, -1);
+    if (!rc) rc = download(h, h->G + (int64_t)tracer * h->L.len, parent, 0, -1);
+    if (keep) {
+        cudaMemcpyAsync(h->G, keep, gbytes, cudaMemcpyDeviceToDevice, h->compute);
+        cudaStreamSynchronize(h->compute);
+        cudaFree(keep);
+    }
+    return rc;
 }
 
 // ---- outputs -------------------------------------------------------------------------------------
@@ -1047,6 +1135,175 @@ extern "C" int lfb_combine(lfb_handle *h, int64_t n, const double *fwd, const do
     }
     // scratch doubles as the zero-initialised work field of outputs: nothing to restore, it is
     // memset before every use
+    return LFB_OK;
+}
+
+
+// ---- device-resident pass outputs ------------------------------------------------------------------
+static int kept_new(lfb_handle *h, int is_f32, const int e[3], int *id)
+{
+    const size_t n = (size_t)e[0] * e[1] * e[2];
+    void *p = nullptr;
+    cudaError_t err = cudaMalloc(&p, n * (is_f32 ? sizeof(float) : sizeof(double)));
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail(LFB_ERR_CUDA, "device memory exhausted while keeping an output (%s); use the host path", cudaGetErrorString(err));
+    }
+    lfb_handle::Kept k;
+    k.p = p; k.is_f32 = is_f32; k.e[0] = e[0]; k.e[1] = e[1]; k.e[2] = e[2];
+    for (size_t q = 0; q < h->kept.size(); ++q)
+        if (!h->kept[q].p) { h->kept[q] = k; *id = (int)q; return LFB_OK; }
+    h->kept.push_back(k);
+    *id = (int)h->kept.size() - 1;
+    return LFB_OK;
+}
+
+static lfb_handle::Kept *kept_get(lfb_handle *h, int id)
+{
+    if (!h || id < 0 || id >= (int)h->kept.size() || !h->kept[id].p) return nullptr;
+    return &h->kept[id];
+}
+
+extern "C" int lfb_output_keep(lfb_handle *h, int kind, int field, int is_f32, int *id)
+{
+    if (!h || !id) return fail(LFB_ERR_ARG, "null argument");
+    CU(cudaSetDevice(h->device));
+    int rc = output_compute(h, kind, field);
+    if (rc) return rc;
+    int e[3];
+    parent_extents(h, -1, e);
+    rc = kept_new(h, is_f32 != 0, e, id);
+    if (rc) return rc;
+    CU(lfb_launch_export(h->kept[*id].p, is_f32 != 0, h->scratch, &h->L, e[0], e[1], e[2], h->compute));
+    h->launches++;
+    return LFB_OK;
+}
+
+extern "C" int lfb_kept_combine(lfb_handle *h, int fwd, int bwd_lo, int bwd_hi, double w_hi, double sign, int *id)
+{
+    if (!h || !id) return fail(LFB_ERR_ARG, "null argument");
+    lfb_handle::Kept *f = kept_get(h, fwd), *lo = kept_get(h, bwd_lo), *hi = w_hi != 0.0 ? kept_get(h, bwd_hi) : lo;
+    if (!f || !lo || !hi) return fail(LFB_ERR_ARG, "unknown kept output id");
+    for (int a = 0; a < 3; ++a)
+        if (f->e[a] != lo->e[a] || f->e[a] != hi->e[a]) return fail(LFB_ERR_ARG, "kept outputs differ in shape");
+    CU(cudaSetDevice(h->device));
+    const lfb_handle::Kept F = *f, LO = *lo, HI = *hi;            // kept_new may move the vector
+    int rc = kept_new(h, 0, F.e, id);
+    if (rc) return rc;
+    const int64_t n = (int64_t)F.e[0] * F.e[1] * F.e[2];
+    CU(lfb_launch_combine_mixed((double *)h->kept[*id].p, F.p, F.is_f32, LO.p, LO.is_f32, HI.p, HI.is_f32, w_hi, sign, n, h->compute));
+    h->launches++;
+    return LFB_OK;
+}
+
+extern "C" int lfb_kept_fetch(lfb_handle *h, int id, void *parent)
+{
+    lfb_handle::Kept *k = kept_get(h, id);
+    if (!k || !parent) return fail(LFB_ERR_ARG, "unknown kept output id / null pointer");
+    CU(cudaSetDevice(h->device));
+    const size_t n = (size_t)k->e[0] * k->e[1] * k->e[2];
+    CU(cudaMemcpyAsync(parent, k->p, n * (k->is_f32 ? sizeof(float) : sizeof(double)), cudaMemcpyDeviceToHost, h->compute));
+    CU(cudaStreamSynchronize(h->compute));
+    return LFB_OK;
+}
+
+extern "C" int lfb_kept_info(lfb_handle *h, int id, int *is_f32, int *extents3, void **device_ptr)
+{
+    lfb_handle::Kept *k = kept_get(h, id);
+    if (!k) return fail(LFB_ERR_ARG, "unknown kept output id");
+    if (is_f32) *is_f32 = k->is_f32;
+    if (extents3) for (int a = 0; a < 3; ++a) extents3[a] = k->e[a];
+    if (device_ptr) {
+        // the pointer is handed to work outside the handle's streams (lfb_remap_to_mean): finish what produces it
+        CU(cudaSetDevice(h->device));
+        CU(cudaStreamSynchronize(h->compute));
+        *device_ptr = k->p;
+    }
+    return LFB_OK;
+}
+
+extern "C" int lfb_kept_release(lfb_handle *h, int id)
+{
+    lfb_handle::Kept *k = kept_get(h, id);
+    if (!k) return fail(LFB_ERR_ARG, "unknown kept output id");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->compute));
+    cudaFree(k->p);
+    k->p = nullptr;
+    return LFB_OK;
+}
+
+// Gather the y-slabs of a kept output on rank `root` (collective over the slab communicator): the interior rows of
+// every rank, the low halo rows of rank 0 and the high halo rows of the last rank -> the GLOBAL parent array.
+extern "C" int lfb_kept_gather(lfb_handle *h, int id, int root, int *gid)
+{
+    if (!h || !gid) return fail(LFB_ERR_ARG, "null argument");
+    lfb_handle::Kept *kp = kept_get(h, id);
+    if (!kp) return fail(LFB_ERR_ARG, "unknown kept output id");
+    if (root < 0 || root >= h->nranks) return fail(LFB_ERR_ARG, "root %d out of range", root);
+    *gid = -1;
+    if (h->nranks == 1) { *gid = id; return LFB_OK; }
+    CU(cudaSetDevice(h->device));
+    const lfb_handle::Kept K = *kp;
+    const int H = h->L.H[1], ny = h->L.N[1], R = h->nranks;
+    const size_t item = K.is_f32 ? sizeof(float) : sizeof(double);
+    const int ex = K.e[0], ey = K.e[1], ez = K.e[2];
+    const int EY = ny * R + 2 * H;
+    auto rows_of = [&](int r, int *lo, int *hi) { *lo = r == 0 ? 0 : H; *hi = r == R - 1 ? ny + 2 * H : ny + H; };
+    int lo, hi;
+    rows_of(h->rank, &lo, &hi);
+    // pack my rows: per z plane a contiguous run of (hi - lo) * ex elements
+    void *pack = nullptr;
+    const size_t my_row_bytes = (size_t)(hi - lo) * ex * item;
+    CU(cudaMalloc(&pack, my_row_bytes * ez));
+    CU(cudaMemcpy2DAsync(pack, my_row_bytes, (const char *)K.p + (size_t)lo * ex * item, (size_t)ey * ex * item, my_row_bytes, ez,
+                         cudaMemcpyDeviceToDevice, h->compute));
+    int rc = LFB_OK;
+    if (h->rank == root) {
+        int ge[3] = {ex, EY, ez};
+        rc = kept_new(h, K.is_f32, ge, gid);
+        if (rc) { cudaFree(pack); return rc; }
+        char *G = (char *)h->kept[*gid].p;
+        std::vector<void *> tmp(R, nullptr);
+        ncclResult_t nr = ncclGroupStart();
+        for (int r = 0; r < R && nr == ncclSuccess; ++r) {
+            if (r == root) continue;
+            int rlo, rhi;
+            rows_of(r, &rlo, &rhi);
+            const size_t bytes = (size_t)(rhi - rlo) * ex * item * ez;
+            if (cudaMalloc(&tmp[r], bytes) != cudaSuccess) { nr = ncclSystemError; break; }
+            nr = ncclRecv(tmp[r], bytes, ncclChar, r, h->comm, h->compute);
+        }
+        if (nr == ncclSuccess) nr = ncclGroupEnd(); else ncclGroupEnd();
+        if (nr != ncclSuccess) rc = fail(LFB_ERR_COMM, "gather of slab outputs failed: %s", ncclGetErrorString(nr));
+        for (int r = 0; r < R && !rc; ++r) {
+            int rlo, rhi;
+            rows_of(r, &rlo, &rhi);
+            const size_t row_bytes = (size_t)(rhi - rlo) * ex * item;
+            const void *src = r == root ? pack : tmp[r];
+            cudaError_t ce = cudaMemcpy2DAsync(G + (size_t)(r * ny + rlo) * ex * item, (size_t)EY * ex * item, src, row_bytes, row_bytes, ez,
+                                               cudaMemcpyDeviceToDevice, h->compute);
+            if (ce != cudaSuccess) rc = fail(LFB_ERR_CUDA, "cudaMemcpy2DAsync: %s", cudaGetErrorString(ce));
+        }
+        cudaStreamSynchronize(h->compute);
+        for (void *t : tmp) if (t) cudaFree(t);
+    } else {
+        ncclResult_t nr = ncclSend(pack, my_row_bytes * ez, ncclChar, root, h->comm, h->compute);
+        if (nr != ncclSuccess) rc = fail(LFB_ERR_COMM, "gather of slab outputs failed: %s", ncclGetErrorString(nr));
+        cudaStreamSynchronize(h->compute);
+    }
+    cudaFree(pack);
+    return rc;
+}
+
+extern "C" int lfb_mem_info(lfb_handle *h, size_t *free_bytes, size_t *total_bytes)
+{
+    if (!h) return fail(LFB_ERR_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    size_t f = 0, t = 0;
+    CU(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
     return LFB_OK;
 }
 

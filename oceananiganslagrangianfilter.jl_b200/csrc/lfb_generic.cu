@@ -30,6 +30,19 @@ __global__ void __launch_bounds__(128) lfb_stage_generic(const __grid_constant__
     const int ijk[3] = {i, j, k};
     const int64_t idx = L.at(i, j, k);
 
+    // face areas and cell volume: regular, or Oceananigans' partial-cell metrics (PartialCellBottom): dz at an x / y
+    // face = min of the two adjacent cell heights
+    T a_lo[3], a_hi[3], vol(P.volume);
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) a_lo[ax] = a_hi[ax] = T(P.area[ax]);
+    if (P.dzc) {
+        const double *__restrict__ hz = P.dzc + idx;
+        if (L.topo[0] != LFB_FLAT) { a_lo[0] = T(P.spacing[1]) * T(fmin(hz[-1], hz[0])); a_hi[0] = T(P.spacing[1]) * T(fmin(hz[0], hz[1])); }
+        if (L.topo[1] != LFB_FLAT) {
+            a_lo[1] = T(P.spacing[0]) * T(fmin(hz[-L.stride[1]], hz[0])); a_hi[1] = T(P.spacing[0]) * T(fmin(hz[0], hz[L.stride[1]]));
+        }
+        vol = T(P.area[2]) * T(hz[0]);
+    }
     // face velocities (low / high face of this cell per axis) and centred velocities for the maps
     T q_lo[3], q_hi[3], q_c[3];
     T div_u(0.0);
@@ -42,9 +55,9 @@ __global__ void __launch_bounds__(128) lfb_stage_generic(const __grid_constant__
         const T hi(P.vel[ax][idx + L.stride[ax]]);
         q_lo[ax] = lo; q_hi[ax] = hi;
         q_c[ax] = (lo + hi) / T(2.0);
-        if (P.advect) div_u = div_u + (T(P.area[ax]) * hi - T(P.area[ax]) * lo);
+        if (P.advect) div_u = div_u + (a_hi[ax] * hi - a_lo[ax] * lo);
     }
-    div_u = div_u / T(P.volume);
+    div_u = div_u / vol;
 
     // periodic images of this cell in the halo: per axis an offset (0 = none); all 2^n - 1 combinations are written
     int64_t wrap[3] = {0, 0, 0};
@@ -57,6 +70,9 @@ __global__ void __launch_bounds__(128) lfb_stage_generic(const __grid_constant__
         if (wrap[ax]) wrap_mask |= 1 << ax;
     }
     const bool nwrap = wrap_mask != 0;
+    // ImmersedBoundaryGrid: flags of this cell and (through the strides) its neighbours
+    const double *__restrict__ imm = P.imm ? P.imm + idx : nullptr;
+    const bool cell_immersed = imm && imm[0] != 0.0;
 
     const int n_sub = P.single_exp ? 1 : 2;
     for (int it = 0; it < P.n_items; ++it) {
@@ -82,13 +98,16 @@ __global__ void __launch_bounds__(128) lfb_stage_generic(const __grid_constant__
                     if (L.topo[ax] == LFB_FLAT || !P.vel_present[ax]) continue;
                     const int64_t s = L.stride[ax];
                     const int m = L.goff[ax] + ijk[ax] + 1;
-                    T c_lo = face_value<T, STRICT>(U + idx, s, m, L.NG[ax], L.topo[ax], q_lo[ax]);
-                    T c_hi = face_value<T, STRICT>(U + idx + s, s, m + 1, L.NG[ax], L.topo[ax], q_hi[ax]);
-                    T F_lo = T(P.area[ax]) * q_lo[ax] * c_lo;
-                    T F_hi = T(P.area[ax]) * q_hi[ax] * c_hi;
+                    T c_lo = face_value<T, STRICT>(U + idx, s, m, L.NG[ax], L.topo[ax], q_lo[ax], P.advect, imm);
+                    T c_hi = face_value<T, STRICT>(U + idx + s, s, m + 1, L.NG[ax], L.topo[ax], q_hi[ax], P.advect, imm ? imm + s : nullptr);
+                    T F_lo = a_lo[ax] * q_lo[ax] * c_lo;
+                    T F_hi = a_hi[ax] * q_hi[ax] * c_hi;
+                    // conditional flux: nothing is advected through a face that touches an immersed cell
+                    if (imm && (imm[-s] != 0.0 || imm[0] != 0.0)) F_lo = T(0.0);
+                    if (imm && (imm[0] != 0.0 || imm[s] != 0.0)) F_hi = T(0.0);
                     div_flux = div_flux + (F_hi - F_lo);
                 }
-                div_flux = div_flux / T(P.volume);
+                div_flux = div_flux / vol;
             }
             // forcing (create_forcing, utils:731-865)
             T forcing;
@@ -113,6 +132,7 @@ __global__ void __launch_bounds__(128) lfb_stage_generic(const __grid_constant__
                 T unew;
                 if (P.first_stage) unew = cval + T(P.dt) * T(P.gamma) * Gn;
                 else               unew = cval + T(P.dt) * (T(P.gamma) * Gn + T(P.zeta) * T(P.G[tix]));
+                if (cell_immersed) unew = T(0.0);          // mask_immersed_field! (update_lagrangian_filter_state.jl:22-24)
                 P.U_new[tix] = val(unew);
                 // periodic halo images of the new state (tracer halo fill of update_state!, fused)
                 if (nwrap) {
@@ -285,6 +305,24 @@ extern "C" cudaError_t lfb_launch_centre_velocity(double *dst, const double *vel
     return cudaGetLastError();
 }
 
+// mask_immersed_field! over a stack of fields (whole padded arrays, halos too): zero where the flag is set
+__global__ void lfb_mask_immersed(double *U, const double *imm, int64_t len, int n_fields)
+{
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; q < len; q += stride)
+        if (imm[q] != 0.0)
+            for (int f = 0; f < n_fields; ++f) U[(int64_t)f * len + q] = 0.0;
+}
+
+extern "C" cudaError_t lfb_launch_mask_immersed(double *U, const double *imm, int64_t len, int n_fields, cudaStream_t stream)
+{
+    int blocks = (int)((len + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    lfb_mask_immersed<<<blocks, 256, 0, stream>>>(U, imm, len, n_fields);
+    return cudaGetLastError();
+}
+
 // dst = factor * src over the whole array (parent(field) .= factor * parent(src), utils:1096-1131,1239-1247)
 __global__ void lfb_scale(double *dst, const double *src, double factor, int64_t n)
 {
@@ -352,6 +390,29 @@ extern "C" cudaError_t lfb_launch_combine(double *out, const double *fwd, const 
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     lfb_combine_kernel<<<blocks, 256, 0, stream>>>(out, fwd, lo, hi, w, sign, n);
+    return cudaGetLastError();
+}
+
+// ... on device-resident pass outputs, each Float32 (as the reference's JLD2Writer rounds them) or Float64
+template <class A, class B, class C2>
+__global__ void lfb_combine_mixed_kernel(double *out, const A *fwd, const B *lo, const C2 *hi, double w, double sign, int64_t n)
+{
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; q < n; q += stride) {
+        const double b = (w == 0.0) ? (double)lo[q] : __dadd_rn(__dmul_rn((double)hi[q], w), __dmul_rn((double)lo[q], 1.0 - w));
+        out[q] = sign < 0 ? __dsub_rn((double)fwd[q], b) : __dadd_rn((double)fwd[q], b);
+    }
+}
+
+extern "C" cudaError_t lfb_launch_combine_mixed(double *out, const void *fwd, int fwd_f32, const void *lo, int lo_f32, const void *hi,
+                                                int hi_f32, double w, double sign, int64_t n, cudaStream_t stream)
+{
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (fwd_f32 != lo_f32 || fwd_f32 != hi_f32) return cudaErrorInvalidValue;     // both passes are written with one writer
+    if (fwd_f32) lfb_combine_mixed_kernel<<<blocks, 256, 0, stream>>>(out, (const float *)fwd, (const float *)lo, (const float *)hi, w, sign, n);
+    else         lfb_combine_mixed_kernel<<<blocks, 256, 0, stream>>>(out, (const double *)fwd, (const double *)lo, (const double *)hi, w, sign, n);
     return cudaGetLastError();
 }
 

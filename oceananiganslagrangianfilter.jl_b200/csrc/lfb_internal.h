@@ -54,8 +54,10 @@ struct LfbStageParams {
     double       *G;          // read as G^- (if use_prev) and overwritten with G^n (if store_G)
     int     n_items;
     int     single_exp;
-    int     advect;
+    int     advect;           // LFB_ADVECTION_* (0 = none)
     int     relax;
+    const double *imm;        // immersed-cell flags (0 / 1), or null: no immersed boundary
+    const double *dzc;        // PartialCellBottom: cell heights dz(i,j,k), or null: regular cells
     LfbItem items[LFB_MAX_ITEMS];
     // inputs at the stage time: u, v, w and the original variables, already interpolated in time (and
     // negated on the backward pass) by lfb_interp_inputs, or aliased to a snapshot slot when the stage
@@ -65,7 +67,7 @@ struct LfbStageParams {
     const double *mask;
     int     vel_present[3];
     // geometry
-    double  area[3], volume;
+    double  area[3], volume, spacing[3];
     double  relax_timescale;
     // RK3 substep: U_new = U_old + dt * (gamma * G + zeta * G^-)
     double  dt, gamma, zeta;

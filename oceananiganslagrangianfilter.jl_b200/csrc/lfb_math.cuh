@@ -15,6 +15,8 @@
 
 #include <cuda_runtime.h>
 
+#include "lfb200.h"
+
 struct sd {
     double v;
     __device__ __forceinline__ sd() {}
@@ -99,38 +101,69 @@ __device__ __forceinline__ double weno5z_increment(double dp, double do_, double
     return fma(-num, r, fma(1.0 / 3.0, dn, (1.0 / 6.0) * do_));
 }
 
-// Upwind face value at face m (1-based; between cells m-1 and m) along one axis.
-//   cm: pointer to cell m; s: stride along the axis; N: global cell count; topo: axis topology;
-//   q: advecting face velocity.
-// Bounded axes degrade WENO5 -> WENO3 -> Centered2 by face index; on the wall
-// faces m = 1, N+1 the zero-flux halo cell mirrors the interior, so Centered2 returns the
-// interior value.
-template <class T, bool STRICT>
-__device__ __forceinline__ T face_value(const double *__restrict__ cm, int64_t s, int m, int N, int topo, T q)
+// Reconstruction kinds of a scheme chain.  Every Oceananigans scheme carries a buffer scheme that takes over where
+// its own stencil would reach outside a Bounded domain or into the immersed boundary (chains, highest order first:
+// WENO5 -> WENO3 -> Centered2, UpwindBiased5 -> 3 -> 1, Centered4 -> Centered2; the first one is printed at
+// OfflineLagrangianFilter.jl:212-214).
+enum { LFB_K_C2, LFB_K_C4, LFB_K_U1, LFB_K_U3, LFB_K_U5, LFB_K_W3, LFB_K_W5 };
+
+// Kind used at face m (1-based; between cells m-1 and m) of an axis of N cells: the first scheme of the chain whose
+// symmetric stencil of `buffer` cells on each side of the face (cells m-b .. m+b-1) lies inside a Bounded domain and
+// outside the immersed boundary (imm: flag of cell m, or null).  For WENO(order=5) without an immersed boundary this
+// is the face-index rule of SURVEY.md App. A.5.
+__device__ __forceinline__ int lfb_face_kind(int scheme, int m, int N, int topo, const double *__restrict__ imm, int64_t s)
 {
-    int order = 5;
-    if (topo == LFB_BOUNDED) {
-        if (m >= 4 && m <= N - 2) order = 5;
-        else if (m >= 3 && m <= N - 1) order = 3;
-        else order = 2;
+    int kind[3], buf[3], n;
+    switch (scheme) {
+    case LFB_ADVECTION_WENO3:     kind[0] = LFB_K_W3; buf[0] = 2; kind[1] = LFB_K_C2; buf[1] = 1; n = 2; break;
+    case LFB_ADVECTION_CENTERED4: kind[0] = LFB_K_C4; buf[0] = 2; kind[1] = LFB_K_C2; buf[1] = 1; n = 2; break;
+    case LFB_ADVECTION_CENTERED2: kind[0] = LFB_K_C2; buf[0] = 1; n = 1; break;
+    case LFB_ADVECTION_UPWIND5:   kind[0] = LFB_K_U5; buf[0] = 3; kind[1] = LFB_K_U3; buf[1] = 2; kind[2] = LFB_K_U1; buf[2] = 1; n = 3; break;
+    case LFB_ADVECTION_UPWIND3:   kind[0] = LFB_K_U3; buf[0] = 2; kind[1] = LFB_K_U1; buf[1] = 1; n = 2; break;
+    case LFB_ADVECTION_UPWIND1:   kind[0] = LFB_K_U1; buf[0] = 1; n = 1; break;
+    default:                      kind[0] = LFB_K_W5; buf[0] = 3; kind[1] = LFB_K_W3; buf[1] = 2; kind[2] = LFB_K_C2; buf[2] = 1; n = 3; break;
     }
-    if (order == 2) {
-        if (m == 1) return T(cm[0]);
-        if (m == N + 1) return T(cm[-s]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (c >= n) break;
+        const int b = buf[c];
+        bool ok = !(topo == LFB_BOUNDED && (m - b < 1 || m + b - 1 > N));
+        if (ok && imm)
+            for (int r = -b; r < b; ++r) if (imm[r * s] != 0.0) { ok = false; break; }
+        if (ok) return kind[c];
+    }
+    return LFB_K_C2;
+}
+
+// Face value at face m (1-based; between cells m-1 and m) along one axis.
+//   cm: pointer to cell m; s: stride along the axis; N: global cell count; topo: axis topology;
+//   q: advecting face velocity; imm: immersed flag of cell m (or null).
+// On the wall faces m = 1, N+1 of a Bounded axis the zero-flux halo cell mirrors the interior, so Centered2 returns
+// the interior value (the device layout does not keep Bounded halos).
+template <class T, bool STRICT>
+__device__ __forceinline__ T face_value(const double *__restrict__ cm, int64_t s, int m, int N, int topo, T q, int scheme,
+                                        const double *__restrict__ imm)
+{
+    const int kind = lfb_face_kind(scheme, m, N, topo, imm, s);
+    if (kind == LFB_K_C2) {
+        if (topo == LFB_BOUNDED && m == 1) return T(cm[0]);
+        if (topo == LFB_BOUNDED && m == N + 1) return T(cm[-s]);
         return (T(cm[-s]) + T(cm[0])) / T(2.0);
     }
+    if (kind == LFB_K_C4)
+        return T(-1.0 / 12.0) * T(cm[-2 * s]) + T(7.0 / 12.0) * T(cm[-s]) + T(7.0 / 12.0) * T(cm[0]) + T(-1.0 / 12.0) * T(cm[s]);
+    // upwind-ordered stencil (p, o, n | e, f): n is the upwind cell
     const bool left = val(q) > 0.0;
-    if (order == 3) {
-        T o = left ? T(cm[-2 * s]) : T(cm[s]);
-        T n = left ? T(cm[-s]) : T(cm[0]);
-        T e = left ? T(cm[0]) : T(cm[-s]);
-        return weno3z_ref<T>(o, n, e);
-    }
-    double p = left ? cm[-3 * s] : cm[2 * s];
-    double o = left ? cm[-2 * s] : cm[s];
-    double n = left ? cm[-s] : cm[0];
-    double e = left ? cm[0] : cm[-s];
-    double f = left ? cm[s] : cm[-2 * s];
+    const double n = left ? cm[-s] : cm[0];
+    if (kind == LFB_K_U1) return T(n);
+    const double o = left ? cm[-2 * s] : cm[s];
+    const double e = left ? cm[0] : cm[-s];
+    if (kind == LFB_K_W3) return weno3z_ref<T>(T(o), T(n), T(e));
+    if (kind == LFB_K_U3) return T(-1.0 / 6.0) * T(o) + T(5.0 / 6.0) * T(n) + T(1.0 / 3.0) * T(e);
+    const double p = left ? cm[-3 * s] : cm[2 * s];
+    const double f = left ? cm[s] : cm[-2 * s];
+    if (kind == LFB_K_U5)
+        return T(2.0 / 60.0) * T(p) + T(-13.0 / 60.0) * T(o) + T(47.0 / 60.0) * T(n) + T(27.0 / 60.0) * T(e) + T(-3.0 / 60.0) * T(f);
     if (STRICT) return weno5z_ref<T>(T(p), T(o), T(n), T(e), T(f));
     return T(n + weno5z_increment(o - p, n - o, e - n, f - e));
 }

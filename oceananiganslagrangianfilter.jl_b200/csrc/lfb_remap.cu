@@ -586,7 +586,7 @@ static int remap3(const lfb_remap_desc *D, const double *const *xi, int n_fields
     for (int a = 0; a < 3; ++a)
         if (D->has_map[a] && xi[a]) {
             RCU3(cudaMalloc(&d_xi[a], len * sizeof(double)));
-            RCU3(cudaMemcpy(d_xi[a], xi[a], len * sizeof(double), cudaMemcpyHostToDevice));
+            RCU3(cudaMemcpy(d_xi[a], xi[a], len * sizeof(double), cudaMemcpyDefault));
         }
     RCU3(cudaMalloc(&d_part, 3 * EXT_BLOCKS * sizeof(double)));
     for (int a = 0; a < 3; ++a) {
@@ -690,7 +690,7 @@ static int remap3(const lfb_remap_desc *D, const double *const *xi, int n_fields
         if (f2) { cleanup(); RFAIL(LFB_ERR_STATE, "remap patch too small on an edge plane"); }
     }
     for (int v = 0; v < n_fields; ++v) {
-        RCU3(cudaMemcpy(d_f, fields[v], len * sizeof(double), cudaMemcpyHostToDevice));
+        RCU3(cudaMemcpy(d_f, fields[v], len * sizeof(double), cudaMemcpyDefault));
         RCU3(cudaMemset(d_out, 0, len * sizeof(double)));                      // halos stay zero (post:748)
         lfb_remap3d_apply<<<grid, block>>>(P, d_tet, d_w, d_f, d_out);
         RCU3(cudaGetLastError());
@@ -699,7 +699,7 @@ static int remap3(const lfb_remap_desc *D, const double *const *xi, int n_fields
             lfb_remap2d_apply<<<g2, block>>>(pl.P2, d_ptri + 3 * pl.off, d_pw + 3 * pl.off, d_f + pl.base, d_out + pl.base);
             RCU3(cudaGetLastError());
         }
-        RCU3(cudaMemcpy(out[v], d_out, len * sizeof(double), cudaMemcpyDeviceToHost));
+        RCU3(cudaMemcpy(out[v], d_out, len * sizeof(double), cudaMemcpyDefault));
     }
     cleanup();
 #undef RCU3
@@ -765,7 +765,7 @@ extern "C" int lfb_remap_to_mean(const lfb_remap_desc *D, const double *const *x
     for (int q = 0; q < 2; ++q)
         if (P.has_map[q]) {
             RCU(cudaMalloc(&d_xi[q], len * sizeof(double)));
-            RCU(cudaMemcpy(d_xi[q], xi[ax[q]], len * sizeof(double), cudaMemcpyHostToDevice));
+            RCU(cudaMemcpy(d_xi[q], xi[ax[q]], len * sizeof(double), cudaMemcpyDefault));
         }
     RCU(cudaMalloc(&d_f, len * sizeof(double)));
     RCU(cudaMalloc(&d_out, len * sizeof(double)));
@@ -792,7 +792,7 @@ extern "C" int lfb_remap_to_mean(const lfb_remap_desc *D, const double *const *x
     }
     if (flag) { cleanup(); RFAIL(LFB_ERR_STATE, "remap patch too small even at radius (%d, %d): displacements too large for the local search", P.r[0], P.r[1]); }
     for (int v = 0; v < n_fields; ++v) {
-        RCU(cudaMemcpy(d_f, fields[v], len * sizeof(double), cudaMemcpyHostToDevice));
+        RCU(cudaMemcpy(d_f, fields[v], len * sizeof(double), cudaMemcpyDefault));
         RCU(cudaMemset(d_out, 0, len * sizeof(double)));                       // halos stay zero (post:748)
         lfb_remap2d_apply<<<grid, block>>>(P, d_tri, d_w, d_f, d_out);
         RCU(cudaGetLastError());
@@ -804,7 +804,7 @@ extern "C" int lfb_remap_to_mean(const lfb_remap_desc *D, const double *const *x
                 RCU(cudaGetLastError());
             }
         }
-        RCU(cudaMemcpy(out[v], d_out, len * sizeof(double), cudaMemcpyDeviceToHost));
+        RCU(cudaMemcpy(out[v], d_out, len * sizeof(double), cudaMemcpyDefault));
     }
     cleanup();
     return LFB_OK;

@@ -761,7 +761,7 @@ static int zt_make_map(CUtensorMap *m, const LfbLayout &L, const void *base, int
 extern "C" int lfb_ztma_supported(const LfbStageParams *P)
 {
     const LfbLayout &L = P->L;
-    if (!P->advect || (P->relax && !P->mask)) return 0;
+    if (P->advect != LFB_ADVECTION_WENO5 || P->imm || (P->relax && !P->mask)) return 0;
     if (L.topo[0] == LFB_FLAT || L.topo[1] == LFB_FLAT || L.topo[2] == LFB_FLAT) return 0;
     if (L.topo[2] == LFB_PERIODIC && L.N[2] < 2 * L.H[2]) return 0;
     if (!(P->vel_present[0] || P->vel_present[1] || P->vel_present[2])) return 0;     // absent components: a zero field

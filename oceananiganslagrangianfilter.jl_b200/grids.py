@@ -134,3 +134,126 @@ class RectilinearGrid:
         object.__setattr__(g, "origin", tuple(o))
         object.__setattr__(g, "_slab", (rank, nranks))
         return g
+
+
+# ---------------------------------------------------------------------------------------------- immersed boundary
+class GridFittedBottom:
+    """Oceananigans' `GridFittedBottom(bottom_height)`: whole cells whose centre lies at or below the bottom are
+    immersed.  `bottom` is a number, a callable of the horizontal non-Flat coordinates (`bottom(x)` / `bottom(x, y)`)
+    or an (Nx, Ny) array of interior values."""
+
+    def __init__(self, bottom):
+        self.bottom = bottom
+
+
+class PartialCellBottom(GridFittedBottom):
+    """Oceananigans' `PartialCellBottom(bottom_height; minimum_fractional_cell_height = 0.2)` as used by the
+    reference's lee-wave example (examples/offline_filter_lee_wave.jl:53): a cell is immersed when its TOP face lies
+    at or below the bottom, and the bottom is capped so that the lowest wet cell keeps at least the minimum fraction
+    of its height.  The partial heights enter the filter PDE through the face areas and cell volumes of the flux
+    divergence (`cell_heights`)."""
+
+    def __init__(self, bottom, minimum_fractional_cell_height: float = 0.2):
+        super().__init__(bottom)
+        self.minimum_fractional_cell_height = float(minimum_fractional_cell_height)
+
+
+class ImmersedBoundaryGrid:
+    """`ImmersedBoundaryGrid(underlying_grid, immersed_boundary)`: the underlying regular grid plus a bottom.  It
+    answers everything RectilinearGrid answers (attribute access is forwarded), and evaluates on the host what the
+    device needs: the immersed-cell flags (`immersed_flags`) and, for partial cells, the cell heights."""
+
+    def __init__(self, underlying_grid: RectilinearGrid, immersed_boundary: GridFittedBottom):
+        if underlying_grid.topology[2] == Flat:
+            raise ValueError("an immersed bottom needs a non-Flat z axis")
+        self.underlying_grid = underlying_grid
+        self.immersed_boundary = immersed_boundary
+
+    def __getattr__(self, name):
+        if name in ("underlying_grid", "immersed_boundary"):
+            raise AttributeError(name)
+        return getattr(self.underlying_grid, name)
+
+    def slab(self, rank: int, nranks: int) -> "ImmersedBoundaryGrid":
+        if nranks == 1:
+            return self
+        ib = self.immersed_boundary
+        if isinstance(ib.bottom, np.ndarray):
+            ny = self.underlying_grid.Ny // nranks
+            ib = type(ib).__new__(type(ib))
+            ib.__dict__.update(self.immersed_boundary.__dict__)
+            ib.bottom = np.asarray(self.immersed_boundary.bottom)[:, rank * ny:(rank + 1) * ny]
+        return ImmersedBoundaryGrid(self.underlying_grid.slab(rank, nranks), ib)
+
+    # ------------------------------------------------------------------ host evaluation
+    def bottom_height(self) -> np.ndarray:
+        """Bottom height on the interior horizontal cells, shape (Nx, Ny), as given (before any capping)."""
+        g, b = self.underlying_grid, self.immersed_boundary.bottom
+        if callable(b):
+            hax = [ax for ax in (0, 1) if g.topology[ax] != Flat]
+            coords = [g.nodes(ax, with_halos=False) for ax in hax]
+            mesh = np.meshgrid(*coords, indexing="ij") if coords else []
+            vals = np.vectorize(lambda *xs: float(b(*xs)))(*mesh) if coords else np.asarray(float(b()))
+            shape = [1, 1]
+            for n, ax in enumerate(hax):
+                shape[ax] = len(coords[n])
+            return np.asarray(vals, dtype=np.float64).reshape(shape)
+        if np.isscalar(b):
+            return np.full((g.Nx, g.Ny), float(b))
+        a = np.asarray(b, dtype=np.float64).reshape(g.Nx, g.Ny)
+        return a
+
+    def _fill_periodic(self, a: np.ndarray) -> np.ndarray:
+        g = self.underlying_grid
+        for ax in range(3):
+            H, N = g.H[ax], g.N[ax]
+            if H == 0 or g.topology[ax] != Periodic:
+                continue
+            lo = [slice(None)] * 3; hi = [slice(None)] * 3; slo = [slice(None)] * 3; shi = [slice(None)] * 3
+            lo[ax] = slice(0, H); slo[ax] = slice(N, N + H)
+            hi[ax] = slice(N + H, N + 2 * H); shi[ax] = slice(H, 2 * H)
+            a[tuple(lo)] = a[tuple(slo)]
+            a[tuple(hi)] = a[tuple(shi)]
+        return a
+
+    def _adjusted_bottom(self):
+        """(zb, z_faces): the bottom height the immersed test uses, per interior column."""
+        g, ib = self.underlying_grid, self.immersed_boundary
+        zb = self.bottom_height()
+        dz = g.spacing[2]
+        zf = g.origin[2] + dz * np.arange(g.Nz + 1)                 # faces k = 1 .. Nz+1
+        if isinstance(ib, PartialCellBottom):
+            eps = ib.minimum_fractional_cell_height
+            zb = zb.copy()
+            for k in range(g.Nz):
+                bottom_cell = (zf[k] <= zb) & (zf[k + 1] >= zb)
+                zb = np.where(bottom_cell, np.minimum(zf[k + 1] - eps * dz, zb), zb)
+        return zb, zf
+
+    def immersed_flags(self) -> np.ndarray:
+        """Parent array (centre, halos included) of 0 / 1 flags: 1 inside the immersed boundary.  Periodic halos
+        carry the periodic images, the halos of Bounded axes stay 0 (no stencil test reads them)."""
+        g, ib = self.underlying_grid, self.immersed_boundary
+        zb, zf = self._adjusted_bottom()
+        if isinstance(ib, PartialCellBottom):
+            ztest = zf[1:]                                             # top face of cell k
+        else:
+            ztest = 0.5 * (zf[:-1] + zf[1:])                           # cell centre
+        inner = (ztest[None, None, :] <= zb[:, :, None]).astype(np.float64)
+        out = np.zeros(g.center_shape(), dtype=np.float64, order="F")
+        out[g.Hx:g.Hx + g.Nx, g.Hy:g.Hy + g.Ny, g.Hz:g.Hz + g.Nz] = inner
+        return np.asfortranarray(self._fill_periodic(out))
+
+    def cell_heights(self):
+        """Parent array of the cell heights dz(i,j,k) for PartialCellBottom (None for whole cells): the lowest wet
+        cell of a column reaches from the (capped) bottom to its top face."""
+        g, ib = self.underlying_grid, self.immersed_boundary
+        if not isinstance(ib, PartialCellBottom):
+            return None
+        zb, zf = self._adjusted_bottom()
+        dz = g.spacing[2]
+        bottom_cell = (zf[None, None, :-1] <= zb[:, :, None]) & (zf[None, None, 1:] >= zb[:, :, None])
+        inner = np.where(bottom_cell, zf[None, None, 1:] - zb[:, :, None], dz)
+        out = np.full(g.center_shape(), dz, dtype=np.float64, order="F")
+        out[g.Hx:g.Hx + g.Nx, g.Hy:g.Hy + g.Ny, g.Hz:g.Hz + g.Nz] = inner
+        return np.asfortranarray(self._fill_periodic(out))

@@ -15,7 +15,7 @@ import numpy as np
 from . import _lib
 from ._lib import check
 from .filter_utils import FilterParams, create_filtered_vars, tracer_layout
-from .grids import RectilinearGrid
+from .grids import ImmersedBoundaryGrid, RectilinearGrid
 
 _KERNELS = {"auto": _lib.KERNEL_AUTO, "generic": _lib.KERNEL_GENERIC, "ztma": _lib.KERNEL_ZTMA}
 
@@ -24,7 +24,11 @@ class LagrangianFilter:
     def __init__(self, grid: RectilinearGrid, *, var_names_to_filter: Sequence[str], velocity_names: Sequence[str],
                  filter_params: FilterParams, with_maps: bool = True, advection=True, n_slots: int = 4,
                  device: int = 0, strict: bool = False, kernel: str = "auto", label: str = "",
-                 relax_timescale: Optional[float] = None, mask: Optional[np.ndarray] = None, config=None):
+                 relax_timescale: Optional[float] = None, mask: Optional[np.ndarray] = None, config=None,
+                 timestepper: str = "RungeKutta3", chi: float = 0.1):
+        """advection: True (the default WENO(order=5)), False / None (advection = nothing), a config.WENO / Centered /
+        UpwindBiased marker or a scheme name of _lib.ADVECTION; timestepper: "RungeKutta3" | "QuasiAdamsBashforth2"
+        (lagrangian_filter.jl:48,85); grid: RectilinearGrid or ImmersedBoundaryGrid."""
         self.L = _lib.load()
         self.grid = grid
         self.var_names = tuple(var_names_to_filter)
@@ -44,7 +48,20 @@ class LagrangianFilter:
         for i in range(filter_params.n_sets):
             d.a[i], d.b[i], d.c[i], d.d[i] = a[i], b[i], c[i], dd[i]
         d.with_maps = int(self.with_maps)
-        d.advection = _lib.ADVECTION_WENO5 if advection else _lib.ADVECTION_NONE
+        if advection is True:
+            advection = "WENO5"
+        elif advection is False:
+            advection = None
+        elif hasattr(advection, "scheme_name"):
+            advection = advection.scheme_name
+        if advection not in _lib.ADVECTION:
+            raise ValueError(f"unknown advection scheme {advection!r}; one of {sorted(k for k in _lib.ADVECTION if k)}")
+        d.advection = _lib.ADVECTION[advection]
+        if timestepper not in _lib.TIMESTEPPER:
+            raise ValueError(f"timestepper must be one of {sorted(_lib.TIMESTEPPER)}")
+        d.timestepper, d.chi = _lib.TIMESTEPPER[timestepper], float(chi)
+        immersed = isinstance(grid, ImmersedBoundaryGrid)
+        d.immersed = int(immersed)
         d.n_slots, d.device, d.strict, d.kernel = int(n_slots), int(device), int(bool(strict)), _KERNELS[kernel]
         d.relaxation = int(relax_timescale is not None)
         d.relax_timescale = float(relax_timescale or 0.0)
@@ -63,6 +80,11 @@ class LagrangianFilter:
         if mask is not None:
             m = _lib.as_parent(mask, self.center_shape)
             check(self.L.lfb_set_mask(self.h, m.ctypes.data))
+        if immersed:
+            flags = _lib.as_parent(grid.immersed_flags(), self.center_shape)
+            heights = grid.cell_heights()
+            hp = _lib.as_parent(heights, self.center_shape) if heights is not None else None
+            check(self.L.lfb_set_immersed(self.h, flags.ctypes.data, hp.ctypes.data if hp is not None else None))
 
     # ------------------------------------------------------------------ lifecycle
     def free_pinned(self):

@@ -178,7 +178,8 @@ def build_model(config: OfflineFilterConfig) -> LagrangianFilter:
     return LagrangianFilter(config.grid, var_names_to_filter=config.var_names_to_filter,
                             velocity_names=config.velocity_names, filter_params=config.filter_params,
                             with_maps=config.map_to_mean or config.compute_mean_velocities,
-                            advection=config.advection is not None, n_slots=config.n_slots, device=config.device,
+                            advection=config.advection, n_slots=config.n_slots, device=config.device,
+                            timestepper=config.timestepper,
                             strict=config.strict, kernel=config.kernel, label=config.label,
                             relax_timescale=config.relax_timescale if config.boundary_relaxation else None,
                             mask=mask, config=config)

@@ -85,6 +85,8 @@ typedef struct {
     lfo_field var[LFO_MAXV];      /* current original variables (aux fields)         */
     lfo_field mask;               /* relaxation mask at centres (optional)           */
     lfo_field imm;                /* 1.0 in immersed cells (ImmersedBoundaryGrid), else 0; halos too */
+    lfo_field dzc;                /* PartialCellBottom: cell heights dz(i,j,k) at centres (optional) */
+    int     partial;
     double  last_dt;              /* AB2: the previous step's dt (Euler step when it changes) */
     /* input series */
     int     n_snap;
@@ -185,6 +187,7 @@ lfo_state *lfo_create(const lfo_problem *P)
     for (int v = 0; v < P->n_vars; ++v) field_alloc(&S->var[v], P, -1);
     field_alloc(&S->mask, P, -1);
     field_alloc(&S->imm, P, -1);
+    field_alloc(&S->dzc, P, -1);
     S->last_dt = INFINITY;        /* Oceananigans Clock: last_dt = Inf */
     return S;
 }
@@ -212,6 +215,7 @@ void lfo_destroy(lfo_state *S)
     for (int v = 0; v < S->P.n_vars; ++v) free(S->var[v].p);
     free(S->mask.p);
     free(S->imm.p);
+    free(S->dzc.p);
     free(S);
 }
 
@@ -284,6 +288,15 @@ void lfo_set_immersed(lfo_state *S, const double *imm_parent)
 {
     memcpy(S->imm.p, imm_parent, sizeof(double) * S->imm.len);
     S->P.immersed = 1;
+}
+
+/* PartialCellBottom (examples/offline_filter_lee_wave.jl:53): cell heights dz(i,j,k) as a parent array.  Oceananigans'
+ * partial-cell metrics: dz at an x (y) face = min of the two adjacent cell heights, so Ax = dy min(dz[i-1], dz[i]),
+ * Ay = dx min(dz[j-1], dz[j]), Az = dx dy, V = dx dy dz[i,j,k]. */
+void lfo_set_cell_heights(lfo_state *S, const double *dz_parent)
+{
+    memcpy(S->dzc.p, dz_parent, sizeof(double) * S->dzc.len);
+    S->partial = 1;
 }
 
 /* mask_immersed_field!: tracers are zero inside the immersed boundary (update_lagrangian_filter_state.jl:22-24) */
@@ -461,7 +474,13 @@ static void compute_tendencies(lfo_state *S)
             const double *cp = me->p + ic;
             double div_flux = 0, div_u = 0;
             if (P->advect) {
-                const double area[3] = {Ax, Ay, Az};
+                double a_lo[3] = {Ax, Ay, Az}, a_hi[3] = {Ax, Ay, Az}, Vc = V;
+                if (S->partial) {
+                    const double *hz = S->dzc.p + ic;
+                    if (P->topo[0] != TOPO_FLAT) { a_lo[0] = dy * fmin(hz[-sc[0]], hz[0]); a_hi[0] = dy * fmin(hz[0], hz[sc[0]]); }
+                    if (P->topo[1] != TOPO_FLAT) { a_lo[1] = dx * fmin(hz[-sc[1]], hz[0]); a_hi[1] = dx * fmin(hz[0], hz[sc[1]]); }
+                    Vc = Az * hz[0];
+                }
                 for (int ax = 0; ax < 3; ++ax) {
                     if (P->topo[ax] == TOPO_FLAT || !P->vel_present[ax]) continue;
                     const lfo_field *vf = &S->vel[ax];
@@ -472,15 +491,15 @@ static void compute_tendencies(lfo_state *S)
                     const double *ip = P->immersed ? S->imm.p + ic : NULL;
                     double c_lo = face_value(P, cp, ip, sc[ax], m, P->N[ax], P->topo[ax], q_lo);
                     double c_hi = face_value(P, cp + sc[ax], ip ? ip + sc[ax] : NULL, sc[ax], m + 1, P->N[ax], P->topo[ax], q_hi);
-                    double F_lo = area[ax] * q_lo * c_lo, F_hi = area[ax] * q_hi * c_hi;
+                    double F_lo = a_lo[ax] * q_lo * c_lo, F_hi = a_hi[ax] * q_hi * c_hi;
                     /* conditional_flux: no advective flux through a face of the immersed boundary */
                     if (ip && (ip[-sc[ax]] != 0.0 || ip[0] != 0.0)) F_lo = 0;
                     if (ip && (ip[0] != 0.0 || ip[sc[ax]] != 0.0)) F_hi = 0;
                     div_flux += (F_hi - F_lo);
-                    div_u += (area[ax] * q_hi - area[ax] * q_lo);
+                    div_u += (a_hi[ax] * q_hi - a_lo[ax] * q_lo);
                 }
-                div_flux = div_flux / V;
-                div_u = div_u / V;
+                div_flux = div_flux / Vc;
+                div_u = div_u / Vc;
             }
             /* forcing */
             double forcing;

@@ -71,6 +71,7 @@ def lib():
                                       PP, PP, PP, C.POINTER(PP)]
         L.lfo_set_mask.argtypes = [C.c_void_p, C.c_void_p]
         L.lfo_set_immersed.argtypes = [C.c_void_p, C.c_void_p]
+        L.lfo_set_cell_heights.argtypes = [C.c_void_p, C.c_void_p]
         L.lfo_update_state.argtypes = [C.c_void_p]
         L.lfo_init_from_data.argtypes = [C.c_void_p]
         L.lfo_negate_maps.argtypes = [C.c_void_p]
@@ -126,8 +127,8 @@ class Oracle:
 
     def __init__(self, N, H, topology, delta, n_vars, velocities="uvw", filter_params=None, with_maps=True,
                  advect=True, relax_timescale=None, mask=None, timestepper="RungeKutta3", chi=0.1, immersed=None,
-                 weights_f32=False):
-        """advect: True (the default WENO(order=5)), False / None (advection = nothing) or a scheme name from
+                 weights_f32=False, cell_heights=None):
+        """cell_heights: parent array of dz(i,j,k) (PartialCellBottom) or None.  advect: True (the default WENO(order=5)), False / None (advection = nothing) or a scheme name from
         ADVECTION; timestepper: "RungeKutta3" | "QuasiAdamsBashforth2"; immersed: parent array of 0 / 1 flags."""
         P = _Problem()
         nc = filter_params["N_coeffs"]
@@ -167,6 +168,10 @@ class Oracle:
             m = np.asfortranarray(immersed, dtype=np.float64)
             assert m.shape == self.center_shape
             self.L.lfo_set_immersed(self.h, m.ctypes.data)
+        if cell_heights is not None:
+            m = np.asfortranarray(cell_heights, dtype=np.float64)
+            assert m.shape == self.center_shape
+            self.L.lfo_set_cell_heights(self.h, m.ctypes.data)
 
     def close(self):
         if self.h:

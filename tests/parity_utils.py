@@ -14,17 +14,24 @@ def rel_l2(a, b):
 
 
 def make_pair(grid, var_names, vel_names, fp, times, fields, *, strict=False, kernel="auto", with_maps=True,
-              advect=True, relax_timescale=None, mask=None, n_slots=None, backward=False, T_end=None):
-    """(oracle, model) loaded with the same series and initialised from data."""
+              advect=True, relax_timescale=None, mask=None, n_slots=None, backward=False, T_end=None,
+              timestepper="RungeKutta3", chi=0.1):
+    """(oracle, model) loaded with the same series and initialised from data.  `advect`: True / False or a scheme
+    name ("WENO3", "Centered4", "UpwindBiased5", ...); `grid` may be an ImmersedBoundaryGrid."""
     T_end = times[-1] if T_end is None else T_end
+    immersed = cell_heights = None
+    if isinstance(grid, lfb200.ImmersedBoundaryGrid):
+        immersed, cell_heights = grid.immersed_flags(), grid.cell_heights()
     o = lo.Oracle(grid.N, grid.H, grid.topology, grid.spacing, len(var_names), "".join(vel_names), fp,
-                  with_maps, advect, relax_timescale, mask)
+                  with_maps, advect, relax_timescale, mask, timestepper=timestepper, chi=chi, immersed=immersed,
+                  cell_heights=cell_heights)
     o.load_series(times, {k: [np.asarray(a, dtype=np.float64) for a in fields[k]] for k in vel_names},
                   [[np.asarray(a, dtype=np.float64) for a in fields[v]] for v in var_names], times[0], T_end,
                   backward=backward)
     m = LagrangianFilter(grid, var_names_to_filter=var_names, velocity_names=vel_names, filter_params=fp,
                          with_maps=with_maps, advection=advect, n_slots=n_slots or max(2, len(times)),
-                         strict=strict, kernel=kernel, relax_timescale=relax_timescale, mask=mask)
+                         strict=strict, kernel=kernel, relax_timescale=relax_timescale, mask=mask,
+                         timestepper=timestepper, chi=chi)
     for s, t in enumerate(times):
         tt = (T_end - t) if backward else (t - times[0])
         for name in tuple(vel_names) + tuple(var_names):

@@ -166,7 +166,7 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in lfb200.h but not exported"
     assert sorted(_lib.EXPORTS) == declared
     L = _lib.load()
-    assert L.lfb_version() == 100
+    assert L.lfb_version() == 110
     assert ctypes.sizeof(_lib.Desc) == 3 * 12 + 4 + 24 + 12 + 4 + 4 * 64 + 4 * 6 + 4 + 4 + 8 + 32
     # without a GPU creation must fail loudly, never fall back
     import torch
