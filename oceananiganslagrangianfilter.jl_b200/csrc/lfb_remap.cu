@@ -735,38 +735,26 @@ extern "C" int lfb_remap_to_mean(const lfb_remap_desc *D, const double *const *x
         P.origin[q] = D->origin[a]; P.delta[q] = D->spacing[a]; P.L[q] = D->spacing[a] * D->size[a];
         P.stride[q] = st[a];
     }
-    // normalisation extents of the padded cloud (post:527-628) and the largest displacements
-    for (int q = 0; q < 2; ++q) {
-        const int a = ax[q], o = ax[1 - q];
-        double mn = INFINITY, mx = -INFINITY, md = 0;
-        const double lo = P.origin[q], hi = P.origin[q] + P.L[q], pad = D->npad * P.delta[q];
-        for (int j = 0; j < D->size[o]; ++j)
-            for (int i = 0; i < D->size[a]; ++i) {
-                const int64_t idx = (int64_t)(i + D->halo[a]) * st[a] + (int64_t)(j + D->halo[o]) * st[o];
-                const double d = P.has_map[q] ? xi[a][idx] : 0.0;
-                double X = P.origin[q] + P.delta[q] * (i + 0.5) + d;
-                if (fabs(d) / P.delta[q] > md) md = fabs(d) / P.delta[q];
-                if (P.periodic[q] && P.has_map[q]) X -= floor((X - lo) / P.L[q]) * P.L[q];
-                if (X < mn) mn = X;
-                if (X > mx) mx = X;
-                if (P.periodic[q]) {
-                    if (X > hi - pad && X < hi) { if (X - P.L[q] < mn) mn = X - P.L[q]; }
-                    else if (X < lo + pad && X > lo) { if (X + P.L[q] > mx) mx = X + P.L[q]; }
-                }
-            }
-        if (!(md < 1e300)) RFAIL(LFB_ERR_ARG, "non-finite displacement");
-        P.mn[q] = mn; P.rg[q] = mx - mn; P.maxdisp[q] = md; P.pad[q] = pad;
-    }
-    double *d_xi[2] = {nullptr, nullptr}, *d_f = nullptr, *d_out = nullptr, *d_w = nullptr;
+    double *d_xi[2] = {nullptr, nullptr}, *d_f = nullptr, *d_out = nullptr, *d_w = nullptr, *d_part = nullptr;
     int64_t *d_tri = nullptr;
     int *d_flag = nullptr;
     const int64_t nodes = (int64_t)P.n[0] * P.n[1];
-    auto cleanup = [&]() { cudaFree(d_xi[0]); cudaFree(d_xi[1]); cudaFree(d_f); cudaFree(d_out); cudaFree(d_w); cudaFree(d_tri); cudaFree(d_flag); };
+    auto cleanup = [&]() { cudaFree(d_xi[0]); cudaFree(d_xi[1]); cudaFree(d_f); cudaFree(d_out); cudaFree(d_w); cudaFree(d_tri); cudaFree(d_flag); cudaFree(d_part); };
     for (int q = 0; q < 2; ++q)
         if (P.has_map[q]) {
             RCU(cudaMalloc(&d_xi[q], len * sizeof(double)));
-            RCU(cudaMemcpy(d_xi[q], xi[ax[q]], len * sizeof(double), cudaMemcpyDefault));
+            RCU(cudaMemcpy(d_xi[q], xi[ax[q]], len * sizeof(double), cudaMemcpyDefault));      // host or device pointer
         }
+    // normalisation extents of the padded cloud (post:527-628) and the largest displacements, reduced on the device
+    RCU(cudaMalloc(&d_part, 3 * EXT_BLOCKS * sizeof(double)));
+    {
+        const int lo3[3] = {0, 0, 0}, hi3[3] = {D->size[0], D->size[1], D->size[2]};
+        for (int q = 0; q < 2; ++q) {
+            const int ce = cloud_extent(D, d_xi[q], d_part, ax[q], lo3, hi3, st, &P.mn[q], &P.rg[q], &P.maxdisp[q]);
+            if (ce) { cleanup(); RFAIL(ce == -1 ? LFB_ERR_ARG : LFB_ERR_CUDA, ce == -1 ? "non-finite displacement" : "extent kernel failed"); }
+            P.pad[q] = D->npad * P.delta[q];
+        }
+    }
     RCU(cudaMalloc(&d_f, len * sizeof(double)));
     RCU(cudaMalloc(&d_out, len * sizeof(double)));
     RCU(cudaMalloc(&d_w, 3 * nodes * sizeof(double)));

@@ -91,3 +91,64 @@ def exchange_halos_host(local: np.ndarray, H: int, rank: int, world: int, period
     if hi is not None:
         local[:, ny + H:ny + 2 * H, :] = recv_hi.numpy()
     return local
+
+
+# ---------------------------------------------------------------------------------------------- pipeline helpers
+def rank_world(rank=None, world=None):
+    """(rank, world) of this process: the arguments if given, else torch.distributed's when a process group is
+    initialised, else a single rank."""
+    if rank is not None and world is not None:
+        return int(rank), int(world)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def owner_of_time(k: int, world: int) -> int:
+    """Rank that gathers, remaps and holds output time k: the remap is independent per output time (and per
+    variable), so it shards as replicas without a collective."""
+    return k % world
+
+
+class SlabSource:
+    """The input series as rank `rank` sees it: every snapshot cut down to the rank's y-slab (its rows plus Hy halo
+    rows on each side, which hold the neighbours' rows / the periodic images / the global halo)."""
+
+    def __init__(self, source, grid, rank: int, world: int):
+        self.source, self.grid, self.rank, self.world = source, grid, rank, world
+        self.times = source.times
+
+    def has(self, name):
+        return self.source.has(name)
+
+    def snapshot(self, name, n):
+        arr = self.source.snapshot(name, n)
+        if self.world == 1:
+            return arr
+        return slab_of_parent(np.asarray(arr), self.grid, self.rank, self.world, name if name in ("u", "v", "w") else "c")
+
+
+def merge_outputs_on_root(out, rank: int, world: int):
+    """Every rank holds the output times it owns (owner_of_time); rank 0 receives all of them (torch.distributed
+    gather_object, any backend) and returns the complete FilterOutput, the others return theirs unchanged."""
+    import torch.distributed as dist
+    payload = {"times": out.times, "iterations": out.iterations, "fields": out.fields}
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(payload, gathered, dst=0)
+    if rank != 0:
+        return out
+    merged = type(out)([], [])
+    rows = []
+    for part in gathered:
+        for n, (t, it) in enumerate(zip(part["times"], part["iterations"])):
+            rows.append((t, it, {name: series[n] for name, series in part["fields"].items()}))
+    rows.sort(key=lambda r: r[0])
+    merged.times = [r[0] for r in rows]
+    merged.iterations = [r[1] for r in rows]
+    for name in rows[0][2] if rows else ():
+        merged.fields[name] = [r[2][name] for r in rows]
+    return merged

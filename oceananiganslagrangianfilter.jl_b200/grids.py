@@ -257,3 +257,18 @@ class ImmersedBoundaryGrid:
         out = np.full(g.center_shape(), dz, dtype=np.float64, order="F")
         out[g.Hx:g.Hx + g.Nx, g.Hy:g.Hy + g.Ny, g.Hz:g.Hz + g.Nz] = inner
         return np.asfortranarray(self._fill_periodic(out))
+
+    def below_bottom_mask(self) -> np.ndarray:
+        """Boolean parent-shaped array of the cells the reference's `_mask_immersed` blanks before the remap
+        (post:285-298): z_centre < bottom_height (the stored, i.e. capped / grid-fitted, bottom).  For whole cells
+        this is the set of immersed cells; with partial cells it also holds the wet bottom cells whose centre lies
+        below the bottom."""
+        g, ib = self.underlying_grid, self.immersed_boundary
+        if not isinstance(ib, PartialCellBottom):
+            return self.immersed_flags() != 0
+        zb, zf = self._adjusted_bottom()
+        zc = 0.5 * (zf[:-1] + zf[1:])
+        inner = zc[None, None, :] < zb[:, :, None]
+        out = np.zeros(g.center_shape(), dtype=bool, order="F")
+        out[g.Hx:g.Hx + g.Nx, g.Hy:g.Hy + g.Ny, g.Hz:g.Hz + g.Nz] = inner
+        return out

@@ -66,6 +66,7 @@ class LagrangianFilter:
         d.relaxation = int(relax_timescale is not None)
         d.relax_timescale = float(relax_timescale or 0.0)
         self.n_slots = int(n_slots)
+        self.rank, self.nranks = 0, 1
         self._in_flight, self._pinned = [], []
         h = C.c_void_p()
         check(self.L.lfb_create(C.byref(d), C.byref(h)))
@@ -241,10 +242,52 @@ class LagrangianFilter:
                                  float(sign), out.ctypes.data))
         return out
 
+    # ------------------------------------------------------------------ device-resident outputs
+    def output_keep(self, kind: int, field: int, dtype=np.float32) -> int:
+        """Evaluate an output now and keep it on the device (rounded to Float32 like the reference's JLD2Writer when
+        dtype is float32); returns its id."""
+        i = C.c_int32()
+        check(self.L.lfb_output_keep(self.h, kind, field, int(np.dtype(dtype) == np.float32), C.byref(i)))
+        return i.value
+
+    def kept_combine(self, fwd: int, bwd_lo: int, bwd_hi: Optional[int], w_hi: float, sign: float) -> int:
+        i = C.c_int32()
+        check(self.L.lfb_kept_combine(self.h, fwd, bwd_lo, bwd_lo if bwd_hi is None else bwd_hi, float(w_hi), float(sign),
+                                      C.byref(i)))
+        return i.value
+
+    def kept_info(self, kid: int, pointer: bool = False):
+        """(dtype, parent shape[, device pointer]) of a kept output."""
+        f32, ext, ptr = C.c_int32(), (C.c_int32 * 3)(), C.c_void_p()
+        check(self.L.lfb_kept_info(self.h, kid, C.byref(f32), C.byref(ext), C.byref(ptr) if pointer else None))
+        dtype = np.float32 if f32.value else np.float64
+        return (dtype, tuple(ext), ptr.value) if pointer else (dtype, tuple(ext))
+
+    def kept_fetch(self, kid: int) -> np.ndarray:
+        dtype, shape = self.kept_info(kid)
+        out = np.empty(shape, dtype=dtype, order="F")
+        check(self.L.lfb_kept_fetch(self.h, kid, out.ctypes.data))
+        return out
+
+    def kept_release(self, kid: int):
+        check(self.L.lfb_kept_release(self.h, kid))
+
+    def kept_gather(self, kid: int, root: int) -> int:
+        """Collective: the global parent array of a kept output on rank `root` (its id there, -1 elsewhere)."""
+        g = C.c_int32()
+        check(self.L.lfb_kept_gather(self.h, kid, int(root), C.byref(g)))
+        return g.value
+
+    def mem_info(self):
+        f, t = C.c_size_t(), C.c_size_t()
+        check(self.L.lfb_mem_info(self.h, C.byref(f), C.byref(t)))
+        return f.value, t.value
+
     # ------------------------------------------------------------------ multi-GPU
     def comm_init(self, unique_id: bytes, rank: int, nranks: int):
         buf = (C.c_char * 128).from_buffer_copy(unique_id)
         check(self.L.lfb_comm_init(self.h, buf, int(rank), int(nranks)))
+        self.rank, self.nranks = int(rank), int(nranks)
 
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -98,7 +98,7 @@ class SnapshotFeeder:
         if not self.all_resident:
             self.model.wait_transfers()          # bound the number of host arrays kept alive for queued copies
         for name in self.names:
-            arr = self.source.snapshot(name, n)
+            arr = self.source.snapshot(name, n)          # this rank's slab of the snapshot (SlabSource)
             self.model.upload_snapshot(slot, name, arr, self.pass_times[pos], wait=False)
             self.bytes_uploaded += np.asarray(arr).nbytes
         self.slot_of[pos] = slot
@@ -128,32 +128,76 @@ class SnapshotFeeder:
             used.add(slot)
 
 
-def _collect_outputs(model: LagrangianFilter, config: OfflineFilterConfig, dtype) -> Dict[str, np.ndarray]:
-    """create_output_fields (utils:898-1012) evaluated now, with the reference's output names."""
+def _output_specs(model: LagrangianFilter, config: OfflineFilterConfig):
+    """create_output_fields (utils:898-1012): (reference output name, output kind, index) in writer order."""
     ident = "_Eulerian_filtered" if config.advection is None else "_Lagrangian_filtered"
     label = config.label
-    out = {}
-
-    def queue(kind, index):
-        # asynchronous: the copy to the (page-locked) result array overlaps with the following time steps
-        return model.output_async(kind, index, model.pinned_empty(model.center_shape, dtype))
-
-    for q, v in enumerate(config.var_names_to_filter):
-        out[v + label + ident] = queue(_lib.OUT_FILTERED_VAR, q)
+    specs = [(v + label + ident, _lib.OUT_FILTERED_VAR, q) for q, v in enumerate(config.var_names_to_filter)]
     vels = model.velocities_present
     if config.map_to_mean:
-        for m, vel in enumerate(vels):
-            out["xi_" + vel + label] = queue(_lib.OUT_XI, m)
+        specs += [("xi_" + vel + label, _lib.OUT_XI, m) for m, vel in enumerate(vels)]
     if config.compute_mean_velocities:
-        for m, vel in enumerate(vels):
-            out[vel + label + ident] = queue(_lib.OUT_MEAN_VEL, m)
-    return out
+        specs += [(vel + label + ident, _lib.OUT_MEAN_VEL, m) for m, vel in enumerate(vels)]
+    return specs
 
 
-def _run_pass(model, feeder, config, dtype, progress=True):
+class _DeviceStore:
+    """Pass outputs stay on the device as kept arrays (ids): no forward_output / backward_output round trip
+    (the reference writes both files and reads them back, run_offline_lagrangian_filter.jl:77-80, post:45-170)."""
+    on_device = True
+
+    def __init__(self, model, dtype, n_per_time):
+        self.model, self.dtype = model, dtype
+
+    def collect(self, kind, index):
+        return self.model.output_keep(kind, index, self.dtype)
+
+    def finish_pass(self, outputs):
+        return outputs
+
+
+class _HostStore:
+    """Pass outputs are copied to the host through a BOUNDED ring of page-locked buffers (two output times' worth,
+    reused cyclically): the copies overlap with the following time steps, and the pinned footprint does not grow
+    with the number of output times."""
+    on_device = False
+
+    def __init__(self, model, dtype, n_per_time):
+        self.model, self.dtype = model, dtype
+        self.ring = [model.pinned_empty(model.center_shape, dtype) for _ in range(2 * max(1, n_per_time))]
+        self.free = list(range(len(self.ring)))
+        self.pending = []                                   # (holder, ring slot)
+
+    def collect(self, kind, index):
+        if not self.free:
+            self.drain()
+        slot = self.free.pop(0)
+        self.model.output_async(kind, index, self.ring[slot])
+        holder = [None]
+        self.pending.append((holder, slot))
+        return holder
+
+    def drain(self):
+        self.model.wait_transfers()
+        for holder, slot in self.pending:
+            holder[0] = np.array(self.ring[slot], order="F")          # leaves the page-locked staging buffer
+            self.free.append(slot)
+        self.pending = []
+
+    def finish_pass(self, outputs):
+        self.drain()
+        return {t: {k: h[0] for k, h in d.items()} for t, d in outputs.items()}
+
+    def close(self):
+        self.model.free_pinned()
+
+
+def _run_pass(model, feeder, config, store):
     T, Δt, T_out = config.T, config.Δt, config.T_out
+    specs = _output_specs(model, config)
+    collect = lambda: {name: store.collect(kind, index) for name, kind, index in specs}
     feeder.ensure(0.0, 0.0)
-    outputs = {0.0: _collect_outputs(model, config, dtype)}
+    outputs = {0.0: collect()}
     iterations = {0.0: 0}
     for n, step in enumerate(aligned_time_steps(T, Δt, [T_out, T / 10]), 1):
         t = model.time
@@ -162,20 +206,19 @@ def _run_pass(model, feeder, config, dtype, progress=True):
         t = model.time
         if _is_output_time(t, T_out):
             tk = round(t / T_out) * T_out
-            outputs[tk] = _collect_outputs(model, config, dtype)
+            outputs[tk] = collect()
             iterations[tk] = n
     model.wait_transfers()
-    # results leave the page-locked staging arrays, which are released
-    outputs = {t: {k: np.array(v, order="F") for k, v in d.items()} for t, d in outputs.items()}
-    model.free_pinned()
-    return outputs, iterations
+    return store.finish_pass(outputs), iterations
 
 
-def build_model(config: OfflineFilterConfig) -> LagrangianFilter:
+def build_model(config: OfflineFilterConfig, rank: int = 0, world: int = 1) -> LagrangianFilter:
+    """The device model of this rank: the whole grid, or its y-slab (rank r owns rows [r Ny/R, (r+1) Ny/R))."""
+    grid = config.grid.slab(rank, world)
     mask = None
     if config.boundary_relaxation:
-        mask = evaluate_mask(config)
-    return LagrangianFilter(config.grid, var_names_to_filter=config.var_names_to_filter,
+        mask = evaluate_mask(config, grid)
+    return LagrangianFilter(grid, var_names_to_filter=config.var_names_to_filter,
                             velocity_names=config.velocity_names, filter_params=config.filter_params,
                             with_maps=config.map_to_mean or config.compute_mean_velocities,
                             advection=config.advection, n_slots=config.n_slots, device=config.device,
@@ -185,10 +228,10 @@ def build_model(config: OfflineFilterConfig) -> LagrangianFilter:
                             mask=mask, config=config)
 
 
-def evaluate_mask(config) -> np.ndarray:
+def evaluate_mask(config, grid=None) -> np.ndarray:
     """Pre-evaluates `mask_func(x..., mask_params)` at every cell centre, halos included (the reference
     evaluates it inside the forcing closure at the tracer location, utils:592-697)."""
-    g = config.grid
+    g = grid or config.grid
     coords = [g.nodes(ax) for ax in g.nonflat_axes]
     mesh = np.meshgrid(*coords, indexing="ij")
     vals = np.vectorize(lambda *xs: float(config.mask_func(*xs, config.mask_params)))(*mesh)
@@ -198,47 +241,105 @@ def evaluate_mask(config) -> np.ndarray:
     return np.asfortranarray(np.asarray(vals, dtype=np.float64).reshape(shape))
 
 
+def _pick_store(model, config, dtype, n_times, prefer):
+    """Device store when both passes' outputs (plus one output time of combined and gathered FP64 arrays) fit into
+    the free device memory, else the bounded host ring."""
+    specs = _output_specs(model, config)
+    if prefer == "host":
+        return _HostStore
+    n = int(np.prod(model.center_shape))
+    need = 2 * n_times * len(specs) * n * np.dtype(dtype).itemsize + 3 * len(specs) * n * 8 * max(1, model.nranks)
+    free, _ = model.mem_info()
+    if prefer == "device" or need < 0.85 * free:
+        return _DeviceStore
+    if model.nranks > 1:
+        raise MemoryError(f"the pass outputs ({need / 2**30:.1f} GiB) do not fit next to the model on this GPU "
+                          f"({free / 2**30:.1f} GiB free); the multi-GPU pipeline keeps them on the device: use more "
+                          "GPUs or fewer output times")
+    log.info("Pass outputs (%.1f GiB) exceed the free device memory (%.1f GiB): staging them on the host",
+             need / 2**30, free / 2**30)
+    return _HostStore
+
+
 def run_offline_Lagrangian_filter(config: OfflineFilterConfig, output_dtype=np.float32, save: bool = True,
-                                  model: Optional[LagrangianFilter] = None, regrid: bool = True) -> FilterOutput:
-    """Runs the offline Lagrangian filter configured by `config` on the GPU and returns the combined
+                                  model: Optional[LagrangianFilter] = None, regrid: bool = True,
+                                  rank: Optional[int] = None, world: Optional[int] = None,
+                                  output_store: str = "auto", gather_to_root: bool = True) -> FilterOutput:
+    """Runs the offline Lagrangian filter configured by `config` on the GPU(s) and returns the combined
     output (also written to `config.output_filename` unless save=False).
 
     `output_dtype=np.float32` reproduces the reference's JLD2Writer, which rounds every pass output to
-    Float32 before the forward+backward sum; pass np.float64 to keep full precision."""
+    Float32 before the forward+backward sum; pass np.float64 to keep full precision.
+
+    Multi-GPU (one process per GPU, launched with torchrun; `rank` / `world` default to torch.distributed's):
+    every rank owns a y-slab of the grid, both passes run on all ranks (the backward pass starts from the forward
+    pass's final state, run_offline_lagrangian_filter.jl:86-102), the pass outputs stay on the device, are combined
+    there slab by slab, gathered by output time (time k on rank k mod R) and remapped to the mean position on their
+    owner: the remap is sharded by output time.  Rank 0 receives the complete output and
+    writes the file; with gather_to_root=False every rank returns the output times it owns.
+
+    `output_store`: "device" keeps the pass outputs on the device, "host" stages them on the host through a bounded
+    page-locked ring, "auto" picks the device when they fit."""
+    from . import distributed as D
+    rank, world = D.rank_world(rank, world)
     source = config.source()
     file_times = np.asarray(source.times, dtype=np.float64)
     indices = [n for n, t in enumerate(file_times) if config.T_start <= t <= config.T_end]      # utils:124
     if len(indices) < 2:
         raise ValueError("fewer than two snapshots inside [T_start, T_end]")
+    if file_times[indices[0]] != config.T_start or file_times[indices[-1]] != config.T_end:
+        raise ValueError(f"T_start={config.T_start} and T_end={config.T_end} must coincide with snapshot times of the "
+                         f"original data (nearest inside: {file_times[indices[0]]}, {file_times[indices[-1]]}): the "
+                         "filter is initialised from the snapshot at T_start and the backward pass from the one at T_end")
     own_model = model is None
     if own_model:
-        model = build_model(config)
+        model = build_model(config, rank, world)
+        D.init_model_comm(model, rank, world)
         log.info("Created model")
+    elif model.nranks != world:
+        raise ValueError(f"the model passed in belongs to a {model.nranks}-rank communicator, not {world}")
+    store = None
     try:
-        feeder = SnapshotFeeder(model, source, indices, file_times, config.T_start, config.T_end)
+        feeder = SnapshotFeeder(model, D.SlabSource(source, config.grid, rank, world), indices, file_times,
+                                config.T_start, config.T_end)
+        n_times = int(round(config.T / config.T_out)) + 1
+        store = _pick_store(model, config, output_dtype, n_times, output_store)(model, output_dtype,
+                                                                                  len(_output_specs(model, config)))
         # forward pass
         feeder.begin(+1)
         feeder.ensure(0.0, 0.0)
+        if feeder.all_resident:
+            model.wait_transfers()           # the queued uploads are done with the host arrays: let them go
         model.init_from_data()
         log.info("Initialised filtered variables")
-        fwd, iterations = _run_pass(model, feeder, config, output_dtype)
+        fwd, iterations = _run_pass(model, feeder, config, store)
         # backward pass: same snapshots, reversed in time, velocities negated; maps change sign
         feeder.begin(-1)
         model.negate_maps()
         model.reset_clock()
-        bwd, _ = _run_pass(model, feeder, config, output_dtype)
-        out = sum_forward_backward_contributions(config, fwd, bwd, iterations, model=model)
-        if config.output_original_data:
-            out.add_original_data(config, source, indices, file_times)
-        if config.map_to_mean and regrid:
-            regrid_to_mean_position(config, out)
-        if config.compute_Eulerian_filter:
-            compute_Eulerian_filter(config, out)
-        out.stats = {"h2d_bytes": feeder.bytes_uploaded, "kernel_launches": model.kernel_launches,
-                     "kernel": model.kernel_name}
+        bwd, _ = _run_pass(model, feeder, config, store)
+        out = sum_forward_backward_contributions(config, fwd, bwd, iterations, model=model, rank=rank, world=world,
+                                                 regrid=config.map_to_mean and regrid)
+        stats = {"h2d_bytes": feeder.bytes_uploaded, "kernel_launches": model.kernel_launches,
+                 "kernel": model.kernel_name, "output_store": "device" if store.on_device else "host",
+                 "rank": rank, "world": world}
     finally:
+        if store is not None and hasattr(store, "close"):
+            store.close()
         if own_model:
             model.close()
-    if save and config.output_filename:
+    if world > 1 and gather_to_root:
+        out = D.merge_outputs_on_root(out, rank, world)
+        if rank != 0:
+            out.stats = stats
+            return out
+    complete = world == 1 or gather_to_root
+    if complete:
+        if config.output_original_data:
+            out.add_original_data(config, source, indices, file_times)
+        if config.compute_Eulerian_filter:
+            compute_Eulerian_filter(config, out)
+    out.stats = stats
+    if save and config.output_filename and complete:
         out.save(config.output_filename)
     return out

@@ -80,47 +80,106 @@ def _identifier(config) -> str:
     return "_Eulerian_filtered" if getattr(config, "advection", True) is None else "_Lagrangian_filtered"
 
 
-def sum_forward_backward_contributions(config, fwd: Dict[float, Dict[str, np.ndarray]],
-                                       bwd: Dict[float, Dict[str, np.ndarray]], iterations: Dict[float, int],
-                                       model=None) -> FilterOutput:
+def _backward_bracket(btimes: np.ndarray, tb: float):
+    """Index n1 and weight w of the backward series' linear interpolation at pass time tb (post:138-146)."""
+    if tb <= btimes[0]:
+        return 0, 0.0
+    if tb >= btimes[-1]:
+        return len(btimes) - 1, 0.0
+    n1 = int(np.searchsorted(btimes, tb, side="right") - 1)
+    w = 0.0 if btimes[n1] == tb else (tb - btimes[n1]) / (btimes[n1 + 1] - btimes[n1])
+    return n1, w
+
+
+def sum_forward_backward_contributions(config, fwd: Dict[float, Dict[str, object]], bwd: Dict[float, Dict[str, object]],
+                                       iterations: Dict[float, int], model=None, rank: int = 0, world: int = 1,
+                                       regrid: bool = False) -> FilterOutput:
     """out(t_k) = fwd(t_k) + bwd(T - t_k) for filtered variables and maps, fwd - bwd for mean velocities;
     the backward series is interpolated linearly in time (reference post:135-164).  The arithmetic runs
-    on the device (lfb_combine) in FP64 on the (possibly Float32-rounded) pass outputs."""
+    on the device in FP64 on the (possibly Float32-rounded) pass outputs.
+
+    The pass outputs are either host arrays (-> lfb_combine) or ids of arrays kept on the device
+    (-> lfb_kept_combine).  In the second form, which is the only one for world > 1, output time k is then gathered
+    across the y-slabs on rank k mod world, remapped to the mean position there when `regrid` (the remap is
+    sharded by output time) and fetched to the host once; every rank returns the output times it owns."""
     if model is None:
         raise ValueError("sum_forward_backward_contributions needs the device model (lfb_combine); "
                          "there is no CPU path")
+    from .distributed import owner_of_time
     T = config.T
     label = config.label
     ident = _identifier(config)
     mean_vel_names = {vel + label + ident for vel in config.velocity_names} if config.compute_mean_velocities else set()
     ftimes = sorted(fwd.keys())
     btimes = np.array(sorted(bwd.keys()))
-    out = FilterOutput(ftimes, [iterations[t] for t in ftimes])
-    for t in ftimes:
-        tb = T - t
-        if tb <= btimes[0]:
-            n1, w = 0, 0.0
-        elif tb >= btimes[-1]:
-            n1, w = len(btimes) - 1, 0.0
-        else:
-            n1 = int(np.searchsorted(btimes, tb, side="right") - 1)
-            w = 0.0 if btimes[n1] == tb else (tb - btimes[n1]) / (btimes[n1 + 1] - btimes[n1])
-        for name, arr in fwd[t].items():
-            lo = bwd[btimes[n1]][name]
-            hi = bwd[btimes[n1 + 1]][name] if w != 0.0 else None
+    on_device = isinstance(next(iter(fwd[ftimes[0]].values())), (int, np.integer))
+    if world > 1 and not on_device:
+        raise ValueError("the multi-GPU pipeline combines pass outputs kept on the device")
+    mine = [k for k in range(len(ftimes)) if owner_of_time(k, world) == rank]
+    out = FilterOutput([ftimes[k] for k in mine], [iterations[ftimes[k]] for k in mine])
+    if not on_device:
+        for t in ftimes:
+            n1, w = _backward_bracket(btimes, T - t)
+            for name, arr in fwd[t].items():
+                lo = bwd[btimes[n1]][name]
+                hi = bwd[btimes[n1 + 1]][name] if w != 0.0 else None
+                sign = -1.0 if name in mean_vel_names else 1.0
+                out.fields.setdefault(name, []).append(model.combine(arr, lo, hi, w, sign))
+        log.info("Combined forward and backward contributions")
+        if regrid:
+            regrid_to_mean_position(config, out)
+        return out
+
+    # ---- device form ----
+    # which backward outputs are still needed by later forward times (they are released as soon as possible)
+    last_use = {}
+    plan = []
+    for k, t in enumerate(ftimes):
+        n1, w = _backward_bracket(btimes, T - t)
+        plan.append((n1, w))
+        last_use[n1] = k
+        if w != 0.0:
+            last_use[n1 + 1] = k
+    names = list(fwd[ftimes[0]].keys())
+    for nb in range(len(btimes)):                      # backward outputs no forward time refers to
+        if nb not in last_use:
+            for name in names:
+                model.kept_release(bwd[btimes[nb]][name])
+    for k, t in enumerate(ftimes):
+        n1, w = plan[k]
+        owner = owner_of_time(k, world)
+        held = {}
+        for name in names:
             sign = -1.0 if name in mean_vel_names else 1.0
-            out.fields.setdefault(name, []).append(model.combine(arr, lo, hi, w, sign))
+            cid = model.kept_combine(fwd[t][name], bwd[btimes[n1]][name], bwd[btimes[n1 + 1]][name] if w != 0.0 else None,
+                                     w, sign)
+            model.kept_release(fwd[t][name])
+            gid = model.kept_gather(cid, owner)            # collective; with one rank gid == cid
+            if gid != cid:
+                model.kept_release(cid)
+            if owner == rank:
+                held[name] = gid
+        for nb in [n for n, last in last_use.items() if last == k]:
+            for name in names:
+                model.kept_release(bwd[btimes[nb]][name])
+        if owner != rank:
+            continue
+        if regrid:
+            from .remap import remap_kept_to_mean
+            for name, arr in remap_kept_to_mean(config, model, held).items():
+                out.fields.setdefault(name, []).append(arr)
+        for name in names:
+            out.fields.setdefault(name, []).append(model.kept_fetch(held[name]))
+            model.kept_release(held[name])
     log.info("Combined forward and backward contributions")
+    if regrid:
+        log.info("Wrote regridded data to new variables with _at_mean suffix")
     return out
 
 
 # ---------------------------------------------------------------------------------------------- remap
-def regrid_to_mean_position(config, out: FilterOutput, extra_vars_to_regrid: Sequence[str] = ()):
-    """Interpolates every `<var>_Lagrangian_filtered` field from the displaced positions x + xi to the
-    grid nodes (generalised Lagrangian mean position), adding `<name>_at_mean` (reference post:327-762)."""
-    from .remap import remap_to_mean, remap_to_mean_device
-    if getattr(config, "advection", True) is None:
-        raise ValueError("Regridding to mean position is not meaningful for Eulerian filtering")
+def _regrid_names(config, extra_vars_to_regrid: Sequence[str] = ()):
+    """Variables regrid_to_mean_position! remaps (post:340-348)."""
     label = config.label
     names = list(config.var_names_to_filter)
     if config.compute_mean_velocities:
@@ -129,15 +188,39 @@ def regrid_to_mean_position(config, out: FilterOutput, extra_vars_to_regrid: Seq
     for n in extra_vars_to_regrid:
         if n not in names:
             names.append(n)
+    return names
+
+
+def regrid_to_mean_position(config, out: FilterOutput, extra_vars_to_regrid: Sequence[str] = ()):
+    """Interpolates every `<var>_Lagrangian_filtered` field from the displaced positions x + xi to the
+    grid nodes (generalised Lagrangian mean position), adding `<name>_at_mean` (reference post:327-762).
+    Runs on the device (lfb_remap_to_mean); there is no host path."""
+    from .remap import remap_to_mean_device
+    if getattr(config, "advection", True) is None:
+        raise ValueError("Regridding to mean position is not meaningful for Eulerian filtering")
+    label = config.label
+    names = _regrid_names(config, extra_vars_to_regrid)
     g = config.grid
+    if len(g.nonflat_axes) < 2:
+        raise ValueError("regridding to the mean position needs at least two non-Flat axes (the reference's "
+                         "LinearNDInterpolator does not exist in one dimension either)")
     for k in range(len(out.times)):
         xi = {vel: out.fields["xi_" + vel + label][k] for vel in config.velocity_names
               if "xi_" + vel + label in out.fields}
-        remap = remap_to_mean_device if len(g.nonflat_axes) >= 2 else remap_to_mean
-        res = remap({n: out.fields[n][k] for n in names}, xi, g.N, g.H, g.topology, g.origin, g.spacing, npad=config.npad)
+        res = remap_to_mean_device({n: out.fields[n][k] for n in names}, xi, g.N, g.H, g.topology, g.origin, g.spacing,
+                                   npad=config.npad, device=getattr(config, "device", 0),
+                                   immersed=_immersed_mask(g))
         for n in names:
             out.fields.setdefault(n + "_at_mean", []).append(res[n + "_at_mean"])
     log.info("Wrote regridded data to new variables with _at_mean suffix")
+
+
+def _immersed_mask(grid):
+    """Cells _mask_immersed (post:285-298) blanks before the remap: z_centre < bottom_height, halos included."""
+    from .grids import ImmersedBoundaryGrid
+    if not isinstance(grid, ImmersedBoundaryGrid):
+        return None
+    return grid.below_bottom_mask()
 
 
 # ---------------------------------------------------------------------------------------------- Eulerian

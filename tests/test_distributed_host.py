@@ -65,7 +65,23 @@ def _worker(rank, world, port, periodic, q):
         parts = [None] * world
         dist.all_gather_object(parts, want)
         ok_gather = np.array_equal(gather_parent(parts, g), glob) if rank == 0 else True
-        q.put((rank, ok_exchange, ok_uid, ok_gather, g.slab(rank, world).origin[1]))
+        # the pipeline's helpers: rank / world discovery, per-rank view of the input series, output times sharded
+        # over the ranks and merged on rank 0
+        from lfb200.distributed import SlabSource, merge_outputs_on_root, owner_of_time, rank_world
+        ok_rw = rank_world() == (rank, world) and rank_world(0, 1) == (0, 1)
+        src = SlabSource(lfb200.InputData([0.0, 1.0], {"b": [glob, 2 * glob]}), g, rank, world)
+        ok_src = np.array_equal(src.snapshot("b", 1), slab_of_parent(2 * glob, g, rank, world)) and src.has("b")
+        times = [0.0, 1.0, 2.0, 3.0, 4.0]
+        mine = [k for k in range(5) if owner_of_time(k, world) == rank]
+        part = lfb200.FilterOutput([times[k] for k in mine], [10 * k for k in mine])
+        part.fields["f"] = [np.full((2, 2), float(k)) for k in mine]
+        merged = merge_outputs_on_root(part, rank, world)
+        if rank == 0:
+            ok_merge = (merged.times == times and merged.iterations == [0, 10, 20, 30, 40] and
+                        [a[0, 0] for a in merged.fields["f"]] == [0.0, 1.0, 2.0, 3.0, 4.0])
+        else:
+            ok_merge = merged is part
+        q.put((rank, ok_exchange, ok_uid, ok_gather and ok_rw and ok_src and ok_merge, g.slab(rank, world).origin[1]))
     finally:
         dist.destroy_process_group()
 

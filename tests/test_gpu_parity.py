@@ -454,6 +454,55 @@ def test_multi_gpu_slabs_match_single_gpu():
     assert "MISMATCH" not in r.stdout
 
 
+def test_multi_gpu_pipeline_matches_single_gpu():
+    """The whole offline pipeline through the public API on 2 ranks (tests/mgpu_pipeline_check.py under torchrun):
+    slab passes, device-side combination, gather by output time, remap sharded by output time."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29518", "tests/mgpu_pipeline_check.py"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MISMATCH" not in r.stdout
+
+
+@pytest.mark.parametrize("size,topology", [((10, 10), ("Periodic", "Flat", "Bounded")),
+                                           ((24, 12, 10), ("Periodic", "Periodic", "Bounded"))])
+def test_device_and_host_output_stores_agree(size, topology):
+    """run_offline_Lagrangian_filter with the pass outputs kept on the device (combined there, handed to the remap as
+    device pointers) and with the bounded page-locked host ring: the same bits, `_at_mean` fields included."""
+    g = lfb200.RectilinearGrid(size=size, extent=tuple(float(s) for s in size), topology=topology)
+    vel_names = ("u", "w") if topology[1] == "Flat" else ("u", "v", "w")
+    times = [0.0, 0.5, 1.0, 1.5, 2.0]
+    fields = make_series(g, times, var_names=("b",), velocity_names=vel_names, T_period=4.0, amplitude=0.5)
+    data = lfb200.InputData(times, {k: [np.asarray(a, dtype=np.float32) for a in v] for k, v in fields.items()})
+    outs = {}
+    for store in ("device", "host"):
+        cfg = lfb200.OfflineFilterConfig(data=data, grid=g, var_names_to_filter=("b",), velocity_names=vel_names, N=2,
+                                         freq_c=2 * np.pi / 2.0, dt=0.1, T_out=0.5, n_slots=5, npad=3)
+        outs[store] = lfb200.run_offline_Lagrangian_filter(cfg, save=False, output_store=store)
+        assert outs[store].stats["output_store"] == store
+    a, b = outs["device"], outs["host"]
+    assert a.times == b.times and a.iterations == b.iterations and set(a.keys()) == set(b.keys())
+    assert any(k.endswith("_at_mean") for k in a.keys())
+    for name in a.keys():
+        for x, y in zip(a[name], b[name]):
+            assert x.dtype == y.dtype and np.array_equal(x, y, equal_nan=True), name
+
+
+def test_t_start_must_sit_on_a_snapshot(golden_sim):
+    g = golden_grid()
+    times, fields = golden_series(golden_sim)
+    data = lfb200.InputData(times, fields)
+    cfg = lfb200.OfflineFilterConfig(data=data, grid=g, var_names_to_filter=("b",), velocity_names=("u", "w"), N=2,
+                                     freq_c=1e-4, T_start=times[0] + 1.0, T_end=times[-1])
+    with pytest.raises(ValueError, match="coincide with snapshot times"):
+        lfb200.run_offline_Lagrangian_filter(cfg, save=False)
+
+
 # ---------------------------------------------------------------------------------------------- BASELINE configs
 EXAMPLE_SHAPES = [
     # BASELINE.json configs[0]: examples/offline_filter_geostrophic_adjustment.jl (400x1x80, P/F/B, u,w,v, N=2)
