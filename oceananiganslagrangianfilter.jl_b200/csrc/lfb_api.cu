@@ -584,8 +584,15 @@ static int fill_all_halos(lfb_handle *h, double *base, int n_fields)
 {
     for (int ax = 0; ax < 3; ++ax) {
         if (h->L.topo[ax] == LFB_FLAT || h->L.H[ax] == 0) continue;
-        if (ax == 1 && h->nranks > 1) continue;
-        CU(lfb_launch_fill_halo_axis(base, h->L.len, n_fields, &h->L, ax, h->L.topo[ax] == LFB_PERIODIC ? 0 : 1, h->compute));
+        int mode = h->L.topo[ax] == LFB_PERIODIC ? 0 : 1;
+        if (ax == 1 && h->nranks > 1) {
+            // y halos come from the neighbour ranks (exchange_y); only the outer edges of a Bounded axis are mirrored here
+            if (h->L.topo[1] != LFB_BOUNDED) continue;
+            if (h->rank == 0) mode = 2;
+            else if (h->rank == h->nranks - 1) mode = 3;
+            else continue;
+        }
+        CU(lfb_launch_fill_halo_axis(base, h->L.len, n_fields, &h->L, ax, mode, h->compute));
         h->launches++;
     }
     return LFB_OK;

@@ -202,7 +202,8 @@ extern "C" cudaError_t lfb_launch_interp_inputs(const LfbInterpParams *P, cudaSt
 // update_lagrangian_filter_state.jl:33-34).  Runs over the full parent extent of
 // the two other axes, like Oceananigans' fill kernels.
 //   mode 0: periodic copy of H cells from the opposite side
-//   mode 1: zero-flux mirror of the first halo cell only
+//   mode 1: zero-flux mirror of the first halo cell only (mode 2 / 3: only on the low / high side -- the outer edge
+//           of the first / last y-slab of a decomposed Bounded axis)
 // n_ax is the interior extent along the axis (N, or N+1 for Face fields on Bounded axes).
 // ------------------------------------------------------------------------------------------------
 __global__ void lfb_fill_halo_axis(double *base, int64_t field_stride, LfbLayout L, int ax, int mode, int n_ax)
@@ -227,12 +228,16 @@ __global__ void lfb_fill_halo_axis(double *base, int64_t field_stride, LfbLayout
             f[dr] = f[sr];
         }
     } else {
-        c[ax] = -1;       int64_t dl = L.at(c[0], c[1], c[2]);
-        c[ax] = 0;        int64_t sl = L.at(c[0], c[1], c[2]);
-        f[dl] = f[sl];
-        c[ax] = n_ax;     int64_t dr = L.at(c[0], c[1], c[2]);
-        c[ax] = n_ax - 1; int64_t sr = L.at(c[0], c[1], c[2]);
-        f[dr] = f[sr];
+        if (mode != 3) {
+            c[ax] = -1;       int64_t dl = L.at(c[0], c[1], c[2]);
+            c[ax] = 0;        int64_t sl = L.at(c[0], c[1], c[2]);
+            f[dl] = f[sl];
+        }
+        if (mode != 2) {
+            c[ax] = n_ax;     int64_t dr = L.at(c[0], c[1], c[2]);
+            c[ax] = n_ax - 1; int64_t sr = L.at(c[0], c[1], c[2]);
+            f[dr] = f[sr];
+        }
     }
 }
 

@@ -39,7 +39,7 @@ def run_cases(rank, world, local, cases=None):
                                          kernel=kernel, n_slots=5, npad=3)
         out = lfb200.run_offline_Lagrangian_filter(cfg, save=False)          # collective: all ranks, y-slabs
         flag = torch.zeros(1, device="cuda")
-        worst, kname = 0.0, out.stats["kernel"]
+        worst, kname, worst_name = 0.0, out.stats["kernel"], ""
         if rank == 0:
             ref = lfb200.run_offline_Lagrangian_filter(cfg, save=False, rank=0, world=1)
             good = out.times == ref.times and out.iterations == ref.iterations and set(out.keys()) == set(ref.keys())
@@ -49,7 +49,8 @@ def run_cases(rank, world, local, cases=None):
                         break
                     if strict:
                         same = np.array_equal(a, b, equal_nan=True)
-                        worst = max(worst, 0.0 if same else float(np.nanmax(np.abs(a - b))))
+                        if not same and float(np.nanmax(np.abs(a - b))) >= worst:
+                            worst, worst_name = float(np.nanmax(np.abs(a - b))), name
                         good = good and same
                     else:
                         m = np.isfinite(b)
@@ -64,7 +65,7 @@ def run_cases(rank, world, local, cases=None):
         dist.all_reduce(flag)
         ok = ok and flag.item() == 0
         lines.append(f"mgpu_pipeline world={world} y={topo_y} kernel={kname} fields={len(out.keys())} "
-                     f"times={len(out.times)}: worst={worst:.3e} {'OK' if flag.item() == 0 else 'MISMATCH'}")
+                     f"times={len(out.times)}: worst={worst:.3e} {worst_name} {'OK' if flag.item() == 0 else 'MISMATCH'}")
     return ok, lines
 
 
