@@ -10,8 +10,9 @@ velocities (u, v, w) => 10 tracers (BASELINE.json configs[4], SURVEY.md section 
 stage: strong scaling, `value` = whole-job cell-updates / max-over-ranks device time.
 
   value      stepping only, inputs resident in HBM, CUDA events on the library's compute stream
-  e2e        the same metric through the host API with HOST buffers: snapshot uploads from pinned host
-             memory (Float32, as on disk), steps, and the Float32 output download every output time
+  e2e        the same metric through the public API, run_offline_Lagrangian_filter(config), with HOST buffers:
+             Float32 snapshot uploads from pinned host memory, forward + backward pass, device-side combination,
+             combined Float64 fields fetched to pinned host memory
   roofline   dominant kernel (the fused stage kernel): algorithmic bytes / mean launch duration vs the
              measured HBM peak in MEASURED_PEAKS.json
   cpu_baseline / --impl reference: the CPU restatement of the reference numerics (oracle/) on a bounded
@@ -233,6 +234,16 @@ def main():
             dist.barrier()
         m.sync()
 
+    # multi-GPU correctness the driver can see: the whole pipeline on small grids, slabs vs one GPU (bit-exact with the
+    # strict kernel, <= 1e-12 with the TMA kernel), before anything is timed
+    mgpu_parity = None
+    if world > 1:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from mgpu_pipeline_check import run_cases
+        ok, lines = run_cases(rank, world, local, cases=(("Periodic", "generic", True, (24, 8 * world, 10), True),
+                                                          ("Periodic", "auto", False, (40, 16 * world, 16), False)))
+        mgpu_parity = {"ok": bool(ok), "cases": lines}
+
     cells_global = args.size[0] * args.size[1] * args.size[2]
     cells_local = g.Nx * g.Ny * g.Nz
     K, W = args.steps, args.warmup
@@ -263,59 +274,67 @@ def main():
     ms_max = float(t_ms.item())
     value = cells_global * N_TRACERS * K / (ms_max * 1e-3)
 
-    # ---- e2e: host buffers, uploads and output downloads inside the timed region --------------------
+    # ---- e2e: the whole offline pipeline through the public API, host buffers inside the timed region --------
+    # run_offline_Lagrangian_filter(config): Float32 snapshots uploaded from page-locked host memory, forward pass,
+    # backward pass (both with their per-output-time outputs kept on the device), device-side combination, and the
+    # combined Float64 fields fetched into page-locked host arrays (every rank its y-slab).  The remap to the mean
+    # position is post-processing and is timed separately (--remap).
     e2e = None
     if not args.no_e2e:
-        m.reset_clock()
-        m.init_from_data()
-        for s in range(n_slots):
-            m.invalidate_slot(s)
-        barrier()
-        # page-locked output ring: two output times' worth of fields, reused cyclically (a consumer would
-        # write them to disk); allocated outside the timed region like any long-lived I/O buffer
+        from lfb200.offline import aligned_time_steps, run_offline_Lagrangian_filter
+
+        class HostSeries:
+            """The synthetic series as this rank's input source: slab parent arrays in page-locked host memory."""
+            def __init__(self):
+                self.times = np.asarray(times)
+
+            def has(self, name):
+                return name in names
+
+            def snapshot(self, name, n):
+                return host[(name, n)]
+
+        src = HostSeries()
+        cfg = lfb200.OfflineFilterConfig(data=src, grid=gglobal, var_names_to_filter=VAR_NAMES, velocity_names=VEL_NAMES,
+                                         filter_params=fp, dt=DT, T_out=T_S, device=local, n_slots=n_slots,
+                                         kernel=args.kernel, output_original_data=False)
+        n_pipe_steps = 2 * len(aligned_time_steps(cfg.T, cfg.dt, [cfg.T_out, cfg.T / 10]))
         n_out = len(VAR_NAMES) + 2 * len(VEL_NAMES)
-        ring = [m.pinned_empty(m.center_shape, np.float32) for _ in range(2 * n_out)]
-        ring_pos = 0
+        n_times = int(round(cfg.T / cfg.T_out)) + 1
+
+        class PinnedPool:
+            """Destination arrays of the combined outputs, allocated before the timed region like any long-lived
+            I/O buffer (a consumer would write them to disk)."""
+            def __init__(self, count, shape, dtype):
+                self.arrays = [m.pinned_empty(shape, dtype) for _ in range(count)]
+                self.next, self.bytes = 0, 0
+
+            def __call__(self, shape, dtype):
+                a = self.arrays[self.next]
+                self.next += 1
+                self.bytes += a.nbytes
+                return a
+
+        pool = PinnedPool(n_out * n_times, m.center_shape, np.float64)
         barrier()
         t0 = time.perf_counter()
-        h2d = d2h = 0
-
-        def upload_async(slot, s):
-            nbytes = 0
-            for name in names:
-                m.upload_snapshot(slot, name, host[(name, s)], times[s], wait=False)
-                nbytes += host[(name, s)].nbytes
-            return nbytes
-
-        h2d += upload_async(0, 0)
-        h2d += upload_async(1, 1)
-        next_snap = 2
-        steps_per_snap = int(round(T_S / DT))
-        for n in range(K):
-            if next_snap < N_SNAP and n * DT >= times[next_snap - 2]:
-                h2d += upload_async(next_snap % n_slots, next_snap)       # one snapshot ahead: overlaps with the steps
-                next_snap += 1
-            m.step(DT)
-            if (n + 1) % steps_per_snap == 0 or n == K - 1:          # output time (T_out = T_s) / end of run
-                if ring_pos + n_out > len(ring):
-                    m.wait_transfers()
-                    ring_pos = 0
-                for q in range(len(VAR_NAMES)):
-                    d2h += m.output_async(_lib.OUT_FILTERED_VAR, q, ring[ring_pos]).nbytes; ring_pos += 1
-                for mi in range(len(VEL_NAMES)):
-                    d2h += m.output_async(_lib.OUT_XI, mi, ring[ring_pos]).nbytes; ring_pos += 1
-                    d2h += m.output_async(_lib.OUT_MEAN_VEL, mi, ring[ring_pos]).nbytes; ring_pos += 1
-        m.wait_transfers()
+        out = run_offline_Lagrangian_filter(cfg, save=False, regrid=False, model=m, rank=rank, world=world,
+                                            output_store="device", gather_to_root=False, local_source=src, alloc=pool)
         barrier()
         wall = time.perf_counter() - t0
+        assert len(out.times) == n_times and out.stats["output_store"] == "device"
         t_w = torch.tensor([wall], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t_w, op=dist.ReduceOp.MAX)
-        e2e = {"value": cells_global * N_TRACERS * K / float(t_w.item()), "unit": UNIT,
-               "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
-               "note": "asynchronous Float32 snapshot uploads from pinned host memory + Float32 output downloads into "
-                       "pinned host memory every T_out (lfb_upload_snapshot_async / lfb_output_async), wall clock "
-                       "between device syncs, max over ranks"}
+        e2e = {"value": cells_global * N_TRACERS * n_pipe_steps / float(t_w.item()), "unit": UNIT,
+               "h2d_bytes_per_step": out.stats["h2d_bytes"] / n_pipe_steps, "d2h_bytes_per_step": pool.bytes / n_pipe_steps,
+               "steps": n_pipe_steps, "wall_s": float(t_w.item()), "phases_rank0": out.stats["phases"],
+               "note": "run_offline_Lagrangian_filter(config) on host buffers: Float32 snapshot uploads from page-locked host "
+                       "memory, forward + backward pass with aligned time steps (outputs every T_out kept on the device), "
+                       "device-side forward+backward combination, combined Float64 fields fetched to page-locked host "
+                       "arrays (per rank: its y-slab); wall clock between device syncs, max over ranks; the remap to the "
+                       "mean position is not included"}
+        del out
 
     if rank == 0:
         peaks = {}
@@ -355,6 +374,8 @@ def main():
                 "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu}
+        if mgpu_parity is not None:
+            line["mgpu_parity"] = mgpu_parity
         print(json.dumps(line), flush=True)
     m.close()
     if world > 1:

@@ -218,9 +218,15 @@ int lfb_output_keep(lfb_handle *h, int kind, int field, int is_f32, int *id);
 int lfb_kept_combine(lfb_handle *h, int fwd, int bwd_lo, int bwd_hi, double w_hi, double sign, int *id);
 /* copy a kept array to the host in its own precision (parent layout) */
 int lfb_kept_fetch(lfb_handle *h, int id, void *parent);
+/* asynchronous form: the copy runs on the download stream behind the work that produces the array; `parent` may be
+ * read after lfb_wait_transfers() (page-locked memory for a real overlap); lfb_kept_release waits for it */
+int lfb_kept_fetch_async(lfb_handle *h, int id, void *parent);
 /* precision, parent extents and raw device pointer of a kept array (any of the outputs may be NULL) */
 int lfb_kept_info(lfb_handle *h, int id, int *is_f32, int *extents3, void **device_ptr);
+/* released arrays go to a per-handle pool and are reused by later kept outputs of the same size (no cudaFree, hence
+ * no device synchronisation, between time steps); lfb_kept_trim returns the pooled memory to the device */
 int lfb_kept_release(lfb_handle *h, int id);
+int lfb_kept_trim(lfb_handle *h);
 /* COLLECTIVE over the communicator of lfb_comm_init: assemble the GLOBAL parent array of a kept output on rank
  * `root` from every rank's y-slab (interior rows from their owners, outer halo rows from the first / last rank).
  * *gid is the new kept id on `root`, -1 elsewhere; with one rank *gid = id. */

@@ -130,8 +130,12 @@ struct lfb_handle {
     double    *send_lo, *send_hi, *recv_lo, *recv_hi;
     size_t     halo_elems;
     // device-resident outputs (lfb_output_keep ...): dense parent arrays
-    struct Kept { void *p; int is_f32; int e[3]; };
+    struct Kept { void *p; int is_f32; int e[3]; cudaEvent_t fetched; };   // fetched: a pending asynchronous fetch
     std::vector<Kept> kept;
+    // released kept arrays, reused by size: cudaMalloc / cudaFree of GB-sized blocks cost milliseconds and cudaFree
+    // synchronises the device, which would stall the queue of time steps at every output time
+    struct Pooled { void *p; size_t bytes; cudaEvent_t fetched; };
+    std::vector<Pooled> kept_pool;
 };
 
 static inline int field_present(const lfb_handle *h, int field_id)
@@ -372,7 +376,8 @@ extern "C" int lfb_destroy(lfb_handle *h)
     for (int f = 0; f < 3; ++f) if (h->vin_alt[f]) cudaFree(h->vin_alt[f]);
     if (h->staging) cudaFree(h->staging);
     for (void *p : h->export_ring) if (p) cudaFree(p);
-    for (auto &k : h->kept) if (k.p) cudaFree(k.p);
+    for (auto &k : h->kept) { if (k.p) cudaFree(k.p); if (k.fetched) cudaEventDestroy(k.fetched); }
+    for (auto &k : h->kept_pool) { if (k.p) cudaFree(k.p); if (k.fetched) cudaEventDestroy(k.fetched); }
     for (cudaEvent_t e : h->ev_export) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_fetched) if (e) cudaEventDestroy(e);
     for (cudaStream_t st : {h->compute, h->copy, h->d2h}) if (st) cudaStreamDestroy(st);
@@ -1150,14 +1155,35 @@ extern "C" int lfb_combine(lfb_handle *h, int64_t n, const double *fwd, const do
 static int kept_new(lfb_handle *h, int is_f32, const int e[3], int *id)
 {
     const size_t n = (size_t)e[0] * e[1] * e[2];
+    const size_t bytes = n * (is_f32 ? sizeof(float) : sizeof(double));
     void *p = nullptr;
-    cudaError_t err = cudaMalloc(&p, n * (is_f32 ? sizeof(float) : sizeof(double)));
-    if (err != cudaSuccess) {
-        cudaGetLastError();
-        return fail(LFB_ERR_CUDA, "device memory exhausted while keeping an output (%s); use the host path", cudaGetErrorString(err));
+    for (size_t q = 0; q < h->kept_pool.size() && !p; ++q)
+        if (h->kept_pool[q].bytes == bytes) {
+            // stream order protects the readers queued on the compute stream; a download still in flight on the d2h
+            // stream is waited for by the compute stream, not by the host
+            if (h->kept_pool[q].fetched) {
+                CU(cudaStreamWaitEvent(h->compute, h->kept_pool[q].fetched, 0));
+                cudaEventDestroy(h->kept_pool[q].fetched);
+            }
+            p = h->kept_pool[q].p;
+            h->kept_pool.erase(h->kept_pool.begin() + q);
+        }
+    if (!p) {
+        cudaError_t err = cudaMalloc(&p, bytes);
+        if (err != cudaSuccess && !h->kept_pool.empty()) {          // give the pooled blocks back and retry
+            cudaGetLastError();
+            cudaDeviceSynchronize();
+            for (auto &k : h->kept_pool) { cudaFree(k.p); if (k.fetched) cudaEventDestroy(k.fetched); }
+            h->kept_pool.clear();
+            err = cudaMalloc(&p, bytes);
+        }
+        if (err != cudaSuccess) {
+            cudaGetLastError();
+            return fail(LFB_ERR_CUDA, "device memory exhausted while keeping an output (%s); use the host path", cudaGetErrorString(err));
+        }
     }
     lfb_handle::Kept k;
-    k.p = p; k.is_f32 = is_f32; k.e[0] = e[0]; k.e[1] = e[1]; k.e[2] = e[2];
+    k.p = p; k.is_f32 = is_f32; k.e[0] = e[0]; k.e[1] = e[1]; k.e[2] = e[2]; k.fetched = nullptr;
     for (size_t q = 0; q < h->kept.size(); ++q)
         if (!h->kept[q].p) { h->kept[q] = k; *id = (int)q; return LFB_OK; }
     h->kept.push_back(k);
@@ -1214,6 +1240,23 @@ extern "C" int lfb_kept_fetch(lfb_handle *h, int id, void *parent)
     return LFB_OK;
 }
 
+// Asynchronous fetch: queued behind what produces the array, copied on the download stream so that the host can keep
+// queuing time steps; `parent` may be read after lfb_wait_transfers() (page-locked memory for a real overlap).
+// lfb_kept_release waits for a pending fetch of the array it frees.
+extern "C" int lfb_kept_fetch_async(lfb_handle *h, int id, void *parent)
+{
+    lfb_handle::Kept *k = kept_get(h, id);
+    if (!k || !parent) return fail(LFB_ERR_ARG, "unknown kept output id / null pointer");
+    CU(cudaSetDevice(h->device));
+    const size_t n = (size_t)k->e[0] * k->e[1] * k->e[2];
+    if (!k->fetched) CU(cudaEventCreateWithFlags(&k->fetched, cudaEventDisableTiming));
+    CU(cudaEventRecord(h->ev_tmp, h->compute));
+    CU(cudaStreamWaitEvent(h->d2h, h->ev_tmp, 0));
+    CU(cudaMemcpyAsync(parent, k->p, n * (k->is_f32 ? sizeof(float) : sizeof(double)), cudaMemcpyDeviceToHost, h->d2h));
+    CU(cudaEventRecord(k->fetched, h->d2h));
+    return LFB_OK;
+}
+
 extern "C" int lfb_kept_info(lfb_handle *h, int id, int *is_f32, int *extents3, void **device_ptr)
 {
     lfb_handle::Kept *k = kept_get(h, id);
@@ -1233,10 +1276,23 @@ extern "C" int lfb_kept_release(lfb_handle *h, int id)
 {
     lfb_handle::Kept *k = kept_get(h, id);
     if (!k) return fail(LFB_ERR_ARG, "unknown kept output id");
+    // no host synchronisation: the block goes to the pool together with the event of a download that may still be
+    // in flight (see kept_new)
+    lfb_handle::Pooled pl;
+    pl.p = k->p; pl.bytes = (size_t)k->e[0] * k->e[1] * k->e[2] * (k->is_f32 ? sizeof(float) : sizeof(double)); pl.fetched = k->fetched;
+    h->kept_pool.push_back(pl);
+    k->p = nullptr; k->fetched = nullptr;
+    return LFB_OK;
+}
+
+extern "C" int lfb_kept_trim(lfb_handle *h)
+{
+    if (!h) return fail(LFB_ERR_ARG, "null handle");
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->compute));
-    cudaFree(k->p);
-    k->p = nullptr;
+    CU(cudaStreamSynchronize(h->d2h));
+    for (auto &k : h->kept_pool) { cudaFree(k.p); if (k.fetched) cudaEventDestroy(k.fetched); }
+    h->kept_pool.clear();
     return LFB_OK;
 }
 

@@ -132,16 +132,23 @@ class SlabSource:
         return slab_of_parent(np.asarray(arr), self.grid, self.rank, self.world, name if name in ("u", "v", "w") else "c")
 
 
-def merge_outputs_on_root(out, rank: int, world: int):
-    """Every rank holds the output times it owns (owner_of_time); rank 0 receives all of them (torch.distributed
-    gather_object, any backend) and returns the complete FilterOutput, the others return theirs unchanged."""
+def merge_outputs_on_root(out, rank: int, world: int, grid=None):
+    """Every rank holds the output times it owns (owner_of_time) as global arrays, or its y-slab of every output time
+    (`out.slab`); rank 0 receives all of them (torch.distributed gather_object, any backend) and returns the complete
+    FilterOutput, the others return theirs unchanged."""
     import torch.distributed as dist
-    payload = {"times": out.times, "iterations": out.iterations, "fields": out.fields}
+    payload = {"times": out.times, "iterations": out.iterations, "fields": out.fields, "slab": out.slab}
     gathered = [None] * world if rank == 0 else None
     dist.gather_object(payload, gathered, dst=0)
     if rank != 0:
         return out
     merged = type(out)([], [])
+    if gathered[0]["slab"] is not None:
+        merged.times, merged.iterations = list(gathered[0]["times"]), list(gathered[0]["iterations"])
+        for name in gathered[0]["fields"]:
+            merged.fields[name] = [gather_parent([part["fields"][name][n] for part in gathered], grid)
+                                   for n in range(len(merged.times))]
+        return merged
     rows = []
     for part in gathered:
         for n, (t, it) in enumerate(zip(part["times"], part["iterations"])):

@@ -88,11 +88,16 @@ class LagrangianFilter:
             check(self.L.lfb_set_immersed(self.h, flags.ctypes.data, hp.ctypes.data if hp is not None else None))
 
     # ------------------------------------------------------------------ lifecycle
-    def free_pinned(self):
-        """Releases every page-locked array handed out by pinned_empty (they must not be used afterwards)."""
-        for p in self._pinned:
+    def free_pinned(self, since: int = 0):
+        """Releases the page-locked arrays handed out by pinned_empty (they must not be used afterwards): all of
+        them, or those allocated after the first `since` ones."""
+        for p in self._pinned[since:]:
             self.L.lfb_host_free(p)
-        self._pinned = []
+        self._pinned = self._pinned[:since]
+
+    @property
+    def n_pinned(self) -> int:
+        return len(self._pinned)
 
     def close(self):
         if getattr(self, "h", None):
@@ -263,14 +268,26 @@ class LagrangianFilter:
         dtype = np.float32 if f32.value else np.float64
         return (dtype, tuple(ext), ptr.value) if pointer else (dtype, tuple(ext))
 
-    def kept_fetch(self, kid: int) -> np.ndarray:
+    def kept_fetch(self, kid: int, alloc=None, wait: bool = True) -> np.ndarray:
+        """Host copy of a kept output; `alloc(shape, dtype)` supplies the (Fortran-ordered) destination array.  With
+        wait=False the copy is only queued (download stream): the array is valid after wait_transfers()."""
         dtype, shape = self.kept_info(kid)
-        out = np.empty(shape, dtype=dtype, order="F")
-        check(self.L.lfb_kept_fetch(self.h, kid, out.ctypes.data))
+        out = np.empty(shape, dtype=dtype, order="F") if alloc is None else alloc(shape, dtype)
+        if out.shape != shape or out.dtype != dtype or not out.flags.f_contiguous:
+            raise ValueError("alloc must return a Fortran-ordered array of the requested shape and dtype")
+        if wait:
+            check(self.L.lfb_kept_fetch(self.h, kid, out.ctypes.data))
+        else:
+            self._in_flight.append(out)
+            check(self.L.lfb_kept_fetch_async(self.h, kid, out.ctypes.data))
         return out
 
     def kept_release(self, kid: int):
         check(self.L.lfb_kept_release(self.h, kid))
+
+    def kept_trim(self):
+        """Return the memory of released kept outputs (pooled for reuse) to the device."""
+        check(self.L.lfb_kept_trim(self.h))
 
     def kept_gather(self, kid: int, root: int) -> int:
         """Collective: the global parent array of a kept output on rank `root` (its id there, -1 elsewhere)."""

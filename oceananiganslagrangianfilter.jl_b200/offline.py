@@ -29,7 +29,7 @@ import numpy as np
 from . import _lib
 from .config import OfflineFilterConfig
 from .model import LagrangianFilter
-from .post import (FilterOutput, compute_Eulerian_filter, regrid_to_mean_position,
+from .post import (FilterOutput, ForwardBackwardCombiner, compute_Eulerian_filter, regrid_to_mean_position,
                    sum_forward_backward_contributions)
 
 log = logging.getLogger("lfb200")
@@ -164,6 +164,7 @@ class _HostStore:
 
     def __init__(self, model, dtype, n_per_time):
         self.model, self.dtype = model, dtype
+        self.mark = model.n_pinned                           # buffers allocated before this store are not ours
         self.ring = [model.pinned_empty(model.center_shape, dtype) for _ in range(2 * max(1, n_per_time))]
         self.free = list(range(len(self.ring)))
         self.pending = []                                   # (holder, ring slot)
@@ -189,13 +190,21 @@ class _HostStore:
         return {t: {k: h[0] for k, h in d.items()} for t, d in outputs.items()}
 
     def close(self):
-        self.model.free_pinned()
+        self.model.free_pinned(since=self.mark)
 
 
-def _run_pass(model, feeder, config, store):
+def _run_pass(model, feeder, config, store, on_output=None):
+    """One pass of the filter simulation (run!(simulation), run_offline_lagrangian_filter.jl:83,102): aligned time
+    steps, outputs every T_out.  `on_output(t, outputs)` sees every output time as soon as it is queued."""
     T, Δt, T_out = config.T, config.Δt, config.T_out
     specs = _output_specs(model, config)
-    collect = lambda: {name: store.collect(kind, index) for name, kind, index in specs}
+
+    def collect(tk=0.0):
+        d = {name: store.collect(kind, index) for name, kind, index in specs}
+        if on_output is not None:
+            on_output(tk, d)
+        return d
+
     feeder.ensure(0.0, 0.0)
     outputs = {0.0: collect()}
     iterations = {0.0: 0}
@@ -206,9 +215,10 @@ def _run_pass(model, feeder, config, store):
         t = model.time
         if _is_output_time(t, T_out):
             tk = round(t / T_out) * T_out
-            outputs[tk] = collect()
+            outputs[tk] = collect(tk)
             iterations[tk] = n
-    model.wait_transfers()
+    if on_output is None:
+        model.wait_transfers()
     return store.finish_pass(outputs), iterations
 
 
@@ -264,7 +274,8 @@ def _pick_store(model, config, dtype, n_times, prefer):
 def run_offline_Lagrangian_filter(config: OfflineFilterConfig, output_dtype=np.float32, save: bool = True,
                                   model: Optional[LagrangianFilter] = None, regrid: bool = True,
                                   rank: Optional[int] = None, world: Optional[int] = None,
-                                  output_store: str = "auto", gather_to_root: bool = True) -> FilterOutput:
+                                  output_store: str = "auto", gather_to_root: bool = True, local_source=None,
+                                  alloc=None) -> FilterOutput:
     """Runs the offline Lagrangian filter configured by `config` on the GPU(s) and returns the combined
     output (also written to `config.output_filename` unless save=False).
 
@@ -279,7 +290,9 @@ def run_offline_Lagrangian_filter(config: OfflineFilterConfig, output_dtype=np.f
     writes the file; with gather_to_root=False every rank returns the output times it owns.
 
     `output_store`: "device" keeps the pass outputs on the device, "host" stages them on the host through a bounded
-    page-locked ring, "auto" picks the device when they fit."""
+    page-locked ring, "auto" picks the device when they fit.  `local_source`: an input source that already yields this
+    rank's y-slab of every snapshot (instead of cutting it out of the global arrays of `config`'s source).
+    `alloc(shape, dtype)`: allocator of the host arrays the combined outputs are fetched into (device store)."""
     from . import distributed as D
     rank, world = D.rank_world(rank, world)
     source = config.source()
@@ -300,27 +313,50 @@ def run_offline_Lagrangian_filter(config: OfflineFilterConfig, output_dtype=np.f
         raise ValueError(f"the model passed in belongs to a {model.nranks}-rank communicator, not {world}")
     store = None
     try:
-        feeder = SnapshotFeeder(model, D.SlabSource(source, config.grid, rank, world), indices, file_times,
+        feeder = SnapshotFeeder(model, local_source or D.SlabSource(source, config.grid, rank, world), indices, file_times,
                                 config.T_start, config.T_end)
         n_times = int(round(config.T / config.T_out)) + 1
         store = _pick_store(model, config, output_dtype, n_times, output_store)(model, output_dtype,
                                                                                   len(_output_specs(model, config)))
+        import time as _time
+        phases, t_mark = {}, _time.perf_counter()
+
+        def phase(name, sync=True):
+            nonlocal t_mark
+            if sync:
+                model.sync()
+            now = _time.perf_counter()
+            phases[name] = now - t_mark
+            t_mark = now
+
         # forward pass
         feeder.begin(+1)
         feeder.ensure(0.0, 0.0)
-        if feeder.all_resident:
-            model.wait_transfers()           # the queued uploads are done with the host arrays: let them go
-        model.init_from_data()
+        model.init_from_data()               # needs the first snapshot only: the other uploads overlap with the steps
         log.info("Initialised filtered variables")
+        phase("queue_uploads_and_init_s", sync=False)      # the uploads keep running under the first time steps
         fwd, iterations = _run_pass(model, feeder, config, store)
+        phase("forward_pass_s")
         # backward pass: same snapshots, reversed in time, velocities negated; maps change sign
         feeder.begin(-1)
         model.negate_maps()
         model.reset_clock()
-        bwd, _ = _run_pass(model, feeder, config, store)
-        out = sum_forward_backward_contributions(config, fwd, bwd, iterations, model=model, rank=rank, world=world,
-                                                 regrid=config.map_to_mean and regrid)
-        stats = {"h2d_bytes": feeder.bytes_uploaded, "kernel_launches": model.kernel_launches,
+        do_regrid = config.map_to_mean and regrid
+        if store.on_device:
+            # every forward time is combined (and its download queued) as soon as its backward partner exists
+            combiner = ForwardBackwardCombiner(config, fwd, iterations, model, rank=rank, world=world, regrid=do_regrid,
+                                               alloc=alloc)
+            _run_pass(model, feeder, config, store, on_output=combiner.feed)
+            phase("backward_pass_with_combination_s")
+            out = combiner.finish()
+            phase("last_downloads_s")
+        else:
+            bwd, _ = _run_pass(model, feeder, config, store)
+            phase("backward_pass_s")
+            out = sum_forward_backward_contributions(config, fwd, bwd, iterations, model=model, rank=rank, world=world,
+                                                     regrid=do_regrid, alloc=alloc)
+            phase("combination_and_remap_s")
+        stats = {"phases": phases,"h2d_bytes": feeder.bytes_uploaded, "kernel_launches": model.kernel_launches,
                  "kernel": model.kernel_name, "output_store": "device" if store.on_device else "host",
                  "rank": rank, "world": world}
     finally:
@@ -329,7 +365,7 @@ def run_offline_Lagrangian_filter(config: OfflineFilterConfig, output_dtype=np.f
         if own_model:
             model.close()
     if world > 1 and gather_to_root:
-        out = D.merge_outputs_on_root(out, rank, world)
+        out = D.merge_outputs_on_root(out, rank, world, config.grid)
         if rank != 0:
             out.stats = stats
             return out

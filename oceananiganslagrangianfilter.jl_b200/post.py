@@ -31,6 +31,7 @@ class FilterOutput:
         self.fields: Dict[str, List[np.ndarray]] = {}
         self.stats: Dict[str, object] = {}
         self.extra: Dict[str, np.ndarray] = {}
+        self.slab = None          # (rank, world): the arrays are this rank's y-slabs of every output time
 
     def __getitem__(self, name):
         return self.fields[name]
@@ -91,90 +92,146 @@ def _backward_bracket(btimes: np.ndarray, tb: float):
     return n1, w
 
 
-def sum_forward_backward_contributions(config, fwd: Dict[float, Dict[str, object]], bwd: Dict[float, Dict[str, object]],
-                                       iterations: Dict[float, int], model=None, rank: int = 0, world: int = 1,
-                                       regrid: bool = False) -> FilterOutput:
-    """out(t_k) = fwd(t_k) + bwd(T - t_k) for filtered variables and maps, fwd - bwd for mean velocities;
-    the backward series is interpolated linearly in time (reference post:135-164).  The arithmetic runs
-    on the device in FP64 on the (possibly Float32-rounded) pass outputs.
+class ForwardBackwardCombiner:
+    """sum_forward_backward_contributions! (post:45-170), incremental: out(t_k) = fwd(t_k) + bwd(T - t_k) for filtered
+    variables and maps, fwd - bwd for mean velocities, the backward series interpolated linearly in time
+    (post:135-164).  The arithmetic runs on the device in FP64 on the (possibly Float32-rounded) pass outputs.
 
-    The pass outputs are either host arrays (-> lfb_combine) or ids of arrays kept on the device
-    (-> lfb_kept_combine).  In the second form, which is the only one for world > 1, output time k is then gathered
-    across the y-slabs on rank k mod world, remapped to the mean position there when `regrid` (the remap is
-    sharded by output time) and fetched to the host once; every rank returns the output times it owns."""
-    if model is None:
-        raise ValueError("sum_forward_backward_contributions needs the device model (lfb_combine); "
-                         "there is no CPU path")
-    from .distributed import owner_of_time
-    T = config.T
-    label = config.label
-    ident = _identifier(config)
-    mean_vel_names = {vel + label + ident for vel in config.velocity_names} if config.compute_mean_velocities else set()
-    ftimes = sorted(fwd.keys())
-    btimes = np.array(sorted(bwd.keys()))
-    on_device = isinstance(next(iter(fwd[ftimes[0]].values())), (int, np.integer))
-    if world > 1 and not on_device:
-        raise ValueError("the multi-GPU pipeline combines pass outputs kept on the device")
-    mine = [k for k in range(len(ftimes)) if owner_of_time(k, world) == rank]
-    out = FilterOutput([ftimes[k] for k in mine], [iterations[ftimes[k]] for k in mine])
-    if not on_device:
-        for t in ftimes:
-            n1, w = _backward_bracket(btimes, T - t)
-            for name, arr in fwd[t].items():
-                lo = bwd[btimes[n1]][name]
-                hi = bwd[btimes[n1 + 1]][name] if w != 0.0 else None
-                sign = -1.0 if name in mean_vel_names else 1.0
-                out.fields.setdefault(name, []).append(model.combine(arr, lo, hi, w, sign))
-        log.info("Combined forward and backward contributions")
-        if regrid:
-            regrid_to_mean_position(config, out)
-        return out
+    The forward outputs are given up front; the backward outputs are fed one output time after the other
+    (`feed(tb, outputs)`, in increasing pass time), and every forward time is combined as soon as the backward
+    outputs bracketing T - t_k exist, so that -- with pass outputs kept on the device -- the combination and the
+    download of the combined fields overlap with the rest of the backward pass.
 
-    # ---- device form ----
-    # which backward outputs are still needed by later forward times (they are released as soon as possible)
-    last_use = {}
-    plan = []
-    for k, t in enumerate(ftimes):
-        n1, w = _backward_bracket(btimes, T - t)
-        plan.append((n1, w))
-        last_use[n1] = k
-        if w != 0.0:
-            last_use[n1 + 1] = k
-    names = list(fwd[ftimes[0]].keys())
-    for nb in range(len(btimes)):                      # backward outputs no forward time refers to
-        if nb not in last_use:
-            for name in names:
-                model.kept_release(bwd[btimes[nb]][name])
-    for k, t in enumerate(ftimes):
-        n1, w = plan[k]
-        owner = owner_of_time(k, world)
+    Pass outputs are either host arrays (-> lfb_combine) or ids of arrays kept on the device (-> lfb_kept_combine;
+    the only form for world > 1).  In the device form the combined arrays are fetched to the host once, into arrays
+    from `alloc(shape, dtype)` (default numpy.empty, Fortran order; pass an allocator of page-locked memory for
+    full-speed asynchronous copies).  With `regrid`, output time k is first gathered across the y-slabs on rank
+    k mod world and remapped to the mean position there (the remap is sharded by output time): every rank ends up
+    with the output times it owns as GLOBAL arrays.  Without it nothing is gathered: every rank ends up with its
+    y-slab of every output time (`out.slab = (rank, world)`)."""
+
+    def __init__(self, config, fwd: Dict[float, Dict[str, object]], iterations: Dict[float, int], model, btimes=None,
+                 rank: int = 0, world: int = 1, regrid: bool = False, alloc=None):
+        if model is None:
+            raise ValueError("sum_forward_backward_contributions needs the device model (lfb_combine); "
+                             "there is no CPU path")
+        from .distributed import owner_of_time
+        self.config, self.model, self.fwd = config, model, fwd
+        self.rank, self.world, self.regrid, self.alloc = rank, world, regrid, alloc
+        label, ident = config.label, _identifier(config)
+        self.mean_vel_names = ({vel + label + ident for vel in config.velocity_names}
+                               if config.compute_mean_velocities else set())
+        self.ftimes = sorted(fwd.keys())
+        # the backward pass takes the same aligned steps, hence writes at the same pass times
+        self.btimes = np.array(sorted(btimes) if btimes is not None else self.ftimes)
+        self.names = list(fwd[self.ftimes[0]].keys())
+        self.on_device = isinstance(fwd[self.ftimes[0]][self.names[0]], (int, np.integer))
+        if world > 1 and not self.on_device:
+            raise ValueError("the multi-GPU pipeline combines pass outputs kept on the device")
+        self.by_time = regrid or world == 1              # else: by slab
+        self.owner = [owner_of_time(k, world) for k in range(len(self.ftimes))]
+        self.mine = [k for k in range(len(self.ftimes)) if not self.by_time or self.owner[k] == rank]
+        self.out = FilterOutput([self.ftimes[k] for k in self.mine], [iterations[self.ftimes[k]] for k in self.mine])
+        if world > 1 and not self.by_time:
+            self.out.slab = (rank, world)
+        self.plan = [_backward_bracket(self.btimes, config.T - t) for t in self.ftimes]
+        self.need = [n1 + (1 if w != 0.0 else 0) for n1, w in self.plan]        # last backward index time k waits for
+        self.last_use = {}
+        for k, (n1, w) in enumerate(self.plan):
+            for nb in ([n1, n1 + 1] if w != 0.0 else [n1]):
+                self.last_use[nb] = max(self.last_use.get(nb, -1), k)
+        self.bwd: Dict[int, Dict[str, object]] = {}
+        self.results: Dict[int, Dict[str, np.ndarray]] = {}
+        self.done = set()
+        self.deferred: List[int] = []                     # combined arrays whose asynchronous fetch may be pending
+
+    def feed(self, tb: float, outputs: Dict[str, object]):
+        nb = int(np.argmin(np.abs(self.btimes - tb)))
+        if abs(self.btimes[nb] - tb) > 1e-9 * max(1.0, abs(tb)):
+            raise ValueError(f"unexpected backward output time {tb}")
+        self.bwd[nb] = outputs
+        if self.on_device and nb not in self.last_use:
+            for name in self.names:
+                self.model.kept_release(outputs[name])
+        have = max(self.bwd) if len(self.bwd) == max(self.bwd) + 1 else -1      # contiguous from 0
+        # collectives (gather) must be issued in the same order on every rank: forward times in decreasing order of t,
+        # i.e. in the order their backward partners appear
+        for k in sorted(range(len(self.ftimes)), key=lambda q: self.need[q]):
+            if k not in self.done and self.need[k] <= have:
+                self._combine(k)
+
+    def _combine(self, k: int):
+        model, t = self.model, self.ftimes[k]
+        n1, w = self.plan[k]
+        self.done.add(k)
+        if not self.on_device:
+            res = {}
+            for name in self.names:
+                sign = -1.0 if name in self.mean_vel_names else 1.0
+                res[name] = model.combine(self.fwd[t][name], self.bwd[n1][name], self.bwd[n1 + 1][name] if w != 0.0 else None,
+                                          w, sign)
+            self.results[k] = res
+            return
+        for kid in self.deferred:                          # the previous output time's copies are long done
+            model.kept_release(kid)
+        self.deferred = []
         held = {}
-        for name in names:
-            sign = -1.0 if name in mean_vel_names else 1.0
-            cid = model.kept_combine(fwd[t][name], bwd[btimes[n1]][name], bwd[btimes[n1 + 1]][name] if w != 0.0 else None,
+        for name in self.names:
+            sign = -1.0 if name in self.mean_vel_names else 1.0
+            cid = model.kept_combine(self.fwd[t][name], self.bwd[n1][name], self.bwd[n1 + 1][name] if w != 0.0 else None,
                                      w, sign)
-            model.kept_release(fwd[t][name])
-            gid = model.kept_gather(cid, owner)            # collective; with one rank gid == cid
+            model.kept_release(self.fwd[t][name])
+            if not self.by_time:
+                held[name] = cid
+                continue
+            gid = model.kept_gather(cid, self.owner[k])    # collective; with one rank gid == cid
             if gid != cid:
                 model.kept_release(cid)
-            if owner == rank:
+            if self.owner[k] == self.rank:
                 held[name] = gid
-        for nb in [n for n, last in last_use.items() if last == k]:
-            for name in names:
-                model.kept_release(bwd[btimes[nb]][name])
-        if owner != rank:
-            continue
-        if regrid:
+        for nb in [n for n, last in self.last_use.items() if last == k]:
+            for name in self.names:
+                model.kept_release(self.bwd[nb][name])
+        if self.by_time and self.owner[k] != self.rank:
+            return
+        res = {}
+        if self.regrid:
             from .remap import remap_kept_to_mean
-            for name, arr in remap_kept_to_mean(config, model, held).items():
-                out.fields.setdefault(name, []).append(arr)
-        for name in names:
-            out.fields.setdefault(name, []).append(model.kept_fetch(held[name]))
-            model.kept_release(held[name])
-    log.info("Combined forward and backward contributions")
-    if regrid:
-        log.info("Wrote regridded data to new variables with _at_mean suffix")
-    return out
+            res.update(remap_kept_to_mean(self.config, model, held))
+        for name in self.names:
+            res[name] = model.kept_fetch(held[name], alloc=self.alloc, wait=False)
+            self.deferred.append(held[name])
+        self.results[k] = res
+
+    def finish(self) -> FilterOutput:
+        if len(self.done) != len(self.ftimes):
+            raise RuntimeError("backward outputs missing: not every forward time could be combined")
+        if self.on_device:
+            self.model.wait_transfers()
+            for kid in self.deferred:
+                self.model.kept_release(kid)
+            self.deferred = []
+            self.model.kept_trim()
+        for k in self.mine:
+            for name, arr in self.results[k].items():
+                self.out.fields.setdefault(name, []).append(arr)
+        log.info("Combined forward and backward contributions")
+        if self.regrid and self.on_device:
+            log.info("Wrote regridded data to new variables with _at_mean suffix")
+        elif self.regrid:
+            regrid_to_mean_position(self.config, self.out)
+        return self.out
+
+
+def sum_forward_backward_contributions(config, fwd: Dict[float, Dict[str, object]], bwd: Dict[float, Dict[str, object]],
+                                       iterations: Dict[float, int], model=None, rank: int = 0, world: int = 1,
+                                       regrid: bool = False, alloc=None) -> FilterOutput:
+    """The combination of two complete passes (see ForwardBackwardCombiner)."""
+    c = ForwardBackwardCombiner(config, fwd, iterations, model, btimes=list(bwd.keys()), rank=rank, world=world,
+                                regrid=regrid, alloc=alloc)
+    for tb in sorted(bwd.keys()):
+        c.feed(tb, bwd[tb])
+    return c.finish()
 
 
 # ---------------------------------------------------------------------------------------------- remap

@@ -25,10 +25,11 @@ from lfb200.synthetic import make_series
 def run_cases(rank, world, local, cases=None):
     """Returns (ok, lines); usable from bench.py (small grid, before the timed region)."""
     ok, lines = True, []
-    cases = cases or (("Periodic", "generic", True, (24, 8 * world, 10)),
-                      ("Bounded", "generic", True, (24, 8 * world, 10)),
-                      ("Periodic", "auto", False, (40, 16 * world, 16)))
-    for topo_y, kernel, strict, size in cases:
+    cases = cases or (("Periodic", "generic", True, (24, 8 * world, 10), True),
+                      ("Bounded", "generic", True, (24, 8 * world, 10), True),
+                      ("Periodic", "auto", False, (40, 16 * world, 16), True),
+                      ("Bounded", "auto", False, (40, 16 * world, 16), False))     # no remap: outputs stay in slabs
+    for topo_y, kernel, strict, size, regrid in cases:
         g = lfb200.RectilinearGrid(size=size, extent=tuple(float(s) for s in size), topology=("Periodic", topo_y, "Bounded"))
         var_names, vel_names = ("T", "b"), ("u", "v", "w")
         times = [0.0, 0.5, 1.0, 1.5, 2.0]
@@ -37,11 +38,11 @@ def run_cases(rank, world, local, cases=None):
         cfg = lfb200.OfflineFilterConfig(data=data, grid=g, var_names_to_filter=var_names, velocity_names=vel_names,
                                          N=2, freq_c=2 * np.pi / 2.0, dt=0.1, T_out=0.5, device=local, strict=strict,
                                          kernel=kernel, n_slots=5, npad=3)
-        out = lfb200.run_offline_Lagrangian_filter(cfg, save=False)          # collective: all ranks, y-slabs
+        out = lfb200.run_offline_Lagrangian_filter(cfg, save=False, regrid=regrid)     # collective: all ranks, y-slabs
         flag = torch.zeros(1, device="cuda")
         worst, kname, worst_name = 0.0, out.stats["kernel"], ""
         if rank == 0:
-            ref = lfb200.run_offline_Lagrangian_filter(cfg, save=False, rank=0, world=1)
+            ref = lfb200.run_offline_Lagrangian_filter(cfg, save=False, regrid=regrid, rank=0, world=1)
             good = out.times == ref.times and out.iterations == ref.iterations and set(out.keys()) == set(ref.keys())
             for name in ref.keys():
                 for a, b in zip(out[name], ref[name]):
@@ -64,7 +65,7 @@ def run_cases(rank, world, local, cases=None):
                 flag += 1
         dist.all_reduce(flag)
         ok = ok and flag.item() == 0
-        lines.append(f"mgpu_pipeline world={world} y={topo_y} kernel={kname} fields={len(out.keys())} "
+        lines.append(f"mgpu_pipeline world={world} y={topo_y} kernel={kname} remap={int(regrid)} fields={len(out.keys())} "
                      f"times={len(out.times)}: worst={worst:.3e} {worst_name} {'OK' if flag.item() == 0 else 'MISMATCH'}")
     return ok, lines
 
