@@ -202,3 +202,168 @@ class JLD2File:
     def series(self, name: str, dtype=np.float64) -> List[np.ndarray]:
         """All snapshots of ``timeseries/<name>`` (parent arrays, halos included), file order."""
         return [np.asarray(self[f"timeseries/{name}/{it}"], dtype=dtype, order="F") for it in self.iterations(name)]
+
+
+# ---------------------------------------------------------------------------------------------- writer
+_M32 = 0xFFFFFFFF
+
+
+def _rot(x: int, k: int) -> int:
+    return ((x << k) | (x >> (32 - k))) & _M32
+
+
+def lookup3(data: bytes, initval: int = 0) -> int:
+    """Bob Jenkins' lookup3 `hashlittle`, the checksum HDF5 puts behind superblocks and version-2 object headers
+    (checked against the checksums stored in the reference's test/data/*.jld2)."""
+    n = len(data)
+    a = b = c = (0xDEADBEEF + n + initval) & _M32
+    i = 0
+    while n > 12:
+        a = (a + int.from_bytes(data[i:i + 4], "little")) & _M32
+        b = (b + int.from_bytes(data[i + 4:i + 8], "little")) & _M32
+        c = (c + int.from_bytes(data[i + 8:i + 12], "little")) & _M32
+        a = (a - c) & _M32; a ^= _rot(c, 4); c = (c + b) & _M32
+        b = (b - a) & _M32; b ^= _rot(a, 6); a = (a + c) & _M32
+        c = (c - b) & _M32; c ^= _rot(b, 8); b = (b + a) & _M32
+        a = (a - c) & _M32; a ^= _rot(c, 16); c = (c + b) & _M32
+        b = (b - a) & _M32; b ^= _rot(a, 19); a = (a + c) & _M32
+        c = (c - b) & _M32; c ^= _rot(b, 4); b = (b + a) & _M32
+        i += 12
+        n -= 12
+    if n == 0:
+        return c
+    t = bytes(data[i:]) + b"\0" * (12 - n)
+    a = (a + int.from_bytes(t[0:4], "little")) & _M32
+    b = (b + int.from_bytes(t[4:8], "little")) & _M32
+    c = (c + int.from_bytes(t[8:12], "little")) & _M32
+    c ^= b; c = (c - _rot(b, 14)) & _M32
+    a ^= c; a = (a - _rot(c, 11)) & _M32
+    b ^= a; b = (b - _rot(a, 25)) & _M32
+    c ^= b; c = (c - _rot(b, 16)) & _M32
+    a ^= c; a = (a - _rot(c, 4)) & _M32
+    b ^= a; b = (b - _rot(a, 14)) & _M32
+    c ^= b; c = (c - _rot(b, 24)) & _M32
+    return c
+
+
+_HEADER_TEXT = b"HDF5-based Julia Data Format, version 0.2.0\x00 (lfb200, Julia-compatible layout, 64-bit LE)\x00"
+_BASE = 512
+# datatype messages exactly as JLD2.jl writes them (version 3, class 1 IEEE float / class 0 fixed point)
+_DT_F64 = bytes.fromhex("31203f000800000000004000340b0034ff030000")
+_DT_F32 = bytes.fromhex("31201f000400000000002000170800177f000000")
+_DT_I64 = bytes.fromhex("30080000080000000000" "4000")          # class 0, signed, size 8, bit offset 0, precision 64
+
+
+def _message(mtype: int, body: bytes) -> bytes:
+    return struct.pack("<BHB", mtype, len(body), 0) + body
+
+
+def _object_header(messages: List[bytes]) -> bytes:
+    """Version-2 object header with one chunk (4-byte chunk size field) and its lookup3 checksum."""
+    body = b"".join(messages)
+    head = b"OHDR" + bytes([2, 0x02]) + struct.pack("<I", len(body)) + body
+    return head + struct.pack("<I", lookup3(head))
+
+
+class JLD2Writer:
+    """Writes the HDF5 subset JLD2.jl itself emits for plain arrays and scalars: a 512-byte
+    text header, a version-2 superblock, version-2 object headers with lookup3 checksums, groups as compact link
+    messages, contiguous datasets of IEEE floats / Int64 with the dimensions listed reversed (Julia order), compact
+    rank-0 scalars.  `write(path, value)` with `path` like "timeseries/u/12"; groups are created on the way.  The
+    file is laid out when `close()` is called (or the `with` block ends).
+
+    Julia-serialised structs (`serialized/grid`, boundary conditions ...) need Julia's type system and are not
+    written: `jldopen(file)["timeseries/u/12"]` works from Julia, `FieldTimeSeries(file, "u")` needs the grid passed
+    in.  JLD2File (above) reads everything written here."""
+
+    def __init__(self, path: str):
+        self.path = path
+        self.tree: Dict[str, object] = {}
+        self.closed = False
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, *a):
+        if exc_type is None:
+            self.close()
+
+    def write(self, path: str, value):
+        parts = [p for p in path.split("/") if p]
+        if not parts:
+            raise ValueError("empty dataset path")
+        node = self.tree
+        for p in parts[:-1]:
+            node = node.setdefault(p, {})
+            if not isinstance(node, dict):
+                raise ValueError(f"{path!r}: {p!r} is a dataset, not a group")
+        if isinstance(value, (bool, np.bool_)):
+            value = int(value)
+        if isinstance(value, (int, np.integer)):
+            value = np.int64(value)
+        elif isinstance(value, (float, np.floating)) and not isinstance(value, np.float32):
+            value = np.float64(value)
+        else:
+            value = np.asarray(value)
+            if value.dtype not in (np.float32, np.float64, np.int64):
+                raise TypeError(f"{path!r}: dtype {value.dtype} is outside the written subset (float32/float64/int64)")
+        node[parts[-1]] = value
+
+    # ------------------------------------------------------------------ layout
+    def close(self):
+        if self.closed:
+            return
+        self.closed = True
+        chunks: List[bytes] = []
+        pos = 48                                              # first object behind the superblock (relative address)
+
+        def emit(b: bytes) -> int:
+            nonlocal pos
+            pad = (-pos) % 8
+            if pad:
+                chunks.append(b"\0" * pad)
+                pos += pad
+            addr = pos
+            chunks.append(b)
+            pos += len(b)
+            return addr
+
+        def dataset(value) -> int:
+            dt = {np.dtype(np.float64): _DT_F64, np.dtype(np.float32): _DT_F32, np.dtype(np.int64): _DT_I64}[np.asarray(value).dtype]
+            msgs = [_message(0x05, bytes([3, 0x09]))]
+            arr = np.asarray(value)
+            if arr.ndim == 0:
+                msgs.append(_message(MSG_DATASPACE, bytes([2, 0, 0, 0])))
+                msgs.append(_message(MSG_DATATYPE, dt))
+                raw = arr.astype(arr.dtype.newbyteorder("<")).tobytes()
+                msgs.append(_message(MSG_LAYOUT, bytes([4, 0]) + struct.pack("<H", len(raw)) + raw))
+            else:
+                raw = np.asfortranarray(arr).astype(arr.dtype.newbyteorder("<"), copy=False).tobytes(order="F")
+                dims = tuple(reversed(arr.shape))
+                msgs.append(_message(MSG_DATASPACE, bytes([2, len(dims), 0, 1]) + struct.pack(f"<{len(dims)}Q", *dims)))
+                msgs.append(_message(MSG_DATATYPE, dt))
+                daddr = emit(raw)
+                msgs.append(_message(MSG_LAYOUT, bytes([4, 1]) + struct.pack("<QQ", daddr, len(raw))))
+            return emit(_object_header(msgs))
+
+        def group(node: Dict[str, object]) -> int:
+            links = []
+            for name, child in node.items():
+                addr = group(child) if isinstance(child, dict) else dataset(child)
+                nb = name.encode()
+                if len(nb) < 256:
+                    links.append(_message(MSG_LINK, bytes([1, 0x10, 1, len(nb)]) + nb + struct.pack("<Q", addr)))
+                else:
+                    links.append(_message(MSG_LINK, bytes([1, 0x11, 1]) + struct.pack("<H", len(nb)) + nb + struct.pack("<Q", addr)))
+            msgs = [_message(0x02, bytes([0, 0]) + b"\xff" * 16), _message(0x0A, bytes([0, 0]))] + links
+            return emit(_object_header(msgs))
+
+        root = group(self.tree)
+        body = b"".join(chunks)
+        eof = _BASE + 48 + len(body)
+        sb = _SIGNATURE + bytes([2, 8, 8, 0]) + struct.pack("<QQQQ", _BASE, 0xFFFFFFFFFFFFFFFF, eof, root)
+        sb += struct.pack("<I", lookup3(sb))
+        with open(self.path, "wb") as fh:
+            fh.write(_HEADER_TEXT.ljust(_BASE, b"\0"))
+            fh.write(sb)
+            fh.write(body)

@@ -64,17 +64,54 @@ class FilterOutput:
             self.fields[name] = series
 
     def save(self, filename: str):
-        """Writes `<stem>.npz` with `timeseries/<name>/<iteration>`-style keys (the JLD2 group layout of
-        the reference flattened into npz keys)."""
-        stem = filename[:-5] if filename.endswith(".jld2") else filename
-        payload = {"timeseries/t": np.array(self.times), "iterations": np.array(self.iterations)}
+        """Writes the combined output with the reference's on-disk layout (SURVEY.md Appendix C;
+        post_processing_utils.jl:395-404, 751-755, 1417-1424): `timeseries/t/<iteration>` scalars and
+        `timeseries/<name>/<iteration>` arrays with halos, in the element type they have here (Float64 for the combined
+        and remapped fields, Float32 for the copied original data), as a JLD2 file (`*.jld2`, written by
+        jld2.JLD2Writer, readable by JLD2.jl's `jldopen` and by jld2.JLD2File) or, for any other suffix, as an `.npz`
+        archive with the same keys.  Returns the path written."""
+        payload = {}
+        for it, t in zip(self.iterations, self.times):
+            payload[f"timeseries/t/{it}"] = float(t)
         for name, series in self.fields.items():
             for it, arr in zip(self.iterations, series):
                 payload[f"timeseries/{name}/{it}"] = arr
         for k, v in self.extra.items():
-            payload[k] = v
-        np.savez(stem + ".npz", **payload)
+            if np.ndim(v) == 1 and len(v) == len(self.iterations):      # per-output-time scalars, e.g. timeseries/t_shifted
+                for it, x in zip(self.iterations, v):
+                    payload[f"{k}/{it}"] = float(x)
+            else:
+                payload[k] = v
+        if filename.endswith(".jld2"):
+            from .jld2 import JLD2Writer
+            with JLD2Writer(filename) as w:
+                for k, v in payload.items():
+                    w.write(k, v)
+            return filename
+        stem = filename[:-4] if filename.endswith(".npz") else filename
+        np.savez(stem + ".npz", **{k: np.asarray(v) for k, v in payload.items()})
         return stem + ".npz"
+
+    @classmethod
+    def load(cls, filename: str) -> "FilterOutput":
+        """Reads a combined output file written by `save` (or by the reference) back: every `timeseries/<name>` group
+        whose entries are plain arrays."""
+        from .jld2 import JLD2File, JLD2FormatError
+        f = JLD2File(filename)
+        its = f.iterations("t")
+        out = cls([f[f"timeseries/t/{it}"] for it in its], its)
+        for name in f.keys("timeseries"):
+            if name == "t":
+                continue
+            try:
+                first = f[f"timeseries/{name}/{its[0]}"]
+            except (KeyError, JLD2FormatError):
+                continue
+            if np.ndim(first) == 0:
+                out.extra[f"timeseries/{name}"] = np.array([f[f"timeseries/{name}/{it}"] for it in its])
+            else:
+                out.fields[name] = [f[f"timeseries/{name}/{it}"] for it in its]
+        return out
 
 
 def _identifier(config) -> str:

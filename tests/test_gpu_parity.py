@@ -58,7 +58,7 @@ def test_golden_case_steps_vs_oracle(golden_sim, strict):
     m.close(); o.close()
 
 
-def test_golden_full_offline_run_vs_reference_file(golden_sim, golden_offline):
+def test_golden_full_offline_run_vs_reference_file(golden_sim, golden_offline, tmp_path):
     """The reference's own integration test (test/test_offline_integration.jl:1-32) through the public API:
     run_offline_Lagrangian_filter on reference_sim, compared with reference_offline_output."""
     times, fields = golden_series(golden_sim)
@@ -68,6 +68,15 @@ def test_golden_full_offline_run_vs_reference_file(golden_sim, golden_offline):
                                      output_filename="")
     out = lfb200.run_offline_Lagrangian_filter(cfg, save=False)
     assert out.iterations == list(golden_offline["iterations"])
+    # the file written for this run has the golden file's `timeseries` layout: same variables, same iteration keys,
+    # same shapes and element types (run_offline_lagrangian_filter.jl:77-80, post:395-404, 751-755)
+    f = lfb200.JLD2File(out.save(str(tmp_path / "filtered_output.jld2")))
+    golden_names = [k for k in golden_offline.files if k not in ("t", "iterations")]
+    assert sorted(f.keys("timeseries")) == sorted(golden_names + ["t"])
+    for name in golden_names:
+        assert f.iterations(name) == list(golden_offline["iterations"])
+        a = f[f"timeseries/{name}/{out.iterations[5]}"]
+        assert a.shape == golden_offline[name][5].shape and a.dtype == golden_offline[name].dtype, name
     # the reference test: isapprox(test, ref; rtol=1e-6) on the u family (array norms, halos included)
     for name in ("u", "u_Lagrangian_filtered", "u_Lagrangian_filtered_at_mean", "u_Eulerian_filtered"):
         got, ref = out.stacked(name), golden_offline[name]
