@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-size", type=int, nargs=3, default=[256, 128, 64])
+    ap.add_argument("--remap", action="store_true",
+                    help="time the remap to the mean position (post-processing, one output time) instead of the stepping")
+    ap.add_argument("--remap-fields", type=int, default=5)
     return ap.parse_args()
 
 
@@ -169,6 +172,57 @@ def workload_config(args, world):
             "decomposition": f"{world} y-slab(s)", "l2": "inputs (>= 25 GB of fields per GPU at full size) exceed the 126 MB L2"}
 
 
+# ------------------------------------------------------------------------------------------------ remap
+def run_remap(args, local):
+    """regrid_to_mean_position! for ONE output time of the workload's grid (post:327-762): synthetic, smooth
+    displacement maps of about half a cell, `--remap-fields` fields sharing one tetrahedron search; inputs resident on
+    the device, result arrays on the host.  Prints its own JSON line (metric: remap nodes/s)."""
+    import ctypes as C
+    import torch
+    import lfb200
+    from lfb200 import _lib
+    g = make_grid(args.size)
+    dev = torch.device("cuda", local)
+    shape = tuple(reversed(g.center_shape()))                 # torch (z, y, x) = Fortran (x, y, z)
+    z, y, x = torch.meshgrid(*[torch.arange(n, device=dev, dtype=torch.float64) for n in shape], indexing="ij")
+    two_pi = 2 * np.pi
+    X, Y, Z = (x - g.Hx + 0.5) / g.Nx, (y - g.Hy + 0.5) / g.Ny, (z - g.Hz + 0.5) / g.Nz
+    xi = [0.45 * g.spacing[0] * torch.sin(two_pi * (X + 2 * Y)) * torch.cos(two_pi * Z),
+          0.40 * g.spacing[1] * torch.cos(two_pi * (2 * X - Y)) * torch.sin(two_pi * Z + 0.3),
+          0.35 * g.spacing[2] * torch.sin(two_pi * (X + Y)) * torch.sin(np.pi * Z)]
+    fields = [torch.sin(two_pi * (X * (q + 1) + Y)) + Z * q for q in range(args.remap_fields)]
+    del x, y, z, X, Y, Z
+    torch.cuda.synchronize()
+    L = _lib.load()
+    d = _lib.RemapDesc()
+    for ax in range(3):
+        d.size[ax], d.halo[ax] = g.N[ax], g.H[ax]
+        d.topology[ax] = _lib.TOPOLOGY[g.topology[ax]]
+        d.origin[ax], d.spacing[ax] = g.origin[ax], g.spacing[ax]
+        d.has_map[ax] = 1
+    d.npad, d.device = 5, local
+    outs = [np.empty(g.center_shape(), dtype=np.float64, order="F") for _ in fields]
+    xp = (C.c_void_p * 3)(*[t.data_ptr() for t in xi])
+    fp_ = (C.c_void_p * len(fields))(*[t.data_ptr() for t in fields])
+    op = (C.c_void_p * len(fields))(*[o.ctypes.data for o in outs])
+    times = []
+    for rep in range(1 + max(1, args.steps // 8)):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _lib.check(L.lfb_remap_to_mean(C.byref(d), xp, len(fields), fp_, op))
+        times.append(time.perf_counter() - t0)
+    best = min(times[1:]) if len(times) > 1 else times[0]
+    nodes = g.Nx * g.Ny * g.Nz
+    inner = outs[0][g.Hx:-g.Hx, g.Hy:-g.Hy, g.Hz:-g.Hz]
+    line = {"metric": "remap nodes/s", "value": nodes / best, "unit": "node/s (one output time, search shared by the fields)",
+            "n_gpus": 1, "seconds_per_output_time": best, "fields": len(fields), "grid": list(args.size),
+            "nan_fraction": float(np.isnan(inner).mean()), "higher_is_better": True, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"remap to the mean position of {len(fields)} fields on the synthetic 3D "
+                                   f"{args.size[0]}x{args.size[1]}x{args.size[2]} grid (Periodic,Periodic,Bounded), displacement maps of "
+                                   "about 0.45 cells, npad = 5; inputs on the device, results on the host"}}
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse()
@@ -188,6 +242,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: lfb200 has no CPU fallback")
     torch.cuda.set_device(local)
+    if args.remap:
+        if rank == 0:
+            run_remap(args, local)
+        return
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     gglobal = make_grid(args.size)

@@ -121,6 +121,7 @@ struct lfb_handle {
     int64_t    stage_launches;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;   // pending stage timings
     int        use_zmarch;
+    int        fold;                       // the TMA kernel runs the (Flat y) grid folded: rows of 32 cells
     int        halos_valid;                // halos of U[cur] are up to date (kept so by the stage kernels)
     // distributed y-slabs
     cudaStream_t comm_stream;
@@ -194,11 +195,14 @@ static int select_kernel(lfb_handle *h)
     P.imm = h->imm;
     for (int ax = 0; ax < 3; ++ax) P.vel_present[ax] = (h->desc.velocity_mask >> ax) & 1;
     P.j0 = 0; P.j1 = h->L.N[1];
-    // 0 generic, 3 TMA-staged z-march (what `auto` picks when the grid allows it)
-    const int ok_tma = lfb_ztma_supported(&P) && !h->desc.strict;
-    const char *need = "a 3-D grid (no Flat axis) with Nx >= 8, Ny >= 4, Nz >= 8, halos >= 3, at least one velocity component, "
-                       "WENO(order=5) advection, no immersed boundary and strict = 0";
+    // 0 generic, 3 TMA-staged z-march (what `auto` picks when the grid allows it; 2 from lfb_ztma_supported: folded, Flat y)
+    const int sup = lfb_ztma_supported(&P);
+    const int fold_v = ((h->desc.velocity_mask >> 1) & 1) && h->desc.n_vars >= LFB_MAX_VARS;   // v travels in the last variable slot
+    const int ok_tma = sup && !h->desc.strict && !(sup == 2 && fold_v);
+    const char *need = "a 3-D grid (or a Flat y axis with a non-Flat x and z) with Nx >= 8, Ny >= 4, Nz >= 8, halos >= 3, at least "
+                       "one velocity component, WENO(order=5) advection, no immersed boundary and strict = 0";
     h->use_zmarch = 0;
+    h->fold = 0;
     switch (h->desc.kernel) {
     case LFB_KERNEL_AUTO: h->use_zmarch = ok_tma ? 3 : 0; break;
     case LFB_KERNEL_GENERIC: break;
@@ -208,6 +212,11 @@ static int select_kernel(lfb_handle *h)
         break;
     default:
         return fail(LFB_ERR_ARG, "kernel id %d: the cp.async z-march kernels (ids 2, 3) were retired; use AUTO, GENERIC or ZTMA", h->desc.kernel);
+    }
+    if (h->use_zmarch == 3 && sup == 2) {
+        h->fold = 1;
+        h->L.fuse_halo[0] = 0;           // the folded kernel does not write the periodic x images: filled before each stage
+        h->halos_valid = 0;
     }
     return LFB_OK;
 }
@@ -349,7 +358,7 @@ extern "C" int lfb_create(const lfb_desc *desc, lfb_handle **out)
     h->export_next = 0;
     h->cur = 0; h->time = 0; h->iteration = 0; h->direction = 1;
     h->launches = 0; h->stage_ms = 0; h->stage_launches = 0;
-    h->use_zmarch = 0;
+    h->use_zmarch = 0; h->fold = 0;
     int rc = create_impl(h);
     if (rc) { lfb_destroy(h); return rc; }
     *out = h;
@@ -833,6 +842,13 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
             const double *b = h->slot_field[(size_t)s2 * N_FIELD_IDS + f];
             const bool neg = backward && f < 3;
             const double *use = a;
+            if (f == 1 && ztma && h->fold) {
+                // Flat y: v is not advected with; it forces its xi_v map from its two snapshots (last variable slot)
+                P.var_fused = 1; P.var_w1 = w1; P.var_w2 = w2;
+                P.var[LFB_MAX_VARS - 1] = a; P.var2[LFB_MAX_VARS - 1] = interp ? b : a;
+                P.vsign = backward ? -1.0 : 1.0;
+                continue;
+            }
             if (f >= 3 && ztma) {
                 // the TMA z-march kernel reads both snapshots of a variable and interpolates in its forcing term
                 P.var_fused = 1; P.var_w1 = w1; P.var_w2 = w2;
@@ -853,9 +869,10 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
         if (I.n_fields) { CU(lfb_launch_interp_inputs(&I, h->compute)); h->launches++; }
     }
     for (int ax = 0; ax < 3; ++ax) P.vel_present[ax] = (h->desc.velocity_mask >> ax) & 1;
+    P.fold = ztma && h->fold;
     if (ztma)
         for (int ax = 0; ax < 3; ++ax)
-            if (!P.vel_present[ax]) {                  // a component that is not advected with: zero face velocity
+            if (!P.vel_present[ax] && !(ax == 1 && h->fold)) {                  // a component that is not advected with: zero face velocity
                 if (!h->zero_field) {
                     CU(cudaMalloc(&h->zero_field, (size_t)h->L.len * sizeof(double)));
                     CU(cudaMemsetAsync(h->zero_field, 0, (size_t)h->L.len * sizeof(double), h->compute));
@@ -871,7 +888,7 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
         else {
             P.pf.on = 1; P.pf.negate = backward; P.pf.w1 = ninterp ? nw1 : 1.0; P.pf.w2 = ninterp ? nw2 : 0.0;
             for (int f = 0; f < 3; ++f) {
-                if (!field_present(h, f)) continue;
+                if (!field_present(h, f) || (f == 1 && h->fold)) continue;
                 P.pf.s1[f] = h->slot_field[(size_t)n1 * N_FIELD_IDS + f];
                 P.pf.s2[f] = h->slot_field[(size_t)(ninterp ? n2 : n1) * N_FIELD_IDS + f];
                 P.pf.dst[f] = pset == 1 ? h->vin_alt[f] : h->cur_in[f];

@@ -83,6 +83,13 @@ struct LfbStageParams {
     int     var_fused;
     const double *var2[LFB_MAX_VARS];
     double  var_w1, var_w2;
+    // TMA z-march kernel on a grid with a Flat y axis (the reference's 2-D examples): the x line of a plane is viewed as
+    // rows of 32 cells (row r = cells [32 r, 32 r + 32), its haloed tile = cells [32 r - 4, 32 r + 36) through a tensor
+    // map whose row stride is smaller than its inner extent), y faces are not computed.  fold_nx = the real Nx.  A v
+    // component named in velocity_names then only forces its xi_v map (cell-centred on the Flat axis): its two
+    // bracketing snapshots travel in var[LFB_MAX_VARS - 1] / var2[...], vsign = -1 on the backward pass.
+    int     fold, fold_nx;
+    double  vsign;
     // second row range [jb0, jb1) of the same launch (the two edge strips of a slab in ONE grid); empty if jb1 <= jb0
     int     jb0, jb1;
     // side job of the TMA z-march kernel: while it computes this stage, its helper warps interpolate the velocities of

@@ -290,96 +290,123 @@ __device__ __forceinline__ void remap3_locate_node(const Remap3Params &P, const 
     auto none = [&]() {
         for (int v = 0; v < 4; ++v) { tet[4 * node + v] = -1; wgt[4 * node + v] = 0.0; }
     };
-    // a: nearest data point to the node
-    double best = INFINITY;
-    bool have = false;
-    for (int d2 = -r2; d2 <= r2; ++d2)
-        for (int d1 = -r1; d1 <= r1; ++d1)
-            for (int d0 = -r0; d0 <= r0; ++d0) {
-                if (!src(i0 + d0, i1 + d1, i2 + d2, t)) continue;
-                const double dd = (t.x - qx) * (t.x - qx) + (t.y - qy) * (t.y - qy) + (t.z - qz) * (t.z - qz);
-                if (dd < best) { best = dd; a = t; have = true; }
-            }
-    if (!have) { none(); return; }
-    // b: nearest neighbour of a (a Delaunay edge)
-    best = INFINITY; have = false;
-    for (int d2 = -r2; d2 <= r2; ++d2)
-        for (int d1 = -r1; d1 <= r1; ++d1)
-            for (int d0 = -r0; d0 <= r0; ++d0) {
-                const int p0 = i0 + d0, p1 = i1 + d1, p2 = i2 + d2;
-                if (same3(a, p0, p1, p2) || !src(p0, p1, p2, t)) continue;
-                const double dd = (t.x - a.x) * (t.x - a.x) + (t.y - a.y) * (t.y - a.y) + (t.z - a.z) * (t.z - a.z);
-                if (dd < best) { best = dd; b = t; have = true; }
-            }
-    if (!have) { none(); return; }
-    // c: smallest circumcircle through a, b: R^2 = |ab|^2 |ac|^2 |bc|^2 / (4 |ab x ac|^2)
-    {
-        const double ux = b.x - a.x, uy = b.y - a.y, uz = b.z - a.z, uu = ux * ux + uy * uy + uz * uz;
-        double bn = 0, bd = -1;
-        have = false;
-        for (int d2 = -r2; d2 <= r2; ++d2)
-            for (int d1 = -r1; d1 <= r1; ++d1)
-                for (int d0 = -r0; d0 <= r0; ++d0) {
-                    const int p0 = i0 + d0, p1 = i1 + d1, p2 = i2 + d2;
-                    if (same3(a, p0, p1, p2) || same3(b, p0, p1, p2) || !src(p0, p1, p2, t)) continue;
-                    const double vx = t.x - a.x, vy = t.y - a.y, vz = t.z - a.z, vv = vx * vx + vy * vy + vz * vz;
-                    const double wx = t.x - b.x, wy = t.y - b.y, wz = t.z - b.z, ww = wx * wx + wy * wy + wz * wz;
-                    const double cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
-                    const double cc = cx * cx + cy * cy + cz * cz;
-                    if (!(cc > 1e-30 * uu * vv)) continue;                  // collinear
-                    const double num = uu * vv * ww;
-                    if (!have || num * bd < bn * cc) { bn = num; bd = cc; c = t; have = true; }
-                }
-        if (!have) { none(); return; }
-    }
-    if (orient3(a, b, c, qx, qy, qz) < 0) { t = b; b = c; c = t; }
     bool found = false;
     double wa = 0, wb = 0, wc = 0, wd = 0, scx = 0, scy = 0, scz = 0, srad2 = 0;
-    for (int step = 0; step < 96; ++step) {
-        // circumcentre o and radius of the face, unit normal towards the node's side
-        const double ux = b.x - a.x, uy = b.y - a.y, uz = b.z - a.z, vx = c.x - a.x, vy = c.y - a.y, vz = c.z - a.z;
-        const double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
-        const double nn = nx * nx + ny * ny + nz * nz, uu = ux * ux + uy * uy + uz * uz, vv = vx * vx + vy * vy + vz * vz;
-        // o - a = (|u|^2 (v x n) + |v|^2 (n x u)) / (2 |n|^2)
-        const double ox = (uu * (vy * nz - vz * ny) + vv * (ny * uz - nz * uy)) / (2 * nn);
-        const double oy = (uu * (vz * nx - vx * nz) + vv * (nz * ux - nx * uz)) / (2 * nn);
-        const double oz = (uu * (vx * ny - vy * nx) + vv * (nx * uy - ny * ux)) / (2 * nn);
-        const double R2 = ox * ox + oy * oy + oz * oz;
-        const double inv_n = rsqrt(nn);
-        const double ex = nx * inv_n, ey = ny * inv_n, ez = nz * inv_n;
-        double bt = INFINITY;
-        bool any = false;
-        for (int d2 = -r2; d2 <= r2; ++d2)
-            for (int d1 = -r1; d1 <= r1; ++d1)
-                for (int d0 = -r0; d0 <= r0; ++d0) {
-                    const int p0 = i0 + d0, p1 = i1 + d1, p2 = i2 + d2;
-                    if (same3(a, p0, p1, p2) || same3(b, p0, p1, p2) || same3(c, p0, p1, p2)) continue;
-                    if (!src(p0, p1, p2, t)) continue;
-                    const double px = t.x - a.x - ox, py = t.y - a.y - oy, pz = t.z - a.z - oz;
-                    const double h = px * ex + py * ey + pz * ez;
-                    if (!(h > 1e-14)) continue;                             // not on the node's side of the face
-                    const double tt = (px * px + py * py + pz * pz - R2) / (2 * h);
-                    if (tt < bt) { bt = tt; d = t; any = true; }
+    // Up to three passes over growing patches.  The early ones search an inner patch two cells, then one cell smaller in
+    // every direction (a fraction of the candidates) and then check that no point of the shell around it lies inside the
+    // circumsphere of the tetrahedron found: the Delaunay tetrahedron that contains the node is the unique one with an
+    // empty circumsphere, so a result that passes is the result of the full search.  Otherwise (rare) the next pass
+    // searches the next larger patch, the last one the full patch.
+    for (int pass = 0; pass < 3 && !found; ++pass) {
+        const int shrink = 2 - pass;
+        const int R0 = max(1, r0 - shrink), R1 = max(1, r1 - shrink), R2 = max(1, r2 - shrink);
+        if (pass < 2 && R0 == max(1, r0 - shrink + 1) && R1 == max(1, r1 - shrink + 1) && R2 == max(1, r2 - shrink + 1)) continue;
+        // a: nearest data point to the node
+        double best = INFINITY;
+        bool have = false;
+        for (int d2 = -R2; d2 <= R2; ++d2)
+            for (int d1 = -R1; d1 <= R1; ++d1)
+                for (int d0 = -R0; d0 <= R0; ++d0) {
+                    if (!src(i0 + d0, i1 + d1, i2 + d2, t)) continue;
+                    const double dd = (t.x - qx) * (t.x - qx) + (t.y - qy) * (t.y - qy) + (t.z - qz) * (t.z - qz);
+                    if (dd < best) { best = dd; a = t; have = true; }
                 }
-        if (!any) break;                                                    // the node is outside the convex hull
-        const double vol = orient3(a, b, c, d.x, d.y, d.z);
-        // barycentric coordinates of the node: replace one vertex by the node in the orientation determinant
-        Cand3 qn; qn.x = qx; qn.y = qy; qn.z = qz;
-        wd = orient3(a, b, c, qx, qy, qz) / vol;
-        wa = orient3(qn, b, c, d.x, d.y, d.z) / vol;
-        wb = orient3(a, qn, c, d.x, d.y, d.z) / vol;
-        wc = orient3(a, b, qn, d.x, d.y, d.z) / vol;
-        if (wa >= 0 && wb >= 0 && wc >= 0) {
-            found = true;
-            scx = a.x + ox + bt * ex; scy = a.y + oy + bt * ey; scz = a.z + oz + bt * ez;
-            srad2 = R2 + bt * bt;
-            break;
+        if (!have) continue;
+        // b: nearest neighbour of a (a Delaunay edge)
+        best = INFINITY; have = false;
+        for (int d2 = -R2; d2 <= R2; ++d2)
+            for (int d1 = -R1; d1 <= R1; ++d1)
+                for (int d0 = -R0; d0 <= R0; ++d0) {
+                    const int p0 = i0 + d0, p1 = i1 + d1, p2 = i2 + d2;
+                    if (same3(a, p0, p1, p2) || !src(p0, p1, p2, t)) continue;
+                    const double dd = (t.x - a.x) * (t.x - a.x) + (t.y - a.y) * (t.y - a.y) + (t.z - a.z) * (t.z - a.z);
+                    if (dd < best) { best = dd; b = t; have = true; }
+                }
+        if (!have) continue;
+        // c: smallest circumcircle through a, b: R^2 = |ab|^2 |ac|^2 |bc|^2 / (4 |ab x ac|^2)
+        {
+            const double ux = b.x - a.x, uy = b.y - a.y, uz = b.z - a.z, uu = ux * ux + uy * uy + uz * uz;
+            double bn = 0, bd = -1;
+            have = false;
+            for (int d2 = -R2; d2 <= R2; ++d2)
+                for (int d1 = -R1; d1 <= R1; ++d1)
+                    for (int d0 = -R0; d0 <= R0; ++d0) {
+                        const int p0 = i0 + d0, p1 = i1 + d1, p2 = i2 + d2;
+                        if (same3(a, p0, p1, p2) || same3(b, p0, p1, p2) || !src(p0, p1, p2, t)) continue;
+                        const double vx = t.x - a.x, vy = t.y - a.y, vz = t.z - a.z, vv = vx * vx + vy * vy + vz * vz;
+                        const double wx = t.x - b.x, wy = t.y - b.y, wz = t.z - b.z, ww = wx * wx + wy * wy + wz * wz;
+                        const double cx = uy * vz - uz * vy, cy = uz * vx - ux * vz, cz = ux * vy - uy * vx;
+                        const double cc = cx * cx + cy * cy + cz * cz;
+                        if (!(cc > 1e-30 * uu * vv)) continue;                  // collinear
+                        const double num = uu * vv * ww;
+                        if (!have || num * bd < bn * cc) { bn = num; bd = cc; c = t; have = true; }
+                    }
+            if (!have) continue;
         }
-        // leave through the face opposite the most negative coordinate; orient the new face towards the node
-        if (wa <= wb && wa <= wc)      { a = d; }          // face (d, b, c)
-        else if (wb <= wa && wb <= wc) { b = d; }          // face (a, d, c)
-        else                           { c = d; }          // face (a, b, d)
         if (orient3(a, b, c, qx, qy, qz) < 0) { t = b; b = c; c = t; }
+        for (int step = 0; step < 96; ++step) {
+            // circumcentre o and radius of the face, unit normal towards the node's side
+            const double ux = b.x - a.x, uy = b.y - a.y, uz = b.z - a.z, vx = c.x - a.x, vy = c.y - a.y, vz = c.z - a.z;
+            const double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+            const double nn = nx * nx + ny * ny + nz * nz, uu = ux * ux + uy * uy + uz * uz, vv = vx * vx + vy * vy + vz * vz;
+            // o - a = (|u|^2 (v x n) + |v|^2 (n x u)) / (2 |n|^2)
+            const double ox = (uu * (vy * nz - vz * ny) + vv * (ny * uz - nz * uy)) / (2 * nn);
+            const double oy = (uu * (vz * nx - vx * nz) + vv * (nz * ux - nx * uz)) / (2 * nn);
+            const double oz = (uu * (vx * ny - vy * nx) + vv * (nx * uy - ny * ux)) / (2 * nn);
+            const double R2c = ox * ox + oy * oy + oz * oz;
+            const double inv_n = rsqrt(nn);
+            const double ex = nx * inv_n, ey = ny * inv_n, ez = nz * inv_n;
+            // fourth vertex: the point on the node's side whose sphere through the face has the lowest centre along the
+            // normal, t = (|p - o|^2 - R^2) / (2 h); candidates are compared as fractions (no division per candidate)
+            double bnum = 0, bh = -1;
+            bool any = false;
+            for (int d2 = -R2; d2 <= R2; ++d2)
+                for (int d1 = -R1; d1 <= R1; ++d1)
+                    for (int d0 = -R0; d0 <= R0; ++d0) {
+                        const int p0 = i0 + d0, p1 = i1 + d1, p2 = i2 + d2;
+                        if (!src(p0, p1, p2, t)) continue;
+                        const double px = t.x - a.x - ox, py = t.y - a.y - oy, pz = t.z - a.z - oz;
+                        const double h = px * ex + py * ey + pz * ez;
+                        if (!(h > 1e-14)) continue;                             // not on the node's side of the face
+                        if (same3(a, p0, p1, p2) || same3(b, p0, p1, p2) || same3(c, p0, p1, p2)) continue;
+                        const double num = px * px + py * py + pz * pz - R2c;
+                        if (!any || num * bh < bnum * h) { bnum = num; bh = h; d = t; any = true; }
+                    }
+            if (!any) break;                                                    // the node is outside the convex hull
+            const double bt = bnum / (2 * bh);
+            const double vol = orient3(a, b, c, d.x, d.y, d.z);
+            // barycentric coordinates of the node: replace one vertex by the node in the orientation determinant
+            Cand3 qn; qn.x = qx; qn.y = qy; qn.z = qz;
+            wd = orient3(a, b, c, qx, qy, qz) / vol;
+            wa = orient3(qn, b, c, d.x, d.y, d.z) / vol;
+            wb = orient3(a, qn, c, d.x, d.y, d.z) / vol;
+            wc = orient3(a, b, qn, d.x, d.y, d.z) / vol;
+            if (wa >= 0 && wb >= 0 && wc >= 0) {
+                found = true;
+                scx = a.x + ox + bt * ex; scy = a.y + oy + bt * ey; scz = a.z + oz + bt * ez;
+                srad2 = R2c + bt * bt;
+                break;
+            }
+            // leave through the face opposite the most negative coordinate; orient the new face towards the node
+            if (wa <= wb && wa <= wc)      { a = d; }          // face (d, b, c)
+            else if (wb <= wa && wb <= wc) { b = d; }          // face (a, d, c)
+            else                           { c = d; }          // face (a, b, d)
+            if (orient3(a, b, c, qx, qy, qz) < 0) { t = b; b = c; c = t; }
+        }
+        if (found && pass < 2) {
+            // is the circumsphere empty of the points of the outer shell?
+            const double lim = srad2 * (1.0 - 1e-10);
+            for (int d2 = -r2; d2 <= r2 && found; ++d2)
+                for (int d1 = -r1; d1 <= r1 && found; ++d1) {
+                    const bool inner_row = d2 >= -R2 && d2 <= R2 && d1 >= -R1 && d1 <= R1;
+                    for (int d0 = -r0; d0 <= r0; ++d0) {
+                        if (inner_row && d0 >= -R0 && d0 <= R0) { d0 = R0; continue; }      // skip the inner patch
+                        if (!src(i0 + d0, i1 + d1, i2 + d2, t)) continue;
+                        const double dd = (t.x - scx) * (t.x - scx) + (t.y - scy) * (t.y - scy) + (t.z - scz) * (t.z - scz);
+                        if (dd < lim) { found = false; break; }
+                    }
+                }
+        }
     }
     if (!found) { none(); return; }
     {

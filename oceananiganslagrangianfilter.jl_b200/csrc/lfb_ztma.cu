@@ -268,7 +268,8 @@ __device__ __noinline__ double zt_top_face_buffer(int m, int Nz, double cw, doub
 
 // WALLS: the general instantiation -- Bounded x or y axes (buffer schemes next to those walls), Periodic z and boundary relaxation;
 // compiled separately so that the all-periodic form keeps its register allocation.
-template <int NSUB, int TY, bool WALLS>
+// FLATY: the folded form for grids with a Flat y axis (LfbStageParams::fold): no y faces, no v tile.
+template <int NSUB, int TY, bool WALLS, bool FLATY>
 __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(const __grid_constant__ LfbZtParams P)
 {
     using SM = ZtSmem<NSUB, TY>;
@@ -295,7 +296,9 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     const LfbItem item = S.items[item_id];
     const int Nz = L.N[2];
     const bool use_G = !S.first_stage;
-    const bool item_var = !item.is_map;
+    const bool flat_v = FLATY && item.is_map && item.src == 1;      // xi_v on a Flat y axis: forced by the cell-centred v
+    const bool item_var = !item.is_map || flat_v;
+    const int  src_map = flat_v ? LFB_MAX_VARS - 1 : item.src;      // tensor maps of the forcing source's two snapshots
     const bool relax = WALLS && S.relax;                  // boundary relaxation: only in the general instantiation
     const bool zper = WALLS && L.topo[2] == LFB_PERIODIC; // Periodic z: likewise
     const ZtK K = {P.k133, P.k13, P.k16, P.eps43};
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         // One loop for the whole warp (bar.sync is warp-aligned): the producer lane issues the TMA loads of the planes
         // ZT_D ahead, the face lanes compute their edge faces, idle lanes only keep the barrier count.
         const int cx = L.xoff + i0 - ZT_HX, cy = L.H[1] + j0 - 3, ix = L.xoff + i0, iy = L.H[1] + j0, z0 = L.H[2];
-        const unsigned in_bytes = 8u * (ZT_CW * TY + 32 * (TY + 1) + 2 * 32 * TY) + (use_G ? NSUB * NT_B : 0u) + (item_var ? 2 * NT_B : 0u) + (relax ? NT_B : 0u);
+        const unsigned in_bytes = 8u * (ZT_CW * TY + (FLATY ? 0 : 32 * (TY + 1)) + 2 * 32 * TY) + (use_G ? NSUB * NT_B : 0u) + (item_var ? 2 * NT_B : 0u) + (relax ? NT_B : 0u);
         auto issue_C = [&](int pz, unsigned bar) {            // haloed tracer planes at z index pz (-2 .. Nz+2)
             const unsigned dst = sbase + oC + (unsigned)((pz + 2) & (ZT_RC - 1)) * CSLOT_B;
 #pragma unroll
@@ -334,15 +337,15 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             if (withC) issue_C(g + 4, bar);
             const unsigned is = sbase + (unsigned)(g & (ZT_RI - 1)) * ISLOT_B;
             tma_load_3d(is + oU, &P.mU, cx, iy, z0 + g, bar);
-            tma_load_3d(is + oV, &P.mV, ix, iy, z0 + g, bar);
+            if (!FLATY) tma_load_3d(is + oV, &P.mV, ix, iy, z0 + g, bar);
             tma_load_3d(is + oW, &P.mW, ix, iy, z0 + g, bar);
             if (use_G) {
 #pragma unroll
                 for (int s = 0; s < NSUB; ++s) tma_load_4d(is + oG + s * VT_B, &P.mG, ix, iy, z0 + g, item.tracer_c + s, bar);
             }
             if (item_var) {
-                tma_load_3d(is + oF, &P.mF[item.src], ix, iy, z0 + g, bar);
-                tma_load_3d(is + oF2, &P.mF2[item.src], ix, iy, z0 + g, bar);
+                tma_load_3d(is + oF, &P.mF[src_map], ix, iy, z0 + g, bar);
+                tma_load_3d(is + oF2, &P.mF2[src_map], ix, iy, z0 + g, bar);
             }
             if (relax) tma_load_3d(is + oM, &P.mM, ix, iy, z0 + g, bar);
         };
@@ -355,13 +358,13 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             }
             if (g >= Nz) return;
             tma_prefetch_3d(&P.mU, cx, iy, z0 + g);
-            tma_prefetch_3d(&P.mV, ix, iy, z0 + g);
+            if (!FLATY) tma_prefetch_3d(&P.mV, ix, iy, z0 + g);
             tma_prefetch_3d(&P.mW, ix, iy, z0 + g);
             if (use_G) {
 #pragma unroll
                 for (int s = 0; s < NSUB; ++s) tma_prefetch_4d(&P.mG, ix, iy, z0 + g, item.tracer_c + s);
             }
-            if (item_var) { tma_prefetch_3d(&P.mF[item.src], ix, iy, z0 + g); tma_prefetch_3d(&P.mF2[item.src], ix, iy, z0 + g); }
+            if (item_var) { tma_prefetch_3d(&P.mF[src_map], ix, iy, z0 + g); tma_prefetch_3d(&P.mF2[src_map], ix, iy, z0 + g); }
         };
         if (kind == 3) {
             mbar_expect_tx(barP, 6u * NSUB * CTP_B);
@@ -369,14 +372,15 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             for (int g = 0; g < ZT_D; ++g) issue_group(g);
         }
         __syncwarp();
-        const bool face_lane = kind == 1 || kind == 2;
+        const bool face_lane = (kind == 1 && !FLATY) || kind == 2;
         const unsigned aT = sbase + oC + 8u * (sub * SM::CTP + (ty + 3) * ZT_CW + tx + ZT_HX);
         const unsigned aQ = sbase + (kind == 1 ? oV + 8u * (ty * 32 + tx) : oU + 8u * (ty * ZT_CW + tx + ZT_HX));
         const unsigned aF = sbase + (kind == 1 ? oFY + 8u * (sub * SM::VT + ty * 32 + tx)
                                                : oFX + 8u * (sub * SM::CTP + (ty + 3) * ZT_CW + tx + ZT_HX));
         // scheme of this lane's face (lower order next to the walls of a Bounded axis)
         const int h_order = kind == 1 ? zt_face_order(L.goff[1] + j0 + ty + 1, L.NG[1], L.topo[1] == LFB_BOUNDED)
-                                      : zt_face_order(L.goff[0] + i0 + tx + 1, L.NG[0], L.topo[0] == LFB_BOUNDED);
+                            : FLATY ? zt_face_order(32 * (j0 + ty) + tx + 1, S.fold_nx, L.topo[0] == LFB_BOUNDED)
+                                    : zt_face_order(L.goff[0] + i0 + tx + 1, L.NG[0], L.topo[0] == LFB_BOUNDED);
         // ---- side job: the velocities of the NEXT stage time (S.pf), for the elements the next stage's tiles read ----
         // Work units of a tile plane, one 128-bit access per lane (two doubles), two rows per warp instruction:
         //   units 0 .. 3 TY/2 - 1   rows (2r, 2r + 1) of the tile in u, v, w
@@ -491,7 +495,8 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     const unsigned a32 = sbase + 8u * t, a32s = a32 + sub * VT_B;
     const unsigned a40 = sbase + 8u * (ty * ZT_CW + tx + ZT_HX), a40s = a40 + 3 * ROW_B + sub * CTP_B;
     const int partner_off = NSUB == 2 ? (sub ? -(int)CTP_B : (int)CTP_B) : 0;
-    const bool active = j0 + ty < j1 && i0 + tx < L.N[0];         // partial tiles at the end of the y range / of x
+    // partial tiles at the end of the y range / of x (folded form: the last row of 32 cells may be partial)
+    const bool active = j0 + ty < j1 && (FLATY ? 32 * (j0 + ty) + tx < S.fold_nx : i0 + tx < L.N[0]);
     const int64_t plane_b = L.plane * 8;                             // byte stride between planes
     // rows beyond j1 / columns beyond Nx (partial tiles) compute like the others but store into the scratch field
     const int64_t cell0 = L.at(i0 + tx, j0 + ty, 0);
@@ -507,10 +512,13 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         }
     }
     // scheme of the west / south face of this column, and (block-uniform) whether any face of the tile is next to a wall
-    const int ox = zt_face_order(L.goff[0] + i0 + tx + 1, L.NG[0], L.topo[0] == LFB_BOUNDED);
-    const int oy = zt_face_order(L.goff[1] + j0 + ty + 1, L.NG[1], L.topo[1] == LFB_BOUNDED);
-    const bool tile_walls = (L.topo[0] == LFB_BOUNDED && (L.goff[0] + i0 < 3 || L.goff[0] + i0 + ZT_TX + 1 >= L.NG[0] - 1)) ||
-                            (L.topo[1] == LFB_BOUNDED && (L.goff[1] + j0 < 3 || L.goff[1] + j0 + TY + 1 >= L.NG[1] - 1));
+    // (folded form: the real column of this thread is 32 (j0 + ty) + tx)
+    const int ox = FLATY ? zt_face_order(32 * (j0 + ty) + tx + 1, S.fold_nx, L.topo[0] == LFB_BOUNDED)
+                         : zt_face_order(L.goff[0] + i0 + tx + 1, L.NG[0], L.topo[0] == LFB_BOUNDED);
+    const int oy = FLATY ? 5 : zt_face_order(L.goff[1] + j0 + ty + 1, L.NG[1], L.topo[1] == LFB_BOUNDED);
+    const bool tile_walls = FLATY ? (L.topo[0] == LFB_BOUNDED && (j0 == 0 || 32 * (j0 + TY) + 1 >= S.fold_nx - 1))
+                                  : ((L.topo[0] == LFB_BOUNDED && (L.goff[0] + i0 < 3 || L.goff[0] + i0 + ZT_TX + 1 >= L.NG[0] - 1)) ||
+                                     (L.topo[1] == LFB_BOUNDED && (L.goff[1] + j0 < 3 || L.goff[1] + j0 + TY + 1 >= L.NG[1] - 1)));
     // block-uniform: does any column of this tile have a periodic image?
     const bool tile_wraps = (L.fuse_halo[0] && (i0 < L.H[0] || i0 + ZT_TX > L.N[0] - L.H[0])) ||
                             (L.fuse_halo[1] && (j0 < L.H[1] || j0 + TY > L.N[1] - L.H[1]));
@@ -524,7 +532,12 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         const double c = item.c, d = item.d, n2 = c * c + d * d;
         k_own = -c;
         k_oth = NSUB == 1 ? 0.0 : (sub == 0 ? -d : d);
-        if (item.is_map) {
+        if (flat_v) {
+            // the cell-centred v at the stage time = the linear interpolation of its two bracketing snapshots
+            const double coef = S.vsign * ((NSUB == 2 && sub == 1) ? -d / n2 : -c / n2);
+            kA = coef * S.var_w1; kB = coef * S.var_w2;
+            aS1 = a32 + oF; aS2 = a32 + oF2;
+        } else if (item.is_map) {
             kA = kB = 0.5 * ((NSUB == 2 && sub == 1) ? -d / n2 : -c / n2);
             if (item.src == 0)      { aS1 = a40 + oU; aS2 = aS1 + 8; }
             else if (item.src == 1) { aS1 = a32 + oV; aS2 = aS1 + 8 * 32; }
@@ -545,8 +558,8 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         else if (sub == 0) kq = item.is_map ? (d * d - c * c) / (n2 * n2) : c / n2;
         else               kq = item.is_map ? (-2.0 * c * d) / (n2 * n2) : d / n2;
         sts(aRX, kq);
-        sts(aRX + 8, item.is_map ? 0.5 : S.var_w1);
-        sts(aRX + 16, item.is_map ? 0.5 : S.var_w2);
+        sts(aRX + 8, flat_v ? S.vsign * S.var_w1 : item.is_map ? 0.5 : S.var_w1);
+        sts(aRX + 16, flat_v ? S.vsign * S.var_w2 : item.is_map ? 0.5 : S.var_w2);
         sts(aRX + 24, 1.0 / S.relax_timescale);
     }
     const double dtg = S.dt * S.gamma, dtz = S.dt * S.zeta;
@@ -591,18 +604,18 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         const unsigned is = (unsigned)(kk & (ZT_RI - 1)) * ISLOT_B;
         const unsigned fb = (unsigned)(kk & (ZT_RI - 1)) * FBUF_B;
         const unsigned aCk = a40s + oC + (unsigned)((kk + 2) & (ZT_RC - 1)) * CSLOT_B;
-        const double cu = lds(a40 + oU + is), cv = lds(a32 + oV + is);
+        const double cu = lds(a40 + oU + is), cv = FLATY ? 0.0 : lds(a32 + oV + is);
         const double cw = lds(a32 + oW + NT_B + is);
         if (!FAST && k == 0) wb = lds(a32 + oW + is);
-        double fx = zt_face<8>(aCk, cu, K), fy = zt_face<ROW_B>(aCk, cv, K);
+        double fx = zt_face<8>(aCk, cu, K), fy = FLATY ? 0.0 : zt_face<ROW_B>(aCk, cv, K);
         if (WALLS && tile_walls) {                        // buffer schemes next to the walls of Bounded x / y axes
             if (ox != 5) fx = zt_face_buffer<8>(aCk, cu, ox);
-            if (oy != 5) fy = zt_face_buffer<ROW_B>(aCk, cv, oy);
+            if (!FLATY && oy != 5) fy = zt_face_buffer<ROW_B>(aCk, cv, oy);
         }
         const double Fw = cu * fx;
         const double Fs = cv * fy;
         sts(a40s + oFX + fb, Fw);
-        sts(a32s + oFY + fb, Fs);
+        if (!FLATY) sts(a32s + oFY + fb, Fs);
         if (!FAST && k == 0) {
             if (zper) {
                 // Periodic z: the bottom face of cell 0 is a WENO5 face between cells -1 and 0 (c[-1] = c[0] - d[-1])
@@ -624,13 +637,14 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         }
         const double Ft = cw * ct;
         // ---- own part of the tendency: c du - dF per axis in units of face velocity, forcing, G^- part of the substep ----
-        const double ue = lds(a40 + oU + is + 8), vn = lds(a32 + oV + is + 8 * 32);
+        const double ue = lds(a40 + oU + is + 8), vn = FLATY ? 0.0 : lds(a32 + oV + is + 8 * 32);
         const double sA = lds(aS1 + is), sB = lds(aS2 + is);
         double forcing = fma(kA, sA, fma(kB, sB, k_own * ck));
         if (relax) forcing = fma(lds(a32 + oM + is) * lds(aRX + 24), fma(lds(aRX), fma(lds(aRX + 8), sA, lds(aRX + 16) * sB), -ck), forcing);
         if (NSUB == 2) forcing = fma(k_oth, lds(aCk + partner_off), forcing);
         const double az = fma(ck, cw - wb, Fb - Ft);
-        part[p] = fma(rdx, fma(ck, ue - cu, Fw), fma(rdy, fma(ck, vn - cv, Fs), fma(rdz, az, forcing)));
+        part[p] = FLATY ? fma(rdx, fma(ck, ue - cu, Fw), fma(rdz, az, forcing))
+                        : fma(rdx, fma(ck, ue - cu, Fw), fma(rdy, fma(ck, vn - cv, Fs), fma(rdz, az, forcing)));
         base[p] = S.first_stage ? ck : fma(dtz, lds(a32s + oG + is), ck);
         // ---- advance the window to cell k+1: d[k+3] = c[k+4] - c[k+3] from the ring ----
         {
@@ -657,8 +671,10 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         constexpr int J = decltype(jtag)::value;
         const int kk = J >= 0 ? 2 + J : k;
         const unsigned fb = (unsigned)(kk & (ZT_RI - 1)) * FBUF_B;
-        const double Fe = lds(a40s + oFX + fb + 8), Fn = lds(a32s + oFY + fb + 8 * 32);
-        const double Gn = fma(nrdx, Fe, fma(nrdy, Fn, part[p]));
+        const double Fe = lds(a40s + oFX + fb + 8);
+        double Gn;
+        if (FLATY) Gn = fma(nrdx, Fe, part[p]);
+        else { const double Fn = lds(a32s + oFY + fb + 8 * 32); Gn = fma(nrdx, Fe, fma(nrdy, Fn, part[p])); }
         const double unew = fma(dtg, Gn, base[p]);
         pUn[0] = unew;
         if (S.store_G) pUn[g_off] = Gn;
@@ -743,14 +759,18 @@ static zt_encode_fn zt_encoder()
     return fn;
 }
 
-// tensor map over one field (rank 3) or a stack of n fields (rank 4) in the padded layout L, box bx x by x bz (x 1)
-static int zt_make_map(CUtensorMap *m, const LfbLayout &L, const void *base, int n_stack, int bx, int by, int bz = 1)
+// tensor map over one field (rank 3) or a stack of n fields (rank 4) in the padded layout L, box bx x by x bz (x 1).
+// fold_rows > 0: the folded view of a grid with a Flat y axis -- rows of 32 cells whose haloed tiles (40 cells) overlap
+// in memory (row stride 32 < inner extent 40; profiles/microbench/tma_overlap.cu), fold_rows rows per plane; rows outside
+// are zero-filled by the TMA unit.
+static int zt_make_map(CUtensorMap *m, const LfbLayout &L, const void *base, int n_stack, int bx, int by, int bz = 1, int fold_rows = 0)
 {
     zt_encode_fn enc = zt_encoder();
     if (!enc) return -1;
     const cuuint32_t rank = n_stack > 0 ? 4 : 3;
     cuuint64_t dim[4] = {(cuuint64_t)L.pitch, (cuuint64_t)L.rows, (cuuint64_t)L.planes, (cuuint64_t)(n_stack > 0 ? n_stack : 1)};
     cuuint64_t str[3] = {(cuuint64_t)L.pitch * 8, (cuuint64_t)L.plane * 8, (cuuint64_t)L.len * 8};
+    if (fold_rows > 0) { dim[0] = ZT_CW; dim[1] = (cuuint64_t)fold_rows; }
     cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, const_cast<void *>(base), dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -758,22 +778,31 @@ static int zt_make_map(CUtensorMap *m, const LfbLayout &L, const void *base, int
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+// Can the z-march kernel run the grid folded (Flat y)?  Periodic or Bounded x; the pitch-40 tile of the last row of 32
+// cells must stay inside the plane.
+static bool zt_foldable(const LfbLayout &L)
+{
+    return L.topo[1] == LFB_FLAT && L.topo[0] != LFB_FLAT && L.topo[2] != LFB_FLAT && L.H[0] >= 3 && L.xoff == LFB_XPAD &&
+           L.plane % 32 == 0 && (int64_t)32 * ((L.N[0] + 31) / 32) + 24 <= L.plane;
+}
+
 extern "C" int lfb_ztma_supported(const LfbStageParams *P)
 {
     const LfbLayout &L = P->L;
     if (P->advect != LFB_ADVECTION_WENO5 || P->imm || (P->relax && !P->mask)) return 0;
-    if (L.topo[0] == LFB_FLAT || L.topo[1] == LFB_FLAT || L.topo[2] == LFB_FLAT) return 0;
+    const bool fold = zt_foldable(L);
+    if (!fold && (L.topo[0] == LFB_FLAT || L.topo[1] == LFB_FLAT || L.topo[2] == LFB_FLAT)) return 0;
     if (L.topo[2] == LFB_PERIODIC && L.N[2] < 2 * L.H[2]) return 0;
     if (!(P->vel_present[0] || P->vel_present[1] || P->vel_present[2])) return 0;     // absent components: a zero field
-    if (L.N[0] < 8 || L.N[1] < 4 || L.N[2] < 8) return 0;
-    if (L.H[0] < 3 || L.H[1] < 3 || L.H[2] < 3) return 0;
+    if (L.N[0] < 8 || (!fold && L.N[1] < 4) || L.N[2] < 8) return 0;
+    if (L.H[0] < 3 || (!fold && L.H[1] < 3) || L.H[2] < 3) return 0;
     if (!zt_encoder()) return 0;
-    return 1;
+    return fold ? 2 : 1;
 }
 
 extern "C" int lfb_ztma_tile_rows(void) { return ZT_TY; }
 
-template <int NSUB, int TY, bool WALLS>
+template <int NSUB, int TY, bool WALLS, bool FLATY>
 static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
 {
     using SM = ZtSmem<NSUB, TY>;
@@ -782,37 +811,61 @@ static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(lfb_stage_ztma<NSUB, TY, WALLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES);
+        cudaError_t e = cudaFuncSetAttribute(lfb_stage_ztma<NSUB, TY, WALLS, FLATY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::BYTES);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     LfbZtParams P;
     memset(&P, 0, sizeof(P));
     P.S = *S;
-    const LfbLayout &L = S->L;
+    LfbStageParams &SS = P.S;
+    int fold_rows = 0;
+    if (FLATY) {
+        // the folded view: rows of 32 cells, row pitch 32, every pointer moved so that interior column 0 sits at
+        // column ZT_HX of the view (element (i, j, k) of the view = real cell (32 j + i, 0, k))
+        LfbLayout &F = SS.L;
+        const LfbLayout &R = S->L;
+        fold_rows = (R.N[0] + 31) / 32;
+        SS.fold = 1; SS.fold_nx = R.N[0];
+        F.N[0] = 32; F.N[1] = fold_rows; F.NG[0] = 32; F.NG[1] = fold_rows; F.goff[0] = F.goff[1] = 0;
+        F.H[1] = 0; F.topo[1] = LFB_PERIODIC;
+        F.xoff = ZT_HX; F.pitch = 32; F.rows = (int)(R.plane / 32); F.stride[1] = 32;
+        F.fuse_halo[0] = F.fuse_halo[1] = 0;
+        const int64_t shift = R.xoff - ZT_HX;
+        auto mv = [&](const double *p) { return p ? p + shift : p; };
+        SS.U_old = mv(S->U_old); SS.U_new = const_cast<double *>(mv(S->U_new)); SS.G = const_cast<double *>(mv(S->G));
+        SS.scratch = const_cast<double *>(mv(S->scratch)); SS.mask = mv(S->mask);
+        for (int a = 0; a < 3; ++a) {
+            SS.vel[a] = mv(S->vel[a]);
+            SS.pf.s1[a] = mv(S->pf.s1[a]); SS.pf.s2[a] = mv(S->pf.s2[a]); SS.pf.dst[a] = const_cast<double *>(mv(S->pf.dst[a]));
+        }
+        SS.pf.dst[1] = nullptr;                                   // v is not advected with on a Flat y axis
+        for (int q = 0; q < LFB_MAX_VARS; ++q) { SS.var[q] = mv(S->var[q]); SS.var2[q] = mv(S->var2[q]); }
+        SS.j0 = 0; SS.j1 = fold_rows; SS.jb0 = SS.jb1 = 0;
+    }
+    const LfbLayout &L = SS.L;
     int n_t = 0;
     for (int q = 0; q < S->n_items; ++q) n_t = S->items[q].tracer_c + NSUB > n_t ? S->items[q].tracer_c + NSUB : n_t;
     int bad = 0;
-    bad |= zt_make_map(&P.mC, L, S->U_old, n_t, ZT_CW, TY + 6);
-    bad |= zt_make_map(&P.mG, L, S->G, n_t, 32, TY);
-    bad |= zt_make_map(&P.mU, L, S->vel[0], 0, ZT_CW, TY);
-    bad |= zt_make_map(&P.mV, L, S->vel[1], 0, 32, TY + 1);
-    bad |= zt_make_map(&P.mW, L, S->vel[2], 0, 32, TY, 2);
-    LfbStageParams &SS = P.S;
+    bad |= zt_make_map(&P.mC, L, SS.U_old, n_t, ZT_CW, TY + 6, 1, fold_rows);
+    bad |= zt_make_map(&P.mG, L, SS.G, n_t, 32, TY, 1, fold_rows);
+    bad |= zt_make_map(&P.mU, L, SS.vel[0], 0, ZT_CW, TY, 1, fold_rows);
+    if (!FLATY) bad |= zt_make_map(&P.mV, L, SS.vel[1], 0, 32, TY + 1);
+    bad |= zt_make_map(&P.mW, L, SS.vel[2], 0, 32, TY, 2, fold_rows);
     if (!SS.var_fused) { SS.var_w1 = 1.0; SS.var_w2 = 0.0; }         // inputs already interpolated: one source
     for (int q = 0; q < LFB_MAX_VARS; ++q)
-        if (S->var[q]) {
-            bad |= zt_make_map(&P.mF[q], L, S->var[q], 0, 32, TY);
-            bad |= zt_make_map(&P.mF2[q], L, S->var_fused ? S->var2[q] : S->var[q], 0, 32, TY);
+        if (SS.var[q]) {
+            bad |= zt_make_map(&P.mF[q], L, SS.var[q], 0, 32, TY, 1, fold_rows);
+            bad |= zt_make_map(&P.mF2[q], L, SS.var_fused ? SS.var2[q] : SS.var[q], 0, 32, TY, 1, fold_rows);
         }
-    if (S->relax) bad |= zt_make_map(&P.mM, L, S->mask, 0, 32, TY);
+    if (S->relax) bad |= zt_make_map(&P.mM, L, SS.mask, 0, 32, TY, 1, fold_rows);
     if (bad) return cudaErrorInvalidValue;
     P.k133 = 13.0 / 3.0; P.k13 = 1.0 / 3.0; P.k16 = 1.0 / 6.0; P.eps43 = LFB_WENO_EPS * (4.0 / 3.0);
     for (int a = 0; a < 3; ++a) P.rd[a] = S->area[a] / S->volume;
-    P.scratch = S->scratch;
-    const int ytiles = (S->j1 - S->j0 + TY - 1) / TY + (S->jb1 > S->jb0 ? (S->jb1 - S->jb0 + TY - 1) / TY : 0);
+    P.scratch = SS.scratch;
+    const int ytiles = (SS.j1 - SS.j0 + TY - 1) / TY + (SS.jb1 > SS.jb0 ? (SS.jb1 - SS.jb0 + TY - 1) / TY : 0);
     dim3 grid(S->n_items * ytiles, (L.N[0] + ZT_TX - 1) / ZT_TX, 1);
-    lfb_stage_ztma<NSUB, TY, WALLS><<<grid, SM::THREADS, SM::BYTES, stream>>>(P);
+    lfb_stage_ztma<NSUB, TY, WALLS, FLATY><<<grid, SM::THREADS, SM::BYTES, stream>>>(P);
     return cudaGetLastError();
 }
 
@@ -820,6 +873,10 @@ extern "C" cudaError_t lfb_launch_stage_ztma(const LfbStageParams *P, cudaStream
 {
     if (P->j1 <= P->j0) return cudaSuccess;
     const bool walls = P->L.topo[0] == LFB_BOUNDED || P->L.topo[1] == LFB_BOUNDED || P->L.topo[2] == LFB_PERIODIC || P->relax;   // the general instantiation
-    if (walls) return P->single_exp ? zt_launch<1, ZT_TY, true>(P, stream) : zt_launch<2, ZT_TY, true>(P, stream);
-    return P->single_exp ? zt_launch<1, ZT_TY, false>(P, stream) : zt_launch<2, ZT_TY, false>(P, stream);
+    if (P->fold) {
+        if (walls) return P->single_exp ? zt_launch<1, ZT_TY, true, true>(P, stream) : zt_launch<2, ZT_TY, true, true>(P, stream);
+        return P->single_exp ? zt_launch<1, ZT_TY, false, true>(P, stream) : zt_launch<2, ZT_TY, false, true>(P, stream);
+    }
+    if (walls) return P->single_exp ? zt_launch<1, ZT_TY, true, false>(P, stream) : zt_launch<2, ZT_TY, true, false>(P, stream);
+    return P->single_exp ? zt_launch<1, ZT_TY, false, false>(P, stream) : zt_launch<2, ZT_TY, false, false>(P, stream);
 }

@@ -423,6 +423,41 @@ def test_ztma_with_absent_velocity_component(vel_names):
     m.close(); o.close()
 
 
+@pytest.mark.parametrize("size,topology,var_names,vel_names,N,backward,relax", [
+    ((10, 10), ("Periodic", "Flat", "Bounded"), ("b",), ("u", "w"), 2, False, False),           # the golden case's shape: one partial row
+    ((400, 80), ("Periodic", "Flat", "Bounded"), ("T", "b"), ("u", "w", "v"), 2, False, False),   # BASELINE config 1 (v forces xi_v only)
+    ((100, 100), ("Periodic", "Flat", "Bounded"), ("T", "b"), ("u", "w"), 4, True, False),         # lee-wave shape, backward pass
+    ((70, 24), ("Periodic", "Flat", "Bounded"), ("b",), ("u", "w"), 1, True, False),               # partial last row, single exponential
+    ((45, 16), ("Periodic", "Flat", "Bounded"), ("b",), ("w", "v"), 2, False, False),              # odd Nx (no side-job prefetch), u absent
+    ((96, 20), ("Bounded", "Flat", "Bounded"), ("T",), ("u", "w"), 2, False, False),               # walls in x
+    ((64, 16), ("Periodic", "Flat", "Periodic"), ("b",), ("u", "w", "v"), 2, True, False),         # Periodic z, v on the Flat axis, backward
+    ((80, 24), ("Bounded", "Flat", "Bounded"), ("b",), ("u", "w", "v"), 2, False, True),           # boundary relaxation
+])
+def test_ztma_folded_2d_grids_vs_oracle(size, topology, var_names, vel_names, N, backward, relax):
+    """Grids with a Flat y axis (every 2-D example of the reference) on the TMA z-march kernel: the x line is folded
+    into rows of 32 cells read through overlapping tensor-map rows (profiles/microbench/tma_overlap.cu), y faces are
+    skipped, a v component only forces its xi_v map.  Against the CPU oracle on the same inputs."""
+    g = lfb200.RectilinearGrid(size=size, extent=tuple(float(s) for s in size), topology=topology)
+    times = [0.0, 0.5, 1.0]
+    fields = make_series(g, times, var_names=var_names, velocity_names=vel_names, T_period=2.0)
+    fp = lfb200.set_offline_BW2_filter_params(N=N, freq_c=2 * np.pi / 2.0)
+    kw = {}
+    if relax:
+        x, z = g.nodes(0)[:, None, None], g.nodes(2)[None, None, :]
+        kw = dict(relax_timescale=0.7, mask=np.asfortranarray(np.exp(-((x - g.origin[0]) / 6.0) ** 2) + 0.1 * np.cos(z) ** 2))
+    o, m = make_pair(g, var_names, vel_names, fp, times, fields, kernel="auto", backward=backward, **kw)
+    assert m.kernel_name == "ztma"
+    names = oracle_names(var_names, vel_names, fp)
+    o.init_from_data(); m.init_from_data()
+    for dt in (0.1, 0.1, 0.05, 0.25, 0.2, 0.3):
+        o.step(dt); m.step(dt)
+    compare_state(o, m, names, TOL_STEP)
+    # tendencies of the final state (generic kernel on the same handle) agree too
+    o.update_state()
+    assert rel_l2(m.tendency(names[0])[3:-3, :, 3:-3], o.tendency(0)[3:-3, :, 3:-3]) < 1e-10
+    m.close(); o.close()
+
+
 def test_zmarch_matches_generic_on_larger_grid():
     g = lfb200.RectilinearGrid(size=(128, 64, 40), extent=(128.0, 64.0, 40.0), topology=("Periodic", "Periodic", "Bounded"))
     var_names, vel_names = ("T", "b"), ("u", "v", "w")
