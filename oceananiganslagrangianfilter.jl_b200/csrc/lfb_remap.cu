@@ -297,10 +297,15 @@ __device__ __forceinline__ void remap3_locate_node(const Remap3Params &P, const 
     // circumsphere of the tetrahedron found: the Delaunay tetrahedron that contains the node is the unique one with an
     // empty circumsphere, so a result that passes is the result of the full search.  Otherwise (rare) the next pass
     // searches the next larger patch, the last one the full patch.
+    // first patch: the cells a vertex of the enclosing tetrahedron normally comes from (displacement + 1 cell); second:
+    // half way to the full patch
+    const int f0 = min(r0, (int)ceil(P.ax[0].maxdisp) + 1), f1 = min(r1, (int)ceil(P.ax[1].maxdisp) + 1), f2 = min(r2, (int)ceil(P.ax[2].maxdisp) + 1);
     for (int pass = 0; pass < 3 && !found; ++pass) {
-        const int shrink = 2 - pass;
-        const int R0 = max(1, r0 - shrink), R1 = max(1, r1 - shrink), R2 = max(1, r2 - shrink);
-        if (pass < 2 && R0 == max(1, r0 - shrink + 1) && R1 == max(1, r1 - shrink + 1) && R2 == max(1, r2 - shrink + 1)) continue;
+        const int R0 = pass == 0 ? f0 : pass == 1 ? (f0 + r0 + 1) / 2 : r0;
+        const int R1 = pass == 0 ? f1 : pass == 1 ? (f1 + r1 + 1) / 2 : r1;
+        const int R2 = pass == 0 ? f2 : pass == 1 ? (f2 + r2 + 1) / 2 : r2;
+        if (pass == 0 && R0 == r0 && R1 == r1 && R2 == r2) continue;                       // nothing smaller to try
+        if (pass == 1 && ((R0 == f0 && R1 == f1 && R2 == f2) || (R0 == r0 && R1 == r1 && R2 == r2))) continue;
         // a: nearest data point to the node
         double best = INFINITY;
         bool have = false;
@@ -461,11 +466,10 @@ __global__ void lfb_remap3d_locate(const Remap3Params P, const double *__restric
     remap3_locate_node(P, src, i0, i1, i2, tet, wgt, too_small);
 }
 
-// The same with the patch of a block of 32 x R3_BY nodes staged once in shared memory (normalised positions of every
+// The same with the patch of a block of 32 x BY nodes staged once in shared memory (normalised positions of every
 // lattice neighbour any node of the block can reach; x = +inf marks an image the cloud does not hold), so a candidate
 // costs three shared-memory loads instead of three global loads, a wrap, a floor and three divisions.
 #define R3_BX 32
-#define R3_BY 4
 struct Src3Shared {
     const double *px, *py, *pz;
     int b0, b1, b2, e0, e1;          // lattice offset of patch entry 0 and the patch extents in x, y
@@ -479,6 +483,7 @@ struct Src3Shared {
     }
 };
 
+template <int R3_BY>
 __global__ void __launch_bounds__(R3_BX * R3_BY) lfb_remap3d_locate_smem(const Remap3Params P, const double *__restrict__ xi0,
                                                                         const double *__restrict__ xi1, const double *__restrict__ xi2,
                                                                         int64_t *__restrict__ tet, double *__restrict__ wgt,
@@ -644,11 +649,20 @@ static int remap3(const lfb_remap_desc *D, const double *const *xi, int n_fields
     for (int attempt = 0; attempt < 3 && flag; ++attempt) {
         for (int a = 0; a < 3; ++a) P.ax[a].r = r[a];
         RCU3(cudaMemset(d_flag, 0, sizeof(int)));
-        const size_t patch_bytes = (size_t)(R3_BX + 2 * r[0]) * (R3_BY + 2 * r[1]) * (2 * r[2] + 1) * 3 * sizeof(double);
+        // rows of nodes per block: the more nodes share a staged patch, the less staging per node and the more warps per
+        // SM; 8 rows (256 threads) when that patch fits, else 4
+        auto patch_of = [&](int by) { return (size_t)(R3_BX + 2 * r[0]) * (by + 2 * r[1]) * (2 * r[2] + 1) * 3 * sizeof(double); };
+        const int by = (patch_of(8) <= 200 * 1024 && !getenv("LFB200_REMAP_BY4")) ? 8 : 4;
+        const size_t patch_bytes = patch_of(by);
         if (patch_bytes <= 200 * 1024 && !getenv("LFB200_REMAP_GLOBAL")) {
-            RCU3(cudaFuncSetAttribute(lfb_remap3d_locate_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_bytes));
-            dim3 gs((P.ax[0].n + R3_BX - 1) / R3_BX, (P.ax[1].n + R3_BY - 1) / R3_BY, P.ax[2].n);
-            lfb_remap3d_locate_smem<<<gs, R3_BX * R3_BY, patch_bytes>>>(P, d_xi[0], d_xi[1], d_xi[2], d_tet, d_w, d_flag);
+            dim3 gs((P.ax[0].n + R3_BX - 1) / R3_BX, (P.ax[1].n + by - 1) / by, P.ax[2].n);
+            if (by == 8) {
+                RCU3(cudaFuncSetAttribute(lfb_remap3d_locate_smem<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_bytes));
+                lfb_remap3d_locate_smem<8><<<gs, R3_BX * 8, patch_bytes>>>(P, d_xi[0], d_xi[1], d_xi[2], d_tet, d_w, d_flag);
+            } else {
+                RCU3(cudaFuncSetAttribute(lfb_remap3d_locate_smem<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)patch_bytes));
+                lfb_remap3d_locate_smem<4><<<gs, R3_BX * 4, patch_bytes>>>(P, d_xi[0], d_xi[1], d_xi[2], d_tet, d_w, d_flag);
+            }
         } else {
             lfb_remap3d_locate<<<grid, block>>>(P, d_xi[0], d_xi[1], d_xi[2], d_tet, d_w, d_flag);
         }
