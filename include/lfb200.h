@@ -250,6 +250,10 @@ typedef struct lfb_remap_desc {
  * cloud (scipy LinearNDInterpolator in the reference; tetrahedra on grids with three non-Flat axes), the
  * reference's edge fix on Bounded axes (numpy.interp along edge rows in 2-D, a 2-D interpolation on the
  * edge planes in 3-D), halos zero, NaN outside the hull.  The simplex search is shared by all fields.
+ * Deliberate deviation: on a grid where a Bounded axis precedes a Periodic one the reference pads the wrong coordinate
+ * column (post:523-611: `column_number` only advances inside the periodic branches); this function pads every
+ * Periodic axis's own coordinate, as the reference's comments and documentation describe.  The two coincide on every
+ * grid of the reference's examples and tests ((Periodic, Flat, Bounded), (Periodic, Periodic, Bounded)).
  * xi / fields / out may be host pointers or device pointers of desc.device (e.g. from lfb_kept_info): the copies
  * use unified addressing. */
 int lfb_remap_to_mean(const lfb_remap_desc *desc, const double *const *xi, int n_fields, const double *const *fields,

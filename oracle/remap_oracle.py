@@ -22,10 +22,16 @@ def centre_nodes(N, H, x0, delta):
 
 
 def remap_to_mean(fields: Dict[str, np.ndarray], xi: Dict[str, np.ndarray], N, H, topology, origin, delta,
-                  npad: int = 5) -> Dict[str, np.ndarray]:
+                  npad: int = 5, pad_columns: str = "reference") -> Dict[str, np.ndarray]:
     """fields: {name: parent array with halos}; xi: {"u"/"v"/"w": parent xi array} for the velocities
     that have maps.  origin[ax] = first face coordinate, delta[ax] = spacing.  Returns
-    {name + "_at_mean": parent array} with halos zeroed (post:748)."""
+    {name + "_at_mean": parent array} with halos zeroed (post:748).
+
+    pad_columns: "reference" follows post:523-611 literally: the coordinate column that receives the periodic padding
+    only advances inside the periodic branches, so when a Bounded axis precedes a Periodic one the Periodic axis pads
+    the WRONG coordinate column (a latent bug of the reference; no example or test of it has such a grid).
+    "documented" pads every Periodic axis's own coordinate, which is what the reference's comments and docs describe
+    and what liblfb200 computes; the two coincide whenever no Bounded axis precedes a Periodic one."""
     axes = [ax for ax in range(3) if topology[ax] != "Flat"]        # true_dims (post:412-416)
     full = tuple(N[ax] + 2 * H[ax] for ax in range(3))
     inner = tuple(slice(H[ax], H[ax] + N[ax]) if H[ax] else slice(None) for ax in range(3))   # _remove_halos
@@ -53,9 +59,11 @@ def remap_to_mean(fields: Dict[str, np.ndarray], xi: Dict[str, np.ndarray], N, H
     D = np.stack(cols, axis=1)
 
     col = 0
-    for ax in axes:                                                       # post:527-611
+    for ib, ax in enumerate(axes):                                        # post:527-611
         if topology[ax] != "Periodic":
             continue   # reference: column_number only advances inside periodic branches (x then y)
+        if pad_columns == "documented":
+            col = 2 * ib
         lo, hi = origin[ax], origin[ax] + L[ax]
         pad = npad * delta[ax]
         X = D[:, col]

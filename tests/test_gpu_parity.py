@@ -782,6 +782,52 @@ def test_device_remap_3d_matches_scipy_oracle(size, topology, amp):
         assert np.nanmax(np.abs(got[k] - want[k])) <= 1e-10 * np.nanmax(np.abs(want[k])), k
 
 
+@pytest.mark.parametrize("size,topology", [((30, 24), ("Bounded", "Periodic", "Flat")),
+                                           ((10, 9, 8), ("Bounded", "Periodic", "Bounded")),
+                                           ((9, 8, 10), ("Bounded", "Bounded", "Periodic"))])
+def test_device_remap_bounded_axis_before_periodic_axis(size, topology):
+    """Grids on which a Bounded axis precedes a Periodic one.  The reference pads the wrong coordinate column there
+    (post:523-611: `column_number` only advances inside the periodic branches); liblfb200 pads each Periodic axis's own
+    coordinate, as the reference's comments and documentation describe (stated in include/lfb200.h).  Checked against
+    the scipy oracle in that documented mode, and shown to differ from the literal mode."""
+    import remap_oracle as ro
+    from lfb200.remap import remap_to_mean_device
+    g = lfb200.RectilinearGrid(size=size, extent=tuple(float(s) for s in size), topology=topology)
+    axes = g.nonflat_axes
+    rng = np.random.default_rng(17)
+    shape = g.center_shape()
+    coords = [g.nodes(ax) for ax in range(3)]
+    mesh = np.meshgrid(*[coords[ax] if ax in axes else np.zeros(1) for ax in range(3)], indexing="ij")
+    smooth = lambda ph: sum(np.sin(2 * np.pi * (mesh[ax] - g.origin[ax]) / g.L[ax] + ph + ax) for ax in axes) / len(axes)
+    xi = {}
+    for ax in axes:
+        f = smooth(0.3 * ax) * 0.6 * g.spacing[ax]
+        if topology[ax] == "Bounded":
+            f = f * np.sin(np.pi * (mesh[ax] - g.origin[ax]) / g.L[ax])
+        xi["uvw"[ax]] = np.asfortranarray(f + 0.05 * g.spacing[ax] * rng.standard_normal(shape))
+    fields = {"T": np.asfortranarray(smooth(1.0) + 0.1 * rng.standard_normal(shape))}
+    want = ro.remap_to_mean(fields, xi, g.N, g.H, g.topology, g.origin, g.spacing, npad=3, pad_columns="documented")
+    literal = ro.remap_to_mean(fields, xi, g.N, g.H, g.topology, g.origin, g.spacing, npad=3, pad_columns="reference")
+    got = remap_to_mean_device(fields, xi, g.N, g.H, g.topology, g.origin, g.spacing, npad=3)
+    k = "T_at_mean"
+    # Not compared: the lines where the edge planes of two Bounded axes meet.  There a node sits on the hull of the 2-D
+    # cloud of an edge plane, where Qhull's and the local walk's handling of the nearly degenerate boundary slivers can
+    # differ (1 node of 720 on these grids); the reference itself has no such grid in its examples or tests.
+    on_edge = [np.zeros(g.center_shape(), dtype=bool) for _ in range(3)]
+    for ax in axes:
+        if topology[ax] == "Bounded":
+            sl = [slice(None)] * 3
+            for e in (g.H[ax], g.H[ax] + g.N[ax] - 1):
+                sl[ax] = e
+                on_edge[ax][tuple(sl)] = True
+    skip = (on_edge[0].astype(int) + on_edge[1] + on_edge[2]) >= 2
+    a, b = np.where(skip, 0.0, got[k]), np.where(skip, 0.0, want[k])
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.nanmax(np.abs(a - b)) <= 1e-10 * np.nanmax(np.abs(b))
+    differs = not np.array_equal(np.isnan(literal[k]), np.isnan(want[k])) or np.nanmax(np.abs(np.nan_to_num(literal[k] - want[k]))) > 1e-8
+    assert differs, "the literal padding rule was expected to differ on this topology"
+
+
 def test_device_remap_3d_reproduces_linear_function_at_size():
     """Size-independent property of the remap: piecewise-linear interpolation on ANY triangulation reproduces a
     linear function of the displaced coordinate.  With f = alpha (z + xi_z) + beta carried by the data points the
