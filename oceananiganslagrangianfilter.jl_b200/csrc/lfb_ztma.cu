@@ -49,6 +49,9 @@
 #ifndef ZT_L2_PROMOTION
 #define ZT_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_L2_128B
 #endif
+#ifndef ZT_PAIR
+#define ZT_PAIR 0         // 1: the cosine and the sine tracer of an item share a main thread (see the main warps); measured slower (-8 %)
+#endif
 #ifndef ZT_PF
 #define ZT_PF 0           // planes an L2 prefetch (cp.async.bulk.prefetch.tensor) runs ahead; 0 = off: measured slower (6: +2 %, 10: +7 %)
 #endif
@@ -89,7 +92,8 @@ struct ZtSmem {
     static constexpr int O_BAR = O_FL + ZT_RI * FBUF;            // ZT_RI group barriers + the prologue barrier
     static constexpr int DOUBLES = O_BAR + 8 + 8;                // + 2 x 4 relaxation coefficients
     static constexpr int BYTES = DOUBLES * 8;
-    static constexpr int NMAIN = NSUB * NT;
+    static constexpr int NS = (ZT_PAIR && NSUB == 2) ? 2 : 1;    // tracers per main thread
+    static constexpr int NMAIN = NSUB * NT / NS;
     static constexpr int THREADS = NMAIN + NSUB * 32 + 32;
     static_assert(NSUB * TY < 32, "east-edge faces and the producer lane share one warp");
     static_assert(CTP % 16 == 0 && NT % 16 == 0 && VT % 16 == 0 && UT % 16 == 0, "TMA destinations must stay 128-byte aligned");
@@ -212,6 +216,26 @@ __device__ __forceinline__ double zt_face(unsigned a, double q, const ZtK &K)
     const unsigned an = left ? a - S : a;
     const double n = lds(an), e = lds(an + step), o = lds(an - step);
     const double f = lds(an + 2 * step), p = lds(an - 2 * step);
+    return n + zt_inc(o - p, n - o, e - n, f - e, K);
+}
+
+// The upwind decision of a face, shared by every tracer advected by the same velocity: byte offset of the upwind cell n
+// relative to the cell on the high side of the face, and the signed stride that walks the stencil in upwind order.
+struct ZtUp { int an, step; };
+template <int S>
+__device__ __forceinline__ ZtUp zt_up(double q)
+{
+    const bool left = zt_positive(q);
+    ZtUp u;
+    u.an = left ? -S : 0; u.step = left ? S : -S;
+    return u;
+}
+template <int S>
+__device__ __forceinline__ double zt_face_up(unsigned a, const ZtUp &u, const ZtK &K)
+{
+    const unsigned an = a + u.an;
+    const double n = lds(an), e = lds(an + u.step), o = lds(an - u.step);
+    const double f = lds(an + 2 * u.step), p = lds(an - 2 * u.step);
     return n + zt_inc(o - p, n - o, e - n, f - e, K);
 }
 
@@ -488,19 +512,28 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         return;
     }
 
-    // ============ main warps: one cell column of one tracer per thread ============
-    const int t = tid % SM::NT, sub = tid / SM::NT;
+    // ============ main warps: one cell column per thread ============
+    // NS tracers per thread.  With ZT_PAIR the cosine and the sine tracer of the item share a thread: they are advected
+    // by the same velocities, so the velocity loads, the upwind decisions and addresses, the mbarrier waits and the
+    // barrier are executed once for both, the partner value of the coupling term is a register, and two independent
+    // FP64 chains per thread cover the FP64 latency with fewer warps.
+    constexpr int NS = SM::NS;
+    const int t = NS == 2 ? tid : tid % SM::NT, sub0 = NS == 2 ? 0 : tid / SM::NT;
     const int tx = t % ZT_TX, ty = t / ZT_TX;
-    // the four address registers: own cell in the pitch-32 / pitch-40 tiles, shared by the tracers or per tracer
-    const unsigned a32 = sbase + 8u * t, a32s = a32 + sub * VT_B;
-    const unsigned a40 = sbase + 8u * (ty * ZT_CW + tx + ZT_HX), a40s = a40 + 3 * ROW_B + sub * CTP_B;
-    const int partner_off = NSUB == 2 ? (sub ? -(int)CTP_B : (int)CTP_B) : 0;
+    // address registers: own cell in the pitch-32 / pitch-40 tiles; the per-tracer tiles sit at constant offsets
+    const unsigned a32 = sbase + 8u * t, a40 = sbase + 8u * (ty * ZT_CW + tx + ZT_HX);
+    const unsigned a32s0 = a32 + sub0 * VT_B, a40s0 = a40 + 3 * ROW_B + sub0 * CTP_B;
+#define A32S(s) (a32s0 + (unsigned)(s) * VT_B)
+#define A40S(s) (a40s0 + (unsigned)(s) * CTP_B)
+    const int partner_off = (NSUB == 2 && NS == 1) ? (sub0 ? -(int)CTP_B : (int)CTP_B) : 0;
     // partial tiles at the end of the y range / of x (folded form: the last row of 32 cells may be partial)
     const bool active = j0 + ty < j1 && (FLATY ? 32 * (j0 + ty) + tx < S.fold_nx : i0 + tx < L.N[0]);
     const int64_t plane_b = L.plane * 8;                             // byte stride between planes
     // rows beyond j1 / columns beyond Nx (partial tiles) compute like the others but store into the scratch field
     const int64_t cell0 = L.at(i0 + tx, j0 + ty, 0);
-    double *__restrict__ pUn = active ? S.U_new + cell0 + (int64_t)(item.tracer_c + sub) * L.len : P.scratch + cell0;
+    double *__restrict__ pUn[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) pUn[s] = active ? S.U_new + cell0 + (int64_t)(item.tracer_c + sub0 + s) * L.len : P.scratch + cell0;
     const int64_t g_off = active ? (S.G - S.U_new) : 0;              // pG = pUn + g_off
     // offsets of this column's periodic images in the halo (0 = none); y only when the y halo is not owned by a neighbour rank
     int64_t xwrap = 0, ywrap = 0;
@@ -526,73 +559,83 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     // are two shared-memory values: the two faces of the cell for a map (kA = kB carry the 1/2 of the face average),
     // the two bracketing snapshots of the variable for a filtered variable (kA, kB = the weights of the linear
     // interpolation in time of update_input_data!, utils:1036-1058)
-    double kA, kB, k_own, k_oth;
+    double kA[NS], kB[NS], k_oth[NS];
+    const double k_own = -item.c;
     unsigned aS1, aS2;
     {
         const double c = item.c, d = item.d, n2 = c * c + d * d;
-        k_own = -c;
-        k_oth = NSUB == 1 ? 0.0 : (sub == 0 ? -d : d);
-        if (flat_v) {
-            // the cell-centred v at the stage time = the linear interpolation of its two bracketing snapshots
-            const double coef = S.vsign * ((NSUB == 2 && sub == 1) ? -d / n2 : -c / n2);
-            kA = coef * S.var_w1; kB = coef * S.var_w2;
-            aS1 = a32 + oF; aS2 = a32 + oF2;
-        } else if (item.is_map) {
-            kA = kB = 0.5 * ((NSUB == 2 && sub == 1) ? -d / n2 : -c / n2);
-            if (item.src == 0)      { aS1 = a40 + oU; aS2 = aS1 + 8; }
-            else if (item.src == 1) { aS1 = a32 + oV; aS2 = aS1 + 8 * 32; }
-            else                    { aS1 = a32 + oW; aS2 = aS1 + NT_B; }
-        } else {
-            kA = sub == 0 ? S.var_w1 : 0.0; kB = sub == 0 ? S.var_w2 : 0.0;
-            aS1 = a32 + oF; aS2 = a32 + oF2;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int sub = sub0 + s;
+            k_oth[s] = NSUB == 1 ? 0.0 : (sub == 0 ? -d : d);
+            if (flat_v) {
+                // the cell-centred v at the stage time = the linear interpolation of its two bracketing snapshots
+                const double coef = S.vsign * ((NSUB == 2 && sub == 1) ? -d / n2 : -c / n2);
+                kA[s] = coef * S.var_w1; kB[s] = coef * S.var_w2;
+            } else if (item.is_map) {
+                kA[s] = kB[s] = 0.5 * ((NSUB == 2 && sub == 1) ? -d / n2 : -c / n2);
+            } else {
+                kA[s] = sub == 0 ? S.var_w1 : 0.0; kB[s] = sub == 0 ? S.var_w2 : 0.0;
+            }
         }
+        if (flat_v || !item.is_map) { aS1 = a32 + oF; aS2 = a32 + oF2; }
+        else if (item.src == 0)     { aS1 = a40 + oU; aS2 = aS1 + 8; }
+        else if (item.src == 1)     { aS1 = a32 + oV; aS2 = aS1 + 8 * 32; }
+        else                        { aS1 = a32 + oW; aS2 = aS1 + NT_B; }
     }
     // boundary relaxation (utils:584-699): forcing += (1 / tau_r) mask (g_eq - g), g_eq = kq * src with
     // src = wA src1 + wB src2 the interpolated variable / the cell-centred velocity.  The four coefficients of a tracer
     // sit in shared memory (behind the mbarriers), so that they cost no registers in the march.
-    const unsigned aRX = sbase + oBAR + 64u + 32u * sub;
+    const unsigned aRX0 = sbase + oBAR + 64u + 32u * sub0;
+#define ARX(s) (aRX0 + 32u * (unsigned)(s))
     if (relax && t == 0) {
         const double c = item.c, d = item.d, n2 = c * c + d * d;
-        double kq;
-        if (NSUB == 1)     kq = item.is_map ? -1.0 / (c * c) : 1.0 / c;
-        else if (sub == 0) kq = item.is_map ? (d * d - c * c) / (n2 * n2) : c / n2;
-        else               kq = item.is_map ? (-2.0 * c * d) / (n2 * n2) : d / n2;
-        sts(aRX, kq);
-        sts(aRX + 8, flat_v ? S.vsign * S.var_w1 : item.is_map ? 0.5 : S.var_w1);
-        sts(aRX + 16, flat_v ? S.vsign * S.var_w2 : item.is_map ? 0.5 : S.var_w2);
-        sts(aRX + 24, 1.0 / S.relax_timescale);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int sub = sub0 + s;
+            double kq;
+            if (NSUB == 1)     kq = item.is_map ? -1.0 / (c * c) : 1.0 / c;
+            else if (sub == 0) kq = item.is_map ? (d * d - c * c) / (n2 * n2) : c / n2;
+            else               kq = item.is_map ? (-2.0 * c * d) / (n2 * n2) : d / n2;
+            sts(ARX(s), kq);
+            sts(ARX(s) + 8, flat_v ? S.vsign * S.var_w1 : item.is_map ? 0.5 : S.var_w1);
+            sts(ARX(s) + 16, flat_v ? S.vsign * S.var_w2 : item.is_map ? 0.5 : S.var_w2);
+            sts(ARX(s) + 24, 1.0 / S.relax_timescale);
+        }
     }
     const double dtg = S.dt * S.gamma, dtz = S.dt * S.zeta;
     const double rdx = P.rd[0], rdy = P.rd[1], rdz = P.rd[2];
     const double nrdx = -rdx, nrdy = -rdy;
 
     // ---- prologue: the z window of the column -------------------------------------------------------------
-    double d0, d1, d2, d3, d4;                   // d[k-2..k+2], d[m] = c[m+1] - c[m]
-    double Qa, Qb, Qc, Qd;                       // Q[k-1..k+2], Q[m] = 13/3 (d[m] - d[m-1])^2 + 4/3 eps
-    double ck, ck1, ck3;                         // c[k], c[k+1], c[k+3]
-    double Fb = 0.0, wb = 0.0;                   // flux through / w at the bottom face of cell k
-    double dm3 = 0.0;                            // Periodic z: d[-3], for the bottom face of cell 0
+    double d0[NS], d1[NS], d2[NS], d3[NS], d4[NS];   // d[k-2..k+2], d[m] = c[m+1] - c[m]
+    double Qa[NS], Qb[NS], Qc[NS], Qd[NS];           // Q[k-1..k+2], Q[m] = 13/3 (d[m] - d[m-1])^2 + 4/3 eps
+    double ck[NS], ck1[NS], ck3[NS];                 // c[k], c[k+1], c[k+3]
+    double Fb[NS], dm3[NS];                          // flux through the bottom face of cell k; Periodic z: d[-3]
+    double wb = 0.0;                                 // w at the bottom face of cell k
     mbar_wait(barP, 0);
-    {
-        const unsigned aC = a40s + oC;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const unsigned aC = A40S(s) + oC;
         const double cm2 = lds(aC + 0 * CSLOT_B), cm1 = lds(aC + 1 * CSLOT_B);
-        if (zper) dm3 = cm2 - S.U_old[(int64_t)(item.tracer_c + sub) * L.len + L.at(i0 + tx, j0 + ty, -3)];
-        ck = lds(aC + 2 * CSLOT_B); ck1 = lds(aC + 3 * CSLOT_B);
+        Fb[s] = 0.0; dm3[s] = 0.0;
+        if (zper) dm3[s] = cm2 - S.U_old[(int64_t)(item.tracer_c + sub0 + s) * L.len + L.at(i0 + tx, j0 + ty, -3)];
+        ck[s] = lds(aC + 2 * CSLOT_B); ck1[s] = lds(aC + 3 * CSLOT_B);
         const double ck2 = lds(aC + 4 * CSLOT_B);
-        ck3 = lds(aC + 5 * CSLOT_B);
-        d0 = cm1 - cm2; d1 = ck - cm1; d2 = ck1 - ck; d3 = ck2 - ck1; d4 = ck3 - ck2;
-        double s;
-        s = d1 - d0; Qa = fma(K.k133 * s, s, K.eps43);
-        s = d2 - d1; Qb = fma(K.k133 * s, s, K.eps43);
-        s = d3 - d2; Qc = fma(K.k133 * s, s, K.eps43);
-        s = d4 - d3; Qd = fma(K.k133 * s, s, K.eps43);
+        ck3[s] = lds(aC + 5 * CSLOT_B);
+        d0[s] = cm1 - cm2; d1[s] = ck[s] - cm1; d2[s] = ck1[s] - ck[s]; d3[s] = ck2 - ck1[s]; d4[s] = ck3[s] - ck2;
+        double q;
+        q = d1[s] - d0[s]; Qa[s] = fma(K.k133 * q, q, K.eps43);
+        q = d2[s] - d1[s]; Qb[s] = fma(K.k133 * q, q, K.eps43);
+        q = d3[s] - d2[s]; Qc[s] = fma(K.k133 * q, q, K.eps43);
+        q = d4[s] - d3[s]; Qd[s] = fma(K.k133 * q, q, K.eps43);
     }
     // The first in-loop TMA load reuses the ring slot of plane -2: every thread must have read its prologue values,
     // and (main threads pass this barrier only after their wait on barP) the prologue loads must have landed, before
     // the producer lane issues it.
     block_barrier();
 
-    double part[ZT_PB], base[ZT_PB];             // own part of the tendency / of the substep, carried over the barrier
+    double part[NS][ZT_PB], base[NS][ZT_PB];     // own part of the tendency / of the substep, carried over the barrier
 
     // Faces and own tendency part of plane k.  J >= 0: k = 8 m + 2 + J is known modulo the ring period, so every
     // ring offset, flux buffer and mbarrier parity is an immediate and the plane is interior (top face index
@@ -603,60 +646,73 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         const int kk = FAST ? 2 + J : k;         // k modulo 8 where it matters
         const unsigned is = (unsigned)(kk & (ZT_RI - 1)) * ISLOT_B;
         const unsigned fb = (unsigned)(kk & (ZT_RI - 1)) * FBUF_B;
-        const unsigned aCk = a40s + oC + (unsigned)((kk + 2) & (ZT_RC - 1)) * CSLOT_B;
+        const unsigned oCk = oC + (unsigned)((kk + 2) & (ZT_RC - 1)) * CSLOT_B;
+        // velocities and upwind decisions: once for all tracers of the thread
         const double cu = lds(a40 + oU + is), cv = FLATY ? 0.0 : lds(a32 + oV + is);
         const double cw = lds(a32 + oW + NT_B + is);
-        if (!FAST && k == 0) wb = lds(a32 + oW + is);
-        double fx = zt_face<8>(aCk, cu, K), fy = FLATY ? 0.0 : zt_face<ROW_B>(aCk, cv, K);
-        if (WALLS && tile_walls) {                        // buffer schemes next to the walls of Bounded x / y axes
-            if (ox != 5) fx = zt_face_buffer<8>(aCk, cu, ox);
-            if (!FLATY && oy != 5) fy = zt_face_buffer<ROW_B>(aCk, cv, oy);
-        }
-        const double Fw = cu * fx;
-        const double Fs = cv * fy;
-        sts(a40s + oFX + fb, Fw);
-        if (!FLATY) sts(a32s + oFY + fb, Fs);
-        if (!FAST && k == 0) {
-            if (zper) {
-                // Periodic z: the bottom face of cell 0 is a WENO5 face between cells -1 and 0 (c[-1] = c[0] - d[-1])
-                Fb = wb * (zt_positive(wb) ? (ck - d1) + zt_inc(dm3, d0, d1, d2, K) : ck - zt_inc(d3, d2, d1, d0, K));
-            } else {
-                Fb = wb * ck;                            // wall face m = 1: Centered2 on the mirrored halo
-            }
-        }
-        double ct;
-        if (FAST || zper || (k >= 2 && k <= Nz - 4)) {
-            // the window is used by a warp-uniform branch per direction (both only in warps that straddle w = 0)
-            const bool left = zt_positive(cw);
-            const unsigned ml = __ballot_sync(0xffffffffu, left);
-            ct = ck1;
-            if (ml != 0xffffffffu) ct = ck1 - zt_inc_q(d4, d3, d2, d1, Qd, Qc, Qb, K);
-            if (ml != 0u) { const double ctL = ck + zt_inc_q(d0, d1, d2, d3, Qa, Qb, Qc, K); ct = left ? ctL : ct; }
-        } else {
-            ct = zt_top_face_buffer(k + 2, Nz, cw, d1, d2, d3, ck, ck1);
-        }
-        const double Ft = cw * ct;
-        // ---- own part of the tendency: c du - dF per axis in units of face velocity, forcing, G^- part of the substep ----
+        const double wb0 = (!FAST && k == 0) ? lds(a32 + oW + is) : wb;
+        const ZtUp ux = zt_up<8>(cu), uy = zt_up<ROW_B>(cv);
         const double ue = lds(a40 + oU + is + 8), vn = FLATY ? 0.0 : lds(a32 + oV + is + 8 * 32);
         const double sA = lds(aS1 + is), sB = lds(aS2 + is);
-        double forcing = fma(kA, sA, fma(kB, sB, k_own * ck));
-        if (relax) forcing = fma(lds(a32 + oM + is) * lds(aRX + 24), fma(lds(aRX), fma(lds(aRX + 8), sA, lds(aRX + 16) * sB), -ck), forcing);
-        if (NSUB == 2) forcing = fma(k_oth, lds(aCk + partner_off), forcing);
-        const double az = fma(ck, cw - wb, Fb - Ft);
-        part[p] = FLATY ? fma(rdx, fma(ck, ue - cu, Fw), fma(rdz, az, forcing))
-                        : fma(rdx, fma(ck, ue - cu, Fw), fma(rdy, fma(ck, vn - cv, Fs), fma(rdz, az, forcing)));
-        base[p] = S.first_stage ? ck : fma(dtz, lds(a32s + oG + is), ck);
-        // ---- advance the window to cell k+1: d[k+3] = c[k+4] - c[k+3] from the ring ----
-        {
-            Fb = Ft; wb = cw;
-            const double c2 = lds(a40s + oC + (unsigned)((kk + 4) & (ZT_RC - 1)) * CSLOT_B);
-            const double c4 = lds(a40s + oC + (unsigned)((kk + 6) & (ZT_RC - 1)) * CSLOT_B);
-            const double dnew = c4 - ck3;
-            const double s = dnew - d4;
-            d0 = d1; d1 = d2; d2 = d3; d3 = d4; d4 = dnew;
-            Qa = Qb; Qb = Qc; Qc = Qd; Qd = fma(K.k133 * s, s, K.eps43);
-            ck = ck1; ck1 = c2; ck3 = c4;
+        const bool z_weno = FAST || zper || (k >= 2 && k <= Nz - 4);
+        const bool left = zt_positive(cw);
+        const unsigned ml = z_weno ? __ballot_sync(0xffffffffu, left) : 0u;
+        const double dux = ue - cu, dvy = vn - cv, dwz = cw - wb0;
+        double ckk[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) ckk[s] = ck[s];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const unsigned aCk = A40S(s) + oCk;
+            double fx = zt_face_up<8>(aCk, ux, K), fy = FLATY ? 0.0 : zt_face_up<ROW_B>(aCk, uy, K);
+            if (WALLS && tile_walls) {                        // buffer schemes next to the walls of Bounded x / y axes
+                if (ox != 5) fx = zt_face_buffer<8>(aCk, cu, ox);
+                if (!FLATY && oy != 5) fy = zt_face_buffer<ROW_B>(aCk, cv, oy);
+            }
+            const double Fw = cu * fx;
+            const double Fs = cv * fy;
+            sts(A40S(s) + oFX + fb, Fw);
+            if (!FLATY) sts(A32S(s) + oFY + fb, Fs);
+            if (!FAST && k == 0) {
+                if (zper) {
+                    // Periodic z: the bottom face of cell 0 is a WENO5 face between cells -1 and 0 (c[-1] = c[0] - d[-1])
+                    Fb[s] = wb0 * (zt_positive(wb0) ? (ck[s] - d1[s]) + zt_inc(dm3[s], d0[s], d1[s], d2[s], K)
+                                                    : ck[s] - zt_inc(d3[s], d2[s], d1[s], d0[s], K));
+                } else {
+                    Fb[s] = wb0 * ck[s];                     // wall face m = 1: Centered2 on the mirrored halo
+                }
+            }
+            double ct;
+            if (z_weno) {
+                // the window is used by a warp-uniform branch per direction (both only in warps that straddle w = 0)
+                ct = ck1[s];
+                if (ml != 0xffffffffu) ct = ck1[s] - zt_inc_q(d4[s], d3[s], d2[s], d1[s], Qd[s], Qc[s], Qb[s], K);
+                if (ml != 0u) { const double ctL = ck[s] + zt_inc_q(d0[s], d1[s], d2[s], d3[s], Qa[s], Qb[s], Qc[s], K); ct = left ? ctL : ct; }
+            } else {
+                ct = zt_top_face_buffer(k + 2, Nz, cw, d1[s], d2[s], d3[s], ck[s], ck1[s]);
+            }
+            const double Ft = cw * ct;
+            // ---- own part of the tendency: c du - dF per axis in units of face velocity, forcing, G^- part of the substep ----
+            double forcing = fma(kA[s], sA, fma(kB[s], sB, k_own * ck[s]));
+            if (relax) forcing = fma(lds(a32 + oM + is) * lds(ARX(s) + 24), fma(lds(ARX(s)), fma(lds(ARX(s) + 8), sA, lds(ARX(s) + 16) * sB), -ck[s]), forcing);
+            if (NSUB == 2) forcing = fma(k_oth[s], NS == 2 ? ckk[1 - s] : lds(aCk + partner_off), forcing);
+            const double az = fma(ck[s], dwz, Fb[s] - Ft);
+            part[s][p] = FLATY ? fma(rdx, fma(ck[s], dux, Fw), fma(rdz, az, forcing))
+                               : fma(rdx, fma(ck[s], dux, Fw), fma(rdy, fma(ck[s], dvy, Fs), fma(rdz, az, forcing)));
+            base[s][p] = S.first_stage ? ck[s] : fma(dtz, lds(A32S(s) + oG + is), ck[s]);
+            // ---- advance the window to cell k+1: d[k+3] = c[k+4] - c[k+3] from the ring ----
+            {
+                Fb[s] = Ft;
+                const double c2 = lds(A40S(s) + oC + (unsigned)((kk + 4) & (ZT_RC - 1)) * CSLOT_B);
+                const double c4 = lds(A40S(s) + oC + (unsigned)((kk + 6) & (ZT_RC - 1)) * CSLOT_B);
+                const double dnew = c4 - ck3[s];
+                const double q = dnew - d4[s];
+                d0[s] = d1[s]; d1[s] = d2[s]; d2[s] = d3[s]; d3[s] = d4[s]; d4[s] = dnew;
+                Qa[s] = Qb[s]; Qb[s] = Qc[s]; Qc[s] = Qd[s]; Qd[s] = fma(K.k133 * q, q, K.eps43);
+                ck[s] = ck1[s]; ck1[s] = c2; ck3[s] = c4;
+            }
         }
+        wb = cw;
     };
     // wait for the TMA group of plane k.  It is called before the barrier of the interval before, so that the code
     // from one barrier to the next wait is a single basic block in which the finish of the planes just synchronised
@@ -671,27 +727,31 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         constexpr int J = decltype(jtag)::value;
         const int kk = J >= 0 ? 2 + J : k;
         const unsigned fb = (unsigned)(kk & (ZT_RI - 1)) * FBUF_B;
-        const double Fe = lds(a40s + oFX + fb + 8);
-        double Gn;
-        if (FLATY) Gn = fma(nrdx, Fe, part[p]);
-        else { const double Fn = lds(a32s + oFY + fb + 8 * 32); Gn = fma(nrdx, Fe, fma(nrdy, Fn, part[p])); }
-        const double unew = fma(dtg, Gn, base[p]);
-        pUn[0] = unew;
-        if (S.store_G) pUn[g_off] = Gn;
-        if (tile_wraps) {
-            // periodic halo images of the new state (the tracer halo fill of update_state!, fused)
-            if (xwrap) pUn[xwrap] = unew;
-            if (ywrap) { pUn[ywrap] = unew; if (xwrap) pUn[xwrap + ywrap] = unew; }
-        }
-        if (zper && L.fuse_halo[2] && (k < L.H[2] || k >= Nz - L.H[2])) {
-            double *pz = reinterpret_cast<double *>(reinterpret_cast<char *>(pUn) + (k < L.H[2] ? Nz : -Nz) * plane_b);
-            pz[0] = unew;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const double Fe = lds(A40S(s) + oFX + fb + 8);
+            double Gn;
+            if (FLATY) Gn = fma(nrdx, Fe, part[s][p]);
+            else { const double Fn = lds(A32S(s) + oFY + fb + 8 * 32); Gn = fma(nrdx, Fe, fma(nrdy, Fn, part[s][p])); }
+            const double unew = fma(dtg, Gn, base[s][p]);
+            double *__restrict__ pu = pUn[s];
+            pu[0] = unew;
+            if (S.store_G) pu[g_off] = Gn;
             if (tile_wraps) {
-                if (xwrap) pz[xwrap] = unew;
-                if (ywrap) { pz[ywrap] = unew; if (xwrap) pz[xwrap + ywrap] = unew; }
+                // periodic halo images of the new state (the tracer halo fill of update_state!, fused)
+                if (xwrap) pu[xwrap] = unew;
+                if (ywrap) { pu[ywrap] = unew; if (xwrap) pu[xwrap + ywrap] = unew; }
             }
+            if (zper && L.fuse_halo[2] && (k < L.H[2] || k >= Nz - L.H[2])) {
+                double *pz = reinterpret_cast<double *>(reinterpret_cast<char *>(pu) + (k < L.H[2] ? Nz : -Nz) * plane_b);
+                pz[0] = unew;
+                if (tile_wraps) {
+                    if (xwrap) pz[xwrap] = unew;
+                    if (ywrap) { pz[ywrap] = unew; if (xwrap) pz[xwrap + ywrap] = unew; }
+                }
+            }
+            pUn[s] = reinterpret_cast<double *>(reinterpret_cast<char *>(pu) + plane_b);
         }
-        pUn = reinterpret_cast<double *>(reinterpret_cast<char *>(pUn) + plane_b);
     };
     using Dyn = std::integral_constant<int, -1>;
     // generic planes [ka, kb), ZT_PB per barrier
@@ -734,6 +794,9 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
 #undef ZT_WAIT
     }
     generic_range(k, Nz);
+#undef A32S
+#undef A40S
+#undef ARX
 }
 
 #ifndef ZT_TY
