@@ -277,6 +277,10 @@ class OfflineFilterConfig:
         if grid is None:
             raise ValueError("grid=RectilinearGrid(...) is required: this host does not decode the Julia-serialised "
                              "grid stored in the JLD2 file")
+        if hasattr(grid, "immersed_boundary") and map_to_mean:
+            # OfflineLagrangianFilter.jl:428-431
+            log.warning("The final interpolation to mean position does not yet work well with immersed boundaries - "
+                        "consider setting map_to_mean=false")
         if advection is None and map_to_mean:
             log.warning("Advection scheme is 'nothing' (Eulerian filter) so setting map_to_mean=false")
             map_to_mean = False

@@ -703,6 +703,11 @@ extern "C" int lfb_init_from_data(lfb_handle *h)
     }
     h->cur = 0; h->time = 0; h->iteration = 0;
     h->halos_valid = 0;
+    if (h->imm && h->imm_set) {
+        // the reference's first update_state! (mask_immersed_field!, update_lagrangian_filter_state.jl:22-24) runs before the
+        // output writer sees iteration 0: the initial state is masked here, not only before the first stage
+        for (int b = 0; b < 2; ++b) { CU(lfb_launch_mask_immersed(h->U[b], h->imm, L.len, h->n_tracers, h->compute)); h->launches++; }
+    }
     return LFB_OK;
 }
 

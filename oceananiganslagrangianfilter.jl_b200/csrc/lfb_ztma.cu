@@ -52,6 +52,13 @@
 #ifndef ZT_PAIR
 #define ZT_PAIR 0         // 1: the cosine and the sine tracer of an item share a main thread (see the main warps); measured slower (-8 %)
 #endif
+#ifndef ZT_PB
+#define ZT_PB 2           // planes per block barrier
+#endif
+#ifndef ZT_TMA_STORE
+#define ZT_TMA_STORE 0    // 1: the new state and G^n leave through shared memory and cp.async.bulk.tensor stores (UTMASTG);
+                          // measured 2.4 % slower than per-thread STG (profiles/microbench/r02_tma_store_experiment.txt)
+#endif
 #ifndef ZT_PF
 #define ZT_PF 0           // planes an L2 prefetch (cp.async.bulk.prefetch.tensor) runs ahead; 0 = off: measured slower (6: +2 %, 10: +7 %)
 #endif
@@ -66,6 +73,10 @@ struct LfbZtParams {
     alignas(64) CUtensorMap mF[LFB_MAX_VARS];    // original variables, snapshot at or before the stage time, box 32 x TY
     alignas(64) CUtensorMap mF2[LFB_MAX_VARS];   // ... snapshot after it (linear interpolation in the forcing term)
     alignas(64) CUtensorMap mM;                  // relaxation mask (boundary_relaxation), box 32 x TY
+    // store maps (box 32 x TY) of U_new and G for the two row ranges of a launch: their extents end at column Nx and at
+    // row j1 of the range, so the surplus columns / rows of partial tiles are clipped by the TMA unit
+    alignas(64) CUtensorMap mSU[2];
+    alignas(64) CUtensorMap mSG[2];
     double k133, k13, k16, eps43, rd[3];         // 13/3, 1/3, 1/6, 4/3 eps, area / volume per axis
     double *scratch;                             // one field: store target of the rows beyond j1 in partial tiles
 };
@@ -85,11 +96,14 @@ struct ZtSmem {
                          OFF_M = OFF_F2 + NT;                    // relaxation mask
     static constexpr int ISLOT = OFF_M + NT;                     // doubles per input slot
     static constexpr int CSLOT = NSUB * CTP;
-    static constexpr int FBUF = NSUB * (CTP + VT);               // Fx[NSUB] (tracer-tile geometry), Fy[NSUB][TY+1][32]
+    static constexpr int FXT = ZT_TMA_STORE ? UT : CTP;          // x-flux tile of a tracer: [TY][40] (or the tracer-tile geometry)
+    static constexpr int FBUF = NSUB * (FXT + VT);               // Fx[NSUB], Fy[NSUB][TY+1][32]
+    static constexpr int OUTBUF = ZT_TMA_STORE ? ZT_PB * NSUB * 2 * NT : 0;   // per barrier interval: planes x tracers x (U_new, G^n) tiles [TY][32]
     static constexpr int O_C = 0;
     static constexpr int O_IN = O_C + ZT_RC * CSLOT;
     static constexpr int O_FL = O_IN + ZT_RI * ISLOT;
-    static constexpr int O_BAR = O_FL + ZT_RI * FBUF;            // ZT_RI group barriers + the prologue barrier
+    static constexpr int O_OUT = O_FL + ZT_RI * FBUF;            // two interval buffers (written while the other one is being stored)
+    static constexpr int O_BAR = O_OUT + 2 * OUTBUF;             // ZT_RI group barriers + the prologue barrier
     static constexpr int DOUBLES = O_BAR + 8 + 8;                // + 2 x 4 relaxation coefficients
     static constexpr int BYTES = DOUBLES * 8;
     static constexpr int NS = (ZT_PAIR && NSUB == 2) ? 2 : 1;    // tracers per main thread
@@ -140,6 +154,17 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap *map, int x, i
 {
     asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(x), "r"(y), "r"(z), "r"(t) : "memory");
 }
+
+// shared -> global tensor store (bulk async group), and the fences / waits around it
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, unsigned src, int x, int y, int z, int t)
+{
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(x), "r"(y), "r"(z), "r"(t) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // streaming (evict-first) global accesses of the side job: its data is touched once per stage and must not push the
 // velocity tiles the sibling blocks of a tile share out of L2
@@ -286,10 +311,6 @@ __device__ __noinline__ double zt_top_face_buffer(int m, int Nz, double cw, doub
     return 0.5 * (ck + ck1);
 }
 
-#ifndef ZT_PB
-#define ZT_PB 2           // planes per block barrier
-#endif
-
 // WALLS: the general instantiation -- Bounded x or y axes (buffer schemes next to those walls), Periodic z and boundary relaxation;
 // compiled separately so that the all-periodic form keeps its register allocation.
 // FLATY: the folded form for grids with a Flat y axis (LfbStageParams::fold): no y faces, no v tile.
@@ -305,7 +326,8 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     constexpr unsigned oC = 8u * SM::O_C, oIN = 8u * SM::O_IN, oFL = 8u * SM::O_FL, oBAR = 8u * SM::O_BAR;
     constexpr unsigned oU = oIN + 8u * SM::OFF_U, oV = oIN + 8u * SM::OFF_V, oW = oIN + 8u * SM::OFF_W,
                        oG = oIN + 8u * SM::OFF_G, oF = oIN + 8u * SM::OFF_F, oF2 = oIN + 8u * SM::OFF_F2, oM = oIN + 8u * SM::OFF_M;
-    constexpr unsigned oFX = oFL, oFY = oFL + NSUB * CTP_B;
+    constexpr unsigned FXT_B = 8u * SM::FXT, UT_B = 8u * SM::UT, oOUT = 8u * SM::O_OUT, OUTBUF_B = 8u * SM::OUTBUF;
+    constexpr unsigned oFX = oFL, oFY = oFL + NSUB * FXT_B;
     const LfbStageParams &S = P.S;
     const LfbLayout &L = S.L;
     const int tid = threadIdx.x;
@@ -400,7 +422,8 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         const unsigned aT = sbase + oC + 8u * (sub * SM::CTP + (ty + 3) * ZT_CW + tx + ZT_HX);
         const unsigned aQ = sbase + (kind == 1 ? oV + 8u * (ty * 32 + tx) : oU + 8u * (ty * ZT_CW + tx + ZT_HX));
         const unsigned aF = sbase + (kind == 1 ? oFY + 8u * (sub * SM::VT + ty * 32 + tx)
-                                               : oFX + 8u * (sub * SM::CTP + (ty + 3) * ZT_CW + tx + ZT_HX));
+                                  : ZT_TMA_STORE ? oFX + 8u * (sub * SM::UT + ty * ZT_CW + tx + ZT_HX)
+                                                 : oFX + 8u * (sub * SM::CTP + (ty + 3) * ZT_CW + tx + ZT_HX));
         // scheme of this lane's face (lower order next to the walls of a Bounded axis)
         const int h_order = kind == 1 ? zt_face_order(L.goff[1] + j0 + ty + 1, L.NG[1], L.topo[1] == LFB_BOUNDED)
                             : FLATY ? zt_face_order(32 * (j0 + ty) + tx + 1, S.fold_nx, L.topo[0] == LFB_BOUNDED)
@@ -459,12 +482,37 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             }
         };
         double2 va[ZT_PB], vb[ZT_PB];
+#if ZT_TMA_STORE
+        // Stores of the finished planes.  The main threads put U_new and G^n of the two planes of interval n (planes 2n,
+        // 2n + 1) into out-buffer n & 1 after barrier n and fence them to the async proxy; after barrier n + 1 the
+        // producer lane sends the tiles with cp.async.bulk.tensor stores, and waits until the TMA unit has read them
+        // before it arrives at barrier n + 2, behind which the buffer is written again.
+        const CUtensorMap *mSU = &P.mSU[range_b ? 1 : 0], *mSG = &P.mSG[range_b ? 1 : 0];
+        auto store_interval = [&](int n) {
+            const unsigned ob = sbase + oOUT + (unsigned)(n & 1) * OUTBUF_B;
+#pragma unroll
+            for (int p = 0; p < ZT_PB; ++p) {
+                const int k = n * ZT_PB + p;
+                if (k >= Nz) break;
+#pragma unroll
+                for (int s = 0; s < NSUB; ++s) {
+                    const unsigned tile = ob + (unsigned)((p * NSUB + s) * 2) * NT_B;
+                    tma_store_4d(mSU, tile, ix, iy, z0 + k, item.tracer_c + s);
+                    if (S.store_G) tma_store_4d(mSG, tile + NT_B, ix, iy, z0 + k, item.tracer_c + s);
+                }
+            }
+            tma_store_commit();
+        };
+#endif
         if (face_lane) mbar_wait(barP, 0);
         __syncwarp();
         block_barrier();                 // prologue barrier: see the main warps
         for (int k0 = 0; k0 < Nz; k0 += ZT_PB) {
             // the loads of the next barrier interval are issued together at the start of this one, so the consumers
             // can wait for them before this interval's barrier without stalling
+#if ZT_TMA_STORE
+            if (kind == 3 && k0 >= 2 * ZT_PB) store_interval(k0 / ZT_PB - 2);
+#endif
             if (kind == 3) {
 #pragma unroll
                 for (int p = 0; p < ZT_PB; ++p) if (k0 + ZT_D + p < Nz && (ZT_PB == ZT_D || p == 0)) issue_group(k0 + ZT_D + p);
@@ -499,8 +547,19 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             __syncwarp();
             if (pf_on && unit0 + unit_step < NUNIT)
                 for (int p = 0; p < ZT_PB; ++p) if (k0 + p < Nz) pf_rest(k0 + p, unit0 + unit_step, false);
+#if ZT_TMA_STORE
+            if (kind == 3) tma_store_wait_read();
+#endif
             block_barrier();
         }
+#if ZT_TMA_STORE
+        {
+            const int NI = (Nz + ZT_PB - 1) / ZT_PB;
+            if (kind == 3 && NI >= 2) store_interval(NI - 2);
+            block_barrier();             // the main threads have written (and fenced) the last interval
+            if (kind == 3) { store_interval(NI - 1); tma_store_wait_all(); }
+        }
+#endif
         if (pf_on) {
             const int kl = (Nz - 1) / ZT_PB * ZT_PB;     // first plane of the last interval
             if (pa) {
@@ -525,6 +584,8 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     const unsigned a32s0 = a32 + sub0 * VT_B, a40s0 = a40 + 3 * ROW_B + sub0 * CTP_B;
 #define A32S(s) (a32s0 + (unsigned)(s) * VT_B)
 #define A40S(s) (a40s0 + (unsigned)(s) * CTP_B)
+    // own entry of the x-flux tile of tracer s ([TY][40] with TMA stores, else the tracer-tile geometry)
+#define AFX(s) (ZT_TMA_STORE ? a40 + (unsigned)(sub0 + (s)) * UT_B + oFX : A40S(s) + oFX)
     const int partner_off = (NSUB == 2 && NS == 1) ? (sub0 ? -(int)CTP_B : (int)CTP_B) : 0;
     // partial tiles at the end of the y range / of x (folded form: the last row of 32 cells may be partial)
     const bool active = j0 + ty < j1 && (FLATY ? 32 * (j0 + ty) + tx < S.fold_nx : i0 + tx < L.N[0]);
@@ -671,7 +732,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             }
             const double Fw = cu * fx;
             const double Fs = cv * fy;
-            sts(A40S(s) + oFX + fb, Fw);
+            sts(AFX(s) + fb, Fw);
             if (!FLATY) sts(A32S(s) + oFY + fb, Fs);
             if (!FAST && k == 0) {
                 if (zper) {
@@ -729,14 +790,27 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         const unsigned fb = (unsigned)(kk & (ZT_RI - 1)) * FBUF_B;
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
-            const double Fe = lds(A40S(s) + oFX + fb + 8);
+            const double Fe = lds(AFX(s) + fb + 8);
             double Gn;
             if (FLATY) Gn = fma(nrdx, Fe, part[s][p]);
             else { const double Fn = lds(A32S(s) + oFY + fb + 8 * 32); Gn = fma(nrdx, Fe, fma(nrdy, Fn, part[s][p])); }
             const double unew = fma(dtg, Gn, base[s][p]);
+#if ZT_TMA_STORE
+            // out-buffer of this barrier interval: tiles [TY][32] of U_new and G^n per plane and tracer
+            {
+                const unsigned ob = oOUT + (unsigned)((J >= 0 ? ((2 + J) / ZT_PB) : (k / ZT_PB)) & 1) * OUTBUF_B +
+                                    (unsigned)((p * NSUB + sub0 + s) * 2) * NT_B;
+                sts(a32 + ob, unew);
+                if (S.store_G) sts(a32 + ob + NT_B, Gn);
+            }
+            const bool images = active && (tile_wraps || (zper && L.fuse_halo[2] && (k < L.H[2] || k >= Nz - L.H[2])));
+            double *__restrict__ pu = images ? reinterpret_cast<double *>(reinterpret_cast<char *>(pUn[s]) + (int64_t)k * plane_b) : nullptr;
+            if (!images) continue;
+#else
             double *__restrict__ pu = pUn[s];
             pu[0] = unew;
             if (S.store_G) pu[g_off] = Gn;
+#endif
             if (tile_wraps) {
                 // periodic halo images of the new state (the tracer halo fill of update_state!, fused)
                 if (xwrap) pu[xwrap] = unew;
@@ -750,8 +824,13 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
                     if (ywrap) { pz[ywrap] = unew; if (xwrap) pz[xwrap + ywrap] = unew; }
                 }
             }
+#if !ZT_TMA_STORE
             pUn[s] = reinterpret_cast<double *>(reinterpret_cast<char *>(pu) + plane_b);
+#endif
         }
+#if ZT_TMA_STORE
+        if (p == ZT_PB - 1 || k == Nz - 1) fence_proxy_async();      // the interval's tiles become visible to the TMA unit
+#endif
     };
     using Dyn = std::integral_constant<int, -1>;
     // generic planes [ka, kb), ZT_PB per barrier
@@ -794,8 +873,12 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
 #undef ZT_WAIT
     }
     generic_range(k, Nz);
+#if ZT_TMA_STORE
+    block_barrier();                     // the producer lane stores the last interval behind this barrier
+#endif
 #undef A32S
 #undef A40S
+#undef AFX
 #undef ARX
 }
 
@@ -826,7 +909,8 @@ static zt_encode_fn zt_encoder()
 // fold_rows > 0: the folded view of a grid with a Flat y axis -- rows of 32 cells whose haloed tiles (40 cells) overlap
 // in memory (row stride 32 < inner extent 40; profiles/microbench/tma_overlap.cu), fold_rows rows per plane; rows outside
 // are zero-filled by the TMA unit.
-static int zt_make_map(CUtensorMap *m, const LfbLayout &L, const void *base, int n_stack, int bx, int by, int bz = 1, int fold_rows = 0)
+static int zt_make_map(CUtensorMap *m, const LfbLayout &L, const void *base, int n_stack, int bx, int by, int bz = 1, int fold_rows = 0,
+                       int clip_cols = 0, int clip_rows = 0)
 {
     zt_encode_fn enc = zt_encoder();
     if (!enc) return -1;
@@ -834,6 +918,9 @@ static int zt_make_map(CUtensorMap *m, const LfbLayout &L, const void *base, int
     cuuint64_t dim[4] = {(cuuint64_t)L.pitch, (cuuint64_t)L.rows, (cuuint64_t)L.planes, (cuuint64_t)(n_stack > 0 ? n_stack : 1)};
     cuuint64_t str[3] = {(cuuint64_t)L.pitch * 8, (cuuint64_t)L.plane * 8, (cuuint64_t)L.len * 8};
     if (fold_rows > 0) { dim[0] = ZT_CW; dim[1] = (cuuint64_t)fold_rows; }
+    // store maps: the tensor ends at column clip_cols / row clip_rows, what lies beyond is not written
+    if (clip_cols > 0) dim[0] = (cuuint64_t)clip_cols;
+    if (clip_rows > 0) dim[1] = (cuuint64_t)clip_rows;
     cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, const_cast<void *>(base), dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -922,6 +1009,15 @@ static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
             bad |= zt_make_map(&P.mF2[q], L, SS.var_fused ? SS.var2[q] : SS.var[q], 0, 32, TY, 1, fold_rows);
         }
     if (S->relax) bad |= zt_make_map(&P.mM, L, SS.mask, 0, 32, TY, 1, fold_rows);
+#if ZT_TMA_STORE
+    for (int r = 0; r < 2; ++r) {
+        const int jend = r == 0 ? SS.j1 : SS.jb1;
+        if (r == 1 && SS.jb1 <= SS.jb0) break;
+        const int cols = L.xoff + L.N[0], rows = L.H[1] + jend;
+        bad |= zt_make_map(&P.mSU[r], L, SS.U_new, n_t, 32, TY, 1, 0, cols, rows);
+        bad |= zt_make_map(&P.mSG[r], L, SS.G, n_t, 32, TY, 1, 0, cols, rows);
+    }
+#endif
     if (bad) return cudaErrorInvalidValue;
     P.k133 = 13.0 / 3.0; P.k13 = 1.0 / 3.0; P.k16 = 1.0 / 6.0; P.eps43 = LFB_WENO_EPS * (4.0 / 3.0);
     for (int a = 0; a < 3; ++a) P.rd[a] = S->area[a] / S->volume;

@@ -262,7 +262,7 @@ class Oracle:
 def run_offline(times, vel, vars_, var_names, N, H, topology, delta, filter_params, dt, T_out,
                 T_start=None, T_end=None, velocities="uw", map_to_mean=True, compute_mean_velocities=True,
                 advect=True, float32_outputs=True, relax_timescale=None, mask=None, return_state=False,
-                immersed=None, weights_f32=False):
+                immersed=None, weights_f32=False, cell_heights=None, timestepper="RungeKutta3", chi=0.1):
     """Oracle restatement of run_offline_Lagrangian_filter up to and including
     sum_forward_backward_contributions! (reference run_offline_lagrangian_filter.jl:25-105).
 
@@ -279,7 +279,8 @@ def run_offline(times, vel, vars_, var_names, N, H, topology, delta, filter_para
     vars_s = [[v[i] for i in sel] for v in vars_]
     with_maps = map_to_mean or compute_mean_velocities
     o = Oracle(N, H, topology, delta, len(var_names), velocities, filter_params, with_maps, advect,
-               relax_timescale, mask, immersed=immersed, weights_f32=weights_f32)
+               relax_timescale, mask, immersed=immersed, weights_f32=weights_f32, cell_heights=cell_heights,
+               timestepper=timestepper, chi=chi)
     vel_names = [n for n in "uvw" if n in velocities]
 
     def collect():
