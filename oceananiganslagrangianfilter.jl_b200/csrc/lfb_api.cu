@@ -919,8 +919,16 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
     // rows per edge strip: one z-march tile row / the halo width
     const int strip = h->use_zmarch == 3 ? lfb_ztma_tile_rows() : h->L.H[1];
     const bool overlap = update && h->nranks > 1 && Ny >= 4 * strip;
-    auto launch = [&](int j0, int j1, int jb0, int jb1, cudaStream_t st) -> int {
+    // Bounded y on the TMA kernel: only the tile rows next to the walls need the general instantiation (buffer schemes);
+    // rows at least one tile row away from both walls run the all-periodic one
+    const bool split_walls = ztma && !h->fold && h->L.topo[1] == LFB_BOUNDED && Ny >= 4 * strip;
+    // Bounded x likewise: the x tiles whose faces all lie in 4 .. Nx - 2 (tiles 1 .. xt_hi - 1) need no buffer schemes
+    const int n_xt = (h->L.N[0] + 31) / 32, xt_hi = h->L.N[0] >= 35 ? (h->L.N[0] - 35) / 32 + 1 : 0;
+    const bool split_x = ztma && !h->fold && h->L.topo[0] == LFB_BOUNDED && xt_hi >= 3;
+    auto launch_rows = [&](int j0, int j1, int jb0, int jb1, cudaStream_t st) -> int {
         P.j0 = j0; P.j1 = j1; P.jb0 = jb0; P.jb1 = jb1;
+        const int g0 = h->L.goff[1] + j0, g1 = h->L.goff[1] + j1;
+        P.plain_rows = h->L.topo[1] != LFB_BOUNDED || (split_walls && jb1 <= jb0 && g0 >= strip && g1 <= h->L.NG[1] - strip);
         if (ztma) CU(lfb_launch_stage_ztma(&P, st));
         else {
             CU(lfb_launch_stage_generic(&P, h->desc.strict, st));
@@ -929,7 +937,24 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
         h->launches++;
         return LFB_OK;
     };
-    if (!overlap) {
+    auto launch = [&](int j0, int j1, int jb0, int jb1, cudaStream_t st) -> int {
+        P.xt0 = 0; P.xt_n = 0; P.plain_cols = 0;
+        if (!split_x) return launch_rows(j0, j1, jb0, jb1, st);
+        // x tiles next to the west wall, next to the east wall (general instantiation), and the ones between
+        int rc2;
+        P.xt0 = 0; P.xt_n = 1; P.plain_cols = 0;
+        if ((rc2 = launch_rows(j0, j1, jb0, jb1, st))) return rc2;
+        P.xt0 = xt_hi; P.xt_n = n_xt - xt_hi;
+        if ((rc2 = launch_rows(j0, j1, jb0, jb1, st))) return rc2;
+        P.xt0 = 1; P.xt_n = xt_hi - 1; P.plain_cols = 1;
+        return launch_rows(j0, j1, jb0, jb1, st);
+    };
+    if (!overlap && split_walls && h->nranks == 1) {
+        rc = launch(0, strip, Ny - strip, Ny, h->compute);            // the two wall strips, one grid
+        if (rc) return rc;
+        rc = launch(strip, Ny - strip, 0, 0, h->compute);             // everything else
+        if (rc) return rc;
+    } else if (!overlap) {
         rc = launch(0, Ny, 0, 0, h->compute);
         if (rc) return rc;
         if (update && h->nranks > 1) { rc = exchange_y(h, P.U_new, h->n_tracers); if (rc) return rc; }

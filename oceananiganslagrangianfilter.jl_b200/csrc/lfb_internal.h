@@ -90,6 +90,12 @@ struct LfbStageParams {
     // bracketing snapshots travel in var[LFB_MAX_VARS - 1] / var2[...], vsign = -1 on the backward pass.
     int     fold, fold_nx;
     double  vsign;
+    // rows of this launch lie at least one tile row away from the walls of a Bounded y axis (and x, z need no general
+    // treatment): the TMA z-march kernel may use its all-periodic instantiation although topo[1] is Bounded
+    int     plain_rows;
+    // x tiles (of 32 columns) this launch covers: [xt0, xt0 + xt_n); xt_n = 0: all.  plain_cols: they lie away from the
+    // walls of a Bounded x axis, so the all-periodic instantiation may be used although topo[0] is Bounded
+    int     xt0, xt_n, plain_cols;
     // second row range [jb0, jb1) of the same launch (the two edge strips of a slab in ONE grid); empty if jb1 <= jb0
     int     jb0, jb1;
     // side job of the TMA z-march kernel: while it computes this stage, its helper warps interpolate the velocities of

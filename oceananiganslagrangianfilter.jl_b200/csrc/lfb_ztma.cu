@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     const int tid = threadIdx.x;
     const int item_id = blockIdx.x % S.n_items;
     const int ytile = blockIdx.x / S.n_items;
-    const int i0 = blockIdx.y * ZT_TX;
+    const int i0 = (blockIdx.y + S.xt0) * ZT_TX;
     // rows of this tile: range [S.j0, S.j1) first, then (the second edge strip of a slab) [S.jb0, S.jb1)
     const int ytiles_a = (S.j1 - S.j0 + TY - 1) / TY;
     const bool range_b = ytile >= ytiles_a;
@@ -1023,7 +1023,8 @@ static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
     for (int a = 0; a < 3; ++a) P.rd[a] = S->area[a] / S->volume;
     P.scratch = SS.scratch;
     const int ytiles = (SS.j1 - SS.j0 + TY - 1) / TY + (SS.jb1 > SS.jb0 ? (SS.jb1 - SS.jb0 + TY - 1) / TY : 0);
-    dim3 grid(S->n_items * ytiles, (L.N[0] + ZT_TX - 1) / ZT_TX, 1);
+    dim3 grid(S->n_items * ytiles, (!FLATY && S->xt_n > 0) ? S->xt_n : (L.N[0] + ZT_TX - 1) / ZT_TX, 1);
+    if (FLATY) SS.xt0 = 0;
     lfb_stage_ztma<NSUB, TY, WALLS, FLATY><<<grid, SM::THREADS, SM::BYTES, stream>>>(P);
     return cudaGetLastError();
 }
@@ -1031,7 +1032,8 @@ static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
 extern "C" cudaError_t lfb_launch_stage_ztma(const LfbStageParams *P, cudaStream_t stream)
 {
     if (P->j1 <= P->j0) return cudaSuccess;
-    const bool walls = P->L.topo[0] == LFB_BOUNDED || P->L.topo[1] == LFB_BOUNDED || P->L.topo[2] == LFB_PERIODIC || P->relax;   // the general instantiation
+    const bool walls = (P->L.topo[0] == LFB_BOUNDED && !P->plain_cols) || (P->L.topo[1] == LFB_BOUNDED && !P->plain_rows) ||
+                       P->L.topo[2] == LFB_PERIODIC || P->relax;                     // the general instantiation
     if (P->fold) {
         if (walls) return P->single_exp ? zt_launch<1, ZT_TY, true, true>(P, stream) : zt_launch<2, ZT_TY, true, true>(P, stream);
         return P->single_exp ? zt_launch<1, ZT_TY, false, true>(P, stream) : zt_launch<2, ZT_TY, false, true>(P, stream);

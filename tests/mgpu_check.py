@@ -37,7 +37,10 @@ def main():
                                          ("Bounded", "generic", True, (32, 16 * world, 10)),
                                          ("Periodic", "ztma", False, (64, 32 * world, 24)),
                                          ("Periodic", "ztma", False, (32, 20 * world, 12)),
-                                         ("Bounded", "ztma", False, (40, 12 * world, 12))):
+                                         ("Bounded", "ztma", False, (40, 12 * world, 12)),
+                                         # slabs tall enough for the split launch (wall strips on the general
+                                         # instantiation, interior rows on the all-periodic one)
+                                         ("Bounded", "ztma", False, (40, 40 * world, 12))):
         g = lfb200.RectilinearGrid(size=size, extent=tuple(float(s) for s in size), topology=("Periodic", topo_y, "Bounded"))
         var_names, vel_names = ("T", "b"), ("u", "v", "w")
         times = [0.0, 0.5, 1.0]

@@ -352,7 +352,11 @@ def test_ztma_partial_tiles_in_x_and_y(size):
 
 @pytest.mark.parametrize("size,topology,N", [
     ((40, 12, 10), ("Periodic", "Bounded", "Bounded"), 2),        # channel: walls in y
+    ((48, 44, 10), ("Periodic", "Bounded", "Bounded"), 2),        # ... tall enough for the split launch: wall strips on the
+                                                                  # general instantiation, the rows between on the all-periodic one
     ((33, 9, 12), ("Bounded", "Bounded", "Bounded"), 2),          # box
+    ((104, 40, 9), ("Bounded", "Bounded", "Bounded"), 2),         # ... wide and tall enough for the split launches in x and y
+    ((133, 10, 12), ("Bounded", "Periodic", "Bounded"), 1),       # ... in x only, partial last x tile
     ((36, 20, 9), ("Bounded", "Periodic", "Bounded"), 1),         # walls in x, single exponential
     ((70, 17, 14), ("Periodic", "Bounded", "Bounded"), 4),        # several x tiles, partial tiles, two coefficient sets
     ((40, 12, 16), ("Periodic", "Periodic", "Periodic"), 2),      # Periodic z: WENO5 on every z face, z halo images
