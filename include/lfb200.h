@@ -227,6 +227,9 @@ int lfb_kept_info(lfb_handle *h, int id, int *is_f32, int *extents3, void **devi
  * no device synchronisation, between time steps); lfb_kept_trim returns the pooled memory to the device */
 int lfb_kept_release(lfb_handle *h, int id);
 int lfb_kept_trim(lfb_handle *h);
+/* put `count` blocks of `bytes` bytes into the pool ahead of time (before a pass), so that no cudaMalloc happens between
+ * queued time steps */
+int lfb_kept_reserve(lfb_handle *h, size_t bytes, int count);
 /* COLLECTIVE over the communicator of lfb_comm_init: assemble the GLOBAL parent array of a kept output on rank
  * `root` from every rank's y-slab (interior rows from their owners, outer halo rows from the first / last rank).
  * *gid is the new kept id on `root`, -1 elsewhere; with one rank *gid = id. */

@@ -1332,6 +1332,22 @@ extern "C" int lfb_kept_release(lfb_handle *h, int id)
     return LFB_OK;
 }
 
+// Put `count` blocks of `bytes` bytes into the pool ahead of time, so that kept outputs created between time steps find
+// their memory there (a cudaMalloc of a GB-sized block between queued stage kernels stalls the queue for milliseconds).
+extern "C" int lfb_kept_reserve(lfb_handle *h, size_t bytes, int count)
+{
+    if (!h || bytes == 0 || count < 0) return fail(LFB_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(h->device));
+    for (int q = 0; q < count; ++q) {
+        lfb_handle::Pooled pl;
+        pl.p = nullptr; pl.bytes = bytes; pl.fetched = nullptr;
+        cudaError_t err = cudaMalloc(&pl.p, bytes);
+        if (err != cudaSuccess) { cudaGetLastError(); return fail(LFB_ERR_CUDA, "device memory exhausted while reserving kept outputs (%s)", cudaGetErrorString(err)); }
+        h->kept_pool.push_back(pl);
+    }
+    return LFB_OK;
+}
+
 extern "C" int lfb_kept_trim(lfb_handle *h)
 {
     if (!h) return fail(LFB_ERR_ARG, "null handle");

@@ -285,6 +285,11 @@ class LagrangianFilter:
     def kept_release(self, kid: int):
         check(self.L.lfb_kept_release(self.h, kid))
 
+    def kept_reserve(self, count: int, dtype=np.float32, shape=None):
+        """Allocate `count` blocks for kept outputs of this dtype (parent shape) ahead of time."""
+        n = int(np.prod(shape or self.center_shape)) * np.dtype(dtype).itemsize
+        check(self.L.lfb_kept_reserve(self.h, n, int(count)))
+
     def kept_trim(self):
         """Return the memory of released kept outputs (pooled for reuse) to the device."""
         check(self.L.lfb_kept_trim(self.h))

@@ -329,6 +329,12 @@ def run_offline_Lagrangian_filter(config: OfflineFilterConfig, output_dtype=np.f
             phases[name] = now - t_mark
             t_mark = now
 
+        if store.on_device:
+            # the memory of the kept outputs is taken now, not between queued time steps: one pass's outputs (the backward
+            # pass reuses the forward pass's blocks as they are combined) and two output times of combined Float64 fields
+            n_spec = len(_output_specs(model, config))
+            model.kept_reserve((n_times + 1) * n_spec, output_dtype)
+            model.kept_reserve(2 * n_spec, np.float64)
         # forward pass
         feeder.begin(+1)
         feeder.ensure(0.0, 0.0)

@@ -87,3 +87,28 @@ def test_filter_output_file_has_the_reference_layout(tmp_path, golden_offline):
     # the .npz form keeps the same keys
     z = np.load(out.save(str(tmp_path / "filtered_output.npz")))
     assert f"timeseries/xi_u/{its[3]}" in z.files and z[f"timeseries/t/{its[3]}"] == out.times[3]
+
+
+def test_config_reads_a_series_written_by_the_writer(tmp_path, golden_sim):
+    """The input side of the file boundary: a simulation output written with the JLD2 layout (timeseries/<name>/<iter>,
+    timeseries/t/<iter>) is what OfflineFilterConfig(original_data_filename=...) opens (reference load_data,
+    utils:201-215); times, iteration keys and snapshots come back unchanged."""
+    path = str(tmp_path / "sim.jld2")
+    nt = len(golden_sim["t"])
+    its = [3 * n for n in range(nt)]
+    with JLD2Writer(path) as w:
+        for n, it in enumerate(its):
+            w.write(f"timeseries/t/{it}", float(golden_sim["t"][n]))
+            for name in ("u", "w", "b"):
+                w.write(f"timeseries/{name}/{it}", np.asfortranarray(golden_sim[name][n]))
+    g = lfb200.RectilinearGrid(size=(10, 10), x=(-5000, 5000), z=(-100, 0), topology=("Periodic", "Flat", "Bounded"))
+    cfg = lfb200.OfflineFilterConfig(original_data_filename=path, grid=g, var_names_to_filter=("b",), velocity_names=("u", "w"),
+                                     N=2, freq_c=1e-4 / 4)
+    src = cfg.source()
+    np.testing.assert_array_equal(src.times, golden_sim["t"])
+    assert cfg.T_start == golden_sim["t"][0] and cfg.T_end == golden_sim["t"][-1] and cfg.T_out == golden_sim["t"][1] - golden_sim["t"][0]
+    a = src.snapshot("w", 7)
+    assert a.dtype == golden_sim["w"].dtype and np.array_equal(a, golden_sim["w"][7])
+    with pytest.raises(ValueError, match="not found in original data"):
+        lfb200.OfflineFilterConfig(original_data_filename=path, grid=g, var_names_to_filter=("T",), velocity_names=("u", "w"),
+                                   N=2, freq_c=1e-4 / 4)
