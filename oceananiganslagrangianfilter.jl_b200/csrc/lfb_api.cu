@@ -204,7 +204,12 @@ static int select_kernel(lfb_handle *h)
     h->use_zmarch = 0;
     h->fold = 0;
     switch (h->desc.kernel) {
-    case LFB_KERNEL_AUTO: h->use_zmarch = ok_tma ? 3 : 0; break;
+    case LFB_KERNEL_AUTO:
+        // folded (Flat y) grids: a block marches Nz planes one after the other, so short lines (few blocks) are faster on
+        // the generic kernel, which spreads every cell over the GPU: 400 x 80 runs 0.039 ms per stage there against
+        // 0.071 ms folded, 8192 x 1024 runs 4.2 ms against 1.16 ms (scratch/bench_2d.py)
+        h->use_zmarch = (ok_tma && !(sup == 2 && h->L.N[0] < 2048)) ? 3 : 0;
+        break;
     case LFB_KERNEL_GENERIC: break;
     case LFB_KERNEL_ZTMA:
         if (!ok_tma) return fail(LFB_ERR_ARG, "the TMA z-marching kernel needs %s (and cuTensorMapEncodeTiled from the driver)", need);

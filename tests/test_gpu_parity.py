@@ -436,6 +436,7 @@ def test_ztma_with_absent_velocity_component(vel_names):
     ((96, 20), ("Bounded", "Flat", "Bounded"), ("T",), ("u", "w"), 2, False, False),               # walls in x
     ((64, 16), ("Periodic", "Flat", "Periodic"), ("b",), ("u", "w", "v"), 2, True, False),         # Periodic z, v on the Flat axis, backward
     ((80, 24), ("Bounded", "Flat", "Bounded"), ("b",), ("u", "w", "v"), 2, False, True),           # boundary relaxation
+    ((2080, 12), ("Periodic", "Flat", "Bounded"), ("b",), ("u", "w"), 2, False, False),             # long enough for kernel = "auto"
 ])
 def test_ztma_folded_2d_grids_vs_oracle(size, topology, var_names, vel_names, N, backward, relax):
     """Grids with a Flat y axis (every 2-D example of the reference) on the TMA z-march kernel: the x line is folded
@@ -446,10 +447,16 @@ def test_ztma_folded_2d_grids_vs_oracle(size, topology, var_names, vel_names, N,
     fields = make_series(g, times, var_names=var_names, velocity_names=vel_names, T_period=2.0)
     fp = lfb200.set_offline_BW2_filter_params(N=N, freq_c=2 * np.pi / 2.0)
     kw = {}
+    if size[0] >= 2048:      # what "auto" picks
+        m0 = lfb200.LagrangianFilter(g, var_names_to_filter=var_names, velocity_names=vel_names,
+                                     filter_params=lfb200.set_offline_BW2_filter_params(N=N, freq_c=1.0))
+        assert m0.kernel_name == "ztma"
+        m0.close()
     if relax:
         x, z = g.nodes(0)[:, None, None], g.nodes(2)[None, None, :]
         kw = dict(relax_timescale=0.7, mask=np.asfortranarray(np.exp(-((x - g.origin[0]) / 6.0) ** 2) + 0.1 * np.cos(z) ** 2))
-    o, m = make_pair(g, var_names, vel_names, fp, times, fields, kernel="auto", backward=backward, **kw)
+    # kernel = "auto" keeps lines shorter than 2048 cells on the generic kernel (faster at those sizes)
+    o, m = make_pair(g, var_names, vel_names, fp, times, fields, kernel="ztma", backward=backward, **kw)
     assert m.kernel_name == "ztma"
     names = oracle_names(var_names, vel_names, fp)
     o.init_from_data(); m.init_from_data()
