@@ -160,7 +160,9 @@ int lfb_set_mask(lfb_handle *h, const double *parent);
  * lagrangian_filter_tendency_kernel_functions.jl:56).  Needs desc.immersed = 1.
  * cell_heights (or NULL: whole cells, GridFittedBottom): parent array of the cell heights dz(i,j,k) of a
  * PartialCellBottom (the lee-wave example's choice); they enter the flux divergence through Oceananigans'
- * partial-cell metrics Ax = dy min(dz[i-1], dz[i]), Ay = dx min(dz[j-1], dz[j]), Az = dx dy, V = dx dy dz. */
+ * partial-cell metrics Ax = dy min(dz[i-1], dz[i]), Ay = dx min(dz[j-1], dz[j]), Az = dx dy, V = dx dy dz.
+ * Whole-cell immersed grids run on the TMA z-march kernel (face codes as one more TMA tile); with cell_heights the
+ * generic kernel is used (LFB_KERNEL_ZTMA is then refused). */
 int lfb_set_immersed(lfb_handle *h, const double *parent, const double *cell_heights);
 
 /* ---- state ----------------------------------------------------------------------------------- */

@@ -33,6 +33,7 @@ cudaError_t lfb_launch_centre_velocity(double *dst, const double *vel, const Lfb
                                        cudaStream_t stream);
 cudaError_t lfb_launch_scale(double *dst, const double *src, double factor, int64_t n, cudaStream_t stream);
 cudaError_t lfb_launch_mask_immersed(double *U, const double *imm, int64_t len, int n_fields, cudaStream_t stream);
+cudaError_t lfb_launch_build_face_codes(double *codes, const double *imm, const LfbLayout *L, cudaStream_t stream);
 cudaError_t lfb_launch_output(double *out, const LfbOutputParams *P, cudaStream_t stream);
 cudaError_t lfb_launch_combine(double *out, const double *fwd, const double *lo, const double *hi, double w,
                                double sign, int64_t n, cudaStream_t stream);
@@ -87,6 +88,7 @@ struct lfb_handle {
     double    *mask;
     double    *imm;                        // immersed-cell flags (desc.immersed), set by lfb_set_immersed
     double    *dzc;                        // partial-cell heights (optional)
+    double    *codes;                      // face codes of the immersed grid for the TMA z-march kernel
     int        imm_set;
     double     last_dt;                    // AB2: the previous step's dt (an Euler step whenever it changes)
     double    *zero_field;                 // velocity components that are not in velocity_names (TMA z-march path)
@@ -200,7 +202,7 @@ static int select_kernel(lfb_handle *h)
     const int fold_v = ((h->desc.velocity_mask >> 1) & 1) && h->desc.n_vars >= LFB_MAX_VARS;   // v travels in the last variable slot
     const int ok_tma = sup && !h->desc.strict && !(sup == 2 && fold_v);
     const char *need = "a 3-D grid (or a Flat y axis with a non-Flat x and z) with Nx >= 8, Ny >= 4, Nz >= 8, halos >= 3, at least "
-                       "one velocity component, WENO(order=5) advection, no immersed boundary and strict = 0";
+                       "one velocity component, WENO(order=5) advection, whole cells if the grid is immersed (no cell_heights) and strict = 0";
     h->use_zmarch = 0;
     h->fold = 0;
     switch (h->desc.kernel) {
@@ -350,7 +352,7 @@ extern "C" int lfb_create(const lfb_desc *desc, lfb_handle **out)
     // routed through lfb_destroy without touching garbage or leaking what was already allocated
     h->desc = *desc;
     h->device = desc->device;
-    h->U[0] = h->U[1] = h->G = h->scratch = h->mask = h->zero_field = h->imm = h->dzc = nullptr;
+    h->U[0] = h->U[1] = h->G = h->scratch = h->mask = h->zero_field = h->imm = h->dzc = h->codes = nullptr;
     h->imm_set = 0; h->last_dt = INFINITY;
     h->staging = nullptr; h->staging_bytes = 0;
     for (int f = 0; f < N_FIELD_IDS; ++f) h->cur_in[f] = nullptr;
@@ -384,7 +386,7 @@ extern "C" int lfb_destroy(lfb_handle *h)
     for (cudaEvent_t e : h->slot_used) if (e) cudaEventDestroy(e);
     for (auto &pr : h->timing) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto &pr : h->timing_free) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
-    for (double *p : {h->U[0], h->U[1], h->G, h->scratch, h->mask, h->imm, h->dzc, h->zero_field, h->send_lo, h->send_hi, h->recv_lo, h->recv_hi})
+    for (double *p : {h->U[0], h->U[1], h->G, h->scratch, h->mask, h->imm, h->dzc, h->codes, h->zero_field, h->send_lo, h->send_hi, h->recv_lo, h->recv_hi})
         if (p) cudaFree(p);
     for (int f = 0; f < N_FIELD_IDS; ++f) if (h->cur_in[f]) cudaFree(h->cur_in[f]);
     for (int f = 0; f < 3; ++f) if (h->vin_alt[f]) cudaFree(h->vin_alt[f]);
@@ -556,6 +558,19 @@ extern "C" int lfb_set_mask(lfb_handle *h, const double *parent)
     return LFB_OK;
 }
 
+// face codes of an immersed grid for the TMA z-march kernel (rebuilt when the slab decomposition changes the global indices)
+static int build_face_codes(lfb_handle *h)
+{
+    if (h->use_zmarch != 3 || !h->imm) return LFB_OK;
+    const size_t fbytes = (size_t)h->L.len * sizeof(double);
+    if (!h->codes) { CU(cudaMalloc(&h->codes, fbytes)); }
+    CU(cudaMemsetAsync(h->codes, 0, fbytes, h->compute));
+    CU(lfb_launch_build_face_codes(h->codes, h->imm, &h->L, h->compute));
+    h->launches++;
+    CU(cudaStreamSynchronize(h->compute));
+    return LFB_OK;
+}
+
 extern "C" int lfb_set_immersed(lfb_handle *h, const double *parent, const double *cell_heights)
 {
     if (!h || !parent) return fail(LFB_ERR_ARG, "null argument");
@@ -577,6 +592,18 @@ extern "C" int lfb_set_immersed(lfb_handle *h, const double *parent, const doubl
         h->launches++;
         CU(cudaStreamSynchronize(h->compute));
     } else if (h->dzc) { cudaFree(h->dzc); h->dzc = nullptr; }
+    if (h->use_zmarch == 3 && h->dzc) {
+        // partial cells change the face areas and cell volumes: generic kernel
+        if (h->desc.kernel == LFB_KERNEL_ZTMA)
+            return fail(LFB_ERR_ARG, "the TMA z-marching kernel handles immersed grids with whole cells only (no cell_heights)");
+        if (h->fold)        // the generic kernel writes the periodic x images itself again
+            h->L.fuse_halo[0] = h->L.topo[0] == LFB_PERIODIC && h->L.H[0] > 0 && h->L.N[0] >= 2 * h->L.H[0];
+        h->use_zmarch = 0; h->fold = 0;
+    }
+    {
+        int rc = build_face_codes(h);
+        if (rc) return rc;
+    }
     h->imm_set = 1;
     h->halos_valid = 0;
     return LFB_OK;
@@ -818,6 +845,7 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
     P.relax = h->desc.relaxation;
     P.imm = h->imm;
     P.dzc = h->dzc;
+    P.codes = (h->use_zmarch == 3 && update) ? h->codes : nullptr;
     memcpy(P.items, h->items, sizeof(LfbItem) * h->n_items);
     int s1, s2, interp; double w1, w2;
     int rc = bracket(h, tau, &s1, &s2, &w1, &w2, &interp);
@@ -926,10 +954,10 @@ static int launch_stage(lfb_handle *h, double tau, double dt, double gamma, doub
     const bool overlap = update && h->nranks > 1 && Ny >= 4 * strip;
     // Bounded y on the TMA kernel: only the tile rows next to the walls need the general instantiation (buffer schemes);
     // rows at least one tile row away from both walls run the all-periodic one
-    const bool split_walls = ztma && !h->fold && h->L.topo[1] == LFB_BOUNDED && Ny >= 4 * strip;
+    const bool split_walls = ztma && !h->fold && !h->imm && h->L.topo[1] == LFB_BOUNDED && Ny >= 4 * strip;
     // Bounded x likewise: the x tiles whose faces all lie in 4 .. Nx - 2 (tiles 1 .. xt_hi - 1) need no buffer schemes
     const int n_xt = (h->L.N[0] + 31) / 32, xt_hi = h->L.N[0] >= 35 ? (h->L.N[0] - 35) / 32 + 1 : 0;
-    const bool split_x = ztma && !h->fold && h->L.topo[0] == LFB_BOUNDED && xt_hi >= 3;
+    const bool split_x = ztma && !h->fold && !h->imm && h->L.topo[0] == LFB_BOUNDED && xt_hi >= 3;
     auto launch_rows = [&](int j0, int j1, int jb0, int jb1, cudaStream_t st) -> int {
         P.j0 = j0; P.j1 = j1; P.jb0 = jb0; P.jb1 = jb1;
         const int g0 = h->L.goff[1] + j0, g1 = h->L.goff[1] + j1;
@@ -1484,7 +1512,13 @@ extern "C" int lfb_comm_init(lfb_handle *h, const void *id128, int rank, int nra
     CU(cudaMalloc(&h->send_hi, h->halo_elems * sizeof(double)));
     CU(cudaMalloc(&h->recv_lo, h->halo_elems * sizeof(double)));
     CU(cudaMalloc(&h->recv_hi, h->halo_elems * sizeof(double)));
-    return select_kernel(h);
+    int rc = select_kernel(h);
+    if (rc) return rc;
+    if (h->imm_set) {
+        if (h->use_zmarch == 3 && h->dzc) { h->use_zmarch = 0; h->fold = 0; }
+        rc = build_face_codes(h);
+    }
+    return rc;
 }
 
 // ---- introspection -------------------------------------------------------------------------------

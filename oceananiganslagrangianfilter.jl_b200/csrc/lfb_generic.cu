@@ -310,6 +310,39 @@ extern "C" cudaError_t lfb_launch_centre_velocity(double *dst, const double *vel
     return cudaGetLastError();
 }
 
+// Face codes of an immersed grid for the TMA z-march kernel (LfbStageParams::codes): per cell the scheme of its west,
+// south, bottom and top face -- the same chain selection as the generic kernel (lfb_face_kind, WENO(order=5)) -- the domain
+// walls, the faces no flux crosses (they touch an immersed cell) and the cell's immersed flag.  Cells one column / row
+// beyond the interior are coded too (east / north faces of the last tile column / row).
+__global__ void lfb_build_face_codes(double *codes, const double *imm, LfbLayout L)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+    if (i > L.N[0] + 1) return;
+    const int ijk[3] = {i, j, k};
+    const int64_t idx = L.at(i, j, k);
+    auto face = [&](int ax, int up) -> int {          // low face of the cell (up = 0) or of the cell above it along ax
+        if (L.topo[ax] == LFB_FLAT) return 5;
+        const int64_t s = L.stride[ax];
+        const int m = L.goff[ax] + ijk[ax] + 1 + up;
+        const double *f = imm + idx + up * s;
+        if (L.topo[ax] == LFB_BOUNDED && (m < 1 || m > L.NG[ax] + 1)) return 5;        // beyond the domain: never used
+        if (f[-s] != 0.0 || f[0] != 0.0) return 7;
+        if (L.topo[ax] == LFB_BOUNDED && m == 1) return 1;
+        if (L.topo[ax] == LFB_BOUNDED && m == L.NG[ax] + 1) return 0;
+        const int kind = lfb_face_kind(LFB_ADVECTION_WENO5, m, L.NG[ax], L.topo[ax], f, s);
+        return kind == LFB_K_W5 ? 5 : kind == LFB_K_W3 ? 3 : 2;
+    };
+    const int code = face(0, 0) + 8 * face(1, 0) + 64 * face(2, 0) + 512 * face(2, 1) + 4096 * (imm[idx] != 0.0 ? 1 : 0);
+    codes[idx] = (double)code;
+}
+
+extern "C" cudaError_t lfb_launch_build_face_codes(double *codes, const double *imm, const LfbLayout *L, cudaStream_t stream)
+{
+    dim3 block(128, 1, 1), grid((L->N[0] + 2 + 127) / 128, L->N[1] + (L->topo[1] == LFB_FLAT ? 0 : 2), L->N[2]);
+    lfb_build_face_codes<<<grid, block, 0, stream>>>(codes, imm, *L);
+    return cudaGetLastError();
+}
+
 // mask_immersed_field! over a stack of fields (whole padded arrays, halos too): zero where the flag is set
 __global__ void lfb_mask_immersed(double *U, const double *imm, int64_t len, int n_fields)
 {

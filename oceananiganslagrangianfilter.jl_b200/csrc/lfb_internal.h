@@ -58,6 +58,10 @@ struct LfbStageParams {
     int     relax;
     const double *imm;        // immersed-cell flags (0 / 1), or null: no immersed boundary
     const double *dzc;        // PartialCellBottom: cell heights dz(i,j,k), or null: regular cells
+    // immersed boundary on the TMA z-march kernel: per cell the schemes of its west / south / bottom / top face and its
+    // immersed flag, packed by lfb_build_face_codes (code = w + 8 s + 64 b + 512 t + 4096 immersed; face code 5 / 3 / 2 =
+    // WENO5 / WENO3 / Centered2, 1 / 0 = lower / upper domain wall, 7 = no flux: the face touches an immersed cell)
+    const double *codes;
     LfbItem items[LFB_MAX_ITEMS];
     // inputs at the stage time: u, v, w and the original variables, already interpolated in time (and
     // negated on the backward pass) by lfb_interp_inputs, or aliased to a snapshot slot when the stage

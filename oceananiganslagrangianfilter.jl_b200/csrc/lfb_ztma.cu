@@ -73,6 +73,7 @@ struct LfbZtParams {
     alignas(64) CUtensorMap mF[LFB_MAX_VARS];    // original variables, snapshot at or before the stage time, box 32 x TY
     alignas(64) CUtensorMap mF2[LFB_MAX_VARS];   // ... snapshot after it (linear interpolation in the forcing term)
     alignas(64) CUtensorMap mM;                  // relaxation mask (boundary_relaxation), box 32 x TY
+    alignas(64) CUtensorMap mK;                  // face codes of an immersed grid, box 34 x (TY+1)
     // store maps (box 32 x TY) of U_new and G for the two row ranges of a launch: their extents end at column Nx and at
     // row j1 of the range, so the surplus columns / rows of partial tiles are clipped by the TMA unit
     alignas(64) CUtensorMap mSU[2];
@@ -84,7 +85,7 @@ struct LfbZtParams {
 // Shared memory (doubles).  Two tile geometries: pitch 40 (x halo of 4: tracer planes, u, x fluxes; a thread's
 // own cell sits at (ty [+3]) * 40 + tx + 4) and pitch 32 (v, w, G^-, forcing variable, y fluxes; own cell at
 // ty * 32 + tx).  Per-tracer tiles are strided by CTP (pitch 40) or VT (pitch 32) doubles.
-template <int NSUB, int TY>
+template <int NSUB, int TY, bool IMMK = false>
 struct ZtSmem {
     static constexpr int CH = TY + 6;
     static constexpr int CTP = CH * ZT_CW;                       // haloed tracer tile = the TMA box (multiple of 16)
@@ -93,8 +94,10 @@ struct ZtSmem {
     static constexpr int VT = (TY + 1) * 32;                     // [TY+1][32]
     static constexpr int OFF_U = 0, OFF_V = UT, OFF_W = OFF_V + VT, OFF_G = OFF_W + 2 * NT, OFF_F = OFF_G + NSUB * VT,
                          OFF_F2 = OFF_F + NT,                    // forcing variable: the two bracketing snapshots
-                         OFF_M = OFF_F2 + NT;                    // relaxation mask
-    static constexpr int ISLOT = OFF_M + NT;                     // doubles per input slot
+                         OFF_M = OFF_F2 + NT,                    // relaxation mask
+                         OFF_K = OFF_M + NT;                     // face codes of an immersed grid: [TY+1][34] (pitch 34), padded to 128 B
+    static constexpr int KP = 34, KT = IMMK ? ((TY + 1) * KP + 15) / 16 * 16 : 0;     // only the immersed instantiations carry it
+    static constexpr int ISLOT = OFF_K + KT;                     // doubles per input slot
     static constexpr int CSLOT = NSUB * CTP;
     static constexpr int FXT = ZT_TMA_STORE ? UT : CTP;          // x-flux tile of a tracer: [TY][40] (or the tracer-tile geometry)
     static constexpr int FBUF = NSUB * (FXT + VT);               // Fx[NSUB], Fy[NSUB][TY+1][32]
@@ -311,13 +314,24 @@ __device__ __noinline__ double zt_top_face_buffer(int m, int Nz, double cw, doub
     return 0.5 * (ck + ck1);
 }
 
+// ... on an immersed grid the scheme comes from the face code (3 = WENO3-Z, 2 = Centered2, 0 / 1 = domain wall, 7 = no flux)
+__device__ __noinline__ double zt_top_face_coded(int order, double cw, double d1, double d2, double d3, double ck, double ck1)
+{
+    if (order == 3) return zt_top_face_buffer(3, 1 << 30, cw, d1, d2, d3, ck, ck1);
+    if (order == 2) return 0.5 * (ck + ck1);
+    return ck;
+}
+
 // WALLS: the general instantiation -- Bounded x or y axes (buffer schemes next to those walls), Periodic z and boundary relaxation;
 // compiled separately so that the all-periodic form keeps its register allocation.
 // FLATY: the folded form for grids with a Flat y axis (LfbStageParams::fold): no y faces, no v tile.
-template <int NSUB, int TY, bool WALLS, bool FLATY>
+// WALLS = 2: the general instantiation on an immersed grid (whole cells): the scheme of every face and the immersed flag of
+// every cell come from the packed code field (LfbStageParams::codes), one more TMA tile per plane.
+template <int NSUB, int TY, int WALLS, bool FLATY>
 __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(const __grid_constant__ LfbZtParams P)
 {
-    using SM = ZtSmem<NSUB, TY>;
+    constexpr bool IMM = WALLS == 2;
+    using SM = ZtSmem<NSUB, TY, WALLS == 2>;
     extern __shared__ __align__(1024) double zt_smem[];
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(zt_smem);
     constexpr int ROW_B = 8 * ZT_CW;
@@ -325,7 +339,8 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
                        VT_B = 8u * SM::VT, NT_B = 8u * SM::NT;
     constexpr unsigned oC = 8u * SM::O_C, oIN = 8u * SM::O_IN, oFL = 8u * SM::O_FL, oBAR = 8u * SM::O_BAR;
     constexpr unsigned oU = oIN + 8u * SM::OFF_U, oV = oIN + 8u * SM::OFF_V, oW = oIN + 8u * SM::OFF_W,
-                       oG = oIN + 8u * SM::OFF_G, oF = oIN + 8u * SM::OFF_F, oF2 = oIN + 8u * SM::OFF_F2, oM = oIN + 8u * SM::OFF_M;
+                       oG = oIN + 8u * SM::OFF_G, oF = oIN + 8u * SM::OFF_F, oF2 = oIN + 8u * SM::OFF_F2, oM = oIN + 8u * SM::OFF_M, oK = oIN + 8u * SM::OFF_K;
+    constexpr unsigned KROW_B = 8u * SM::KP;
     constexpr unsigned FXT_B = 8u * SM::FXT, UT_B = 8u * SM::UT, oOUT = 8u * SM::O_OUT, OUTBUF_B = 8u * SM::OUTBUF;
     constexpr unsigned oFX = oFL, oFY = oFL + NSUB * FXT_B;
     const LfbStageParams &S = P.S;
@@ -370,7 +385,8 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         // One loop for the whole warp (bar.sync is warp-aligned): the producer lane issues the TMA loads of the planes
         // ZT_D ahead, the face lanes compute their edge faces, idle lanes only keep the barrier count.
         const int cx = L.xoff + i0 - ZT_HX, cy = L.H[1] + j0 - 3, ix = L.xoff + i0, iy = L.H[1] + j0, z0 = L.H[2];
-        const unsigned in_bytes = 8u * (ZT_CW * TY + (FLATY ? 0 : 32 * (TY + 1)) + 2 * 32 * TY) + (use_G ? NSUB * NT_B : 0u) + (item_var ? 2 * NT_B : 0u) + (relax ? NT_B : 0u);
+        const unsigned in_bytes = 8u * (ZT_CW * TY + (FLATY ? 0 : 32 * (TY + 1)) + 2 * 32 * TY) + (use_G ? NSUB * NT_B : 0u) + (item_var ? 2 * NT_B : 0u) + (relax ? NT_B : 0u) +
+                                  (IMM ? 8u * SM::KP * (TY + 1) : 0u);
         auto issue_C = [&](int pz, unsigned bar) {            // haloed tracer planes at z index pz (-2 .. Nz+2)
             const unsigned dst = sbase + oC + (unsigned)((pz + 2) & (ZT_RC - 1)) * CSLOT_B;
 #pragma unroll
@@ -394,6 +410,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
                 tma_load_3d(is + oF2, &P.mF2[src_map], ix, iy, z0 + g, bar);
             }
             if (relax) tma_load_3d(is + oM, &P.mM, ix, iy, z0 + g, bar);
+            if (IMM) tma_load_3d(is + oK, &P.mK, ix, iy, z0 + g, bar);
         };
         // L2 prefetch of the tiles of group g (the shared-memory rings only allow the loads themselves to run one barrier
         // interval ahead; the prefetch runs ZT_PF planes ahead and costs no shared memory)
@@ -540,8 +557,16 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
                     const unsigned cs = (unsigned)((k + 2) & (ZT_RC - 1)) * CSLOT_B;
                     const double q = lds(aQ + (unsigned)(k & (ZT_RI - 1)) * ISLOT_B);
                     double cf = kind == 1 ? zt_face<ROW_B>(aT + cs, q, K) : zt_face<8>(aT + cs, q, K);
-                    if (WALLS && h_order != 5) cf = kind == 1 ? zt_face_buffer<ROW_B>(aT + cs, q, h_order) : zt_face_buffer<8>(aT + cs, q, h_order);
-                    sts(aF + (unsigned)(k & (ZT_RI - 1)) * FBUF_B, q * cf);
+                    if constexpr (IMM) {
+                        // south face of row TY / west face of column 32: the code of that cell
+                        const int code = (int)lds(sbase + oK + (unsigned)(k & (ZT_RI - 1)) * ISLOT_B + 8u * (ty * SM::KP + tx));
+                        const int order = kind == 1 ? (code >> 3) & 7 : code & 7;
+                        if (order != 5) cf = kind == 1 ? zt_face_buffer<ROW_B>(aT + cs, q, order) : zt_face_buffer<8>(aT + cs, q, order);
+                        sts(aF + (unsigned)(k & (ZT_RI - 1)) * FBUF_B, order == 7 ? 0.0 : q * cf);
+                    } else {
+                        if (WALLS && h_order != 5) cf = kind == 1 ? zt_face_buffer<ROW_B>(aT + cs, q, h_order) : zt_face_buffer<8>(aT + cs, q, h_order);
+                        sts(aF + (unsigned)(k & (ZT_RI - 1)) * FBUF_B, q * cf);
+                    }
                 }
             }
             __syncwarp();
@@ -697,6 +722,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     block_barrier();
 
     double part[NS][ZT_PB], base[NS][ZT_PB];     // own part of the tendency / of the substep, carried over the barrier
+    [[maybe_unused]] int cell_imm[ZT_PB] = {};   // immersed grids: this cell of plane p lies inside the boundary
 
     // Faces and own tendency part of plane k.  J >= 0: k = 8 m + 2 + J is known modulo the ring period, so every
     // ring offset, flux buffer and mbarrier parity is an immediate and the plane is interior (top face index
@@ -715,10 +741,20 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         const ZtUp ux = zt_up<8>(cu), uy = zt_up<ROW_B>(cv);
         const double ue = lds(a40 + oU + is + 8), vn = FLATY ? 0.0 : lds(a32 + oV + is + 8 * 32);
         const double sA = lds(aS1 + is), sB = lds(aS2 + is);
-        const bool z_weno = FAST || zper || (k >= 2 && k <= Nz - 4);
+        const bool z_weno = IMM || FAST || zper || (k >= 2 && k <= Nz - 4);      // immersed grids: decided per cell by the code
         const bool left = zt_positive(cw);
         const unsigned ml = z_weno ? __ballot_sync(0xffffffffu, left) : 0u;
         const double dux = ue - cu, dvy = vn - cv, dwz = cw - wb0;
+        // immersed grid: schemes of this cell's west / south / bottom / top face and its immersed flag
+        int ow = ox, os = oy;
+        [[maybe_unused]] int ob = 5, ot = 5;
+        bool buffers = WALLS && tile_walls;
+        if constexpr (IMM) {
+            const int code = (int)lds(sbase + oK + is + 8u * (ty * SM::KP + tx));
+            ow = code & 7; os = (code >> 3) & 7; ob = (code >> 6) & 7; ot = (code >> 9) & 7;
+            cell_imm[p] = (code >> 12) & 1;
+            buffers = true;
+        }
         double ckk[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) ckk[s] = ck[s];
@@ -726,12 +762,12 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
         for (int s = 0; s < NS; ++s) {
             const unsigned aCk = A40S(s) + oCk;
             double fx = zt_face_up<8>(aCk, ux, K), fy = FLATY ? 0.0 : zt_face_up<ROW_B>(aCk, uy, K);
-            if (WALLS && tile_walls) {                        // buffer schemes next to the walls of Bounded x / y axes
-                if (ox != 5) fx = zt_face_buffer<8>(aCk, cu, ox);
-                if (!FLATY && oy != 5) fy = zt_face_buffer<ROW_B>(aCk, cv, oy);
+            if (buffers) {                                    // buffer schemes next to walls / the immersed boundary
+                if (ow != 5) fx = zt_face_buffer<8>(aCk, cu, ow);
+                if (!FLATY && os != 5) fy = zt_face_buffer<ROW_B>(aCk, cv, os);
             }
-            const double Fw = cu * fx;
-            const double Fs = cv * fy;
+            double Fw = cu * fx, Fs = cv * fy;
+            if constexpr (IMM) { if (ow == 7) Fw = 0.0; if (os == 7) Fs = 0.0; }
             sts(AFX(s) + fb, Fw);
             if (!FLATY) sts(A32S(s) + oFY + fb, Fs);
             if (!FAST && k == 0) {
@@ -741,10 +777,16 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
                                                     : ck[s] - zt_inc(d3[s], d2[s], d1[s], d0[s], K));
                 } else {
                     Fb[s] = wb0 * ck[s];                     // wall face m = 1: Centered2 on the mirrored halo
+                    if constexpr (IMM) { if (ob == 7) Fb[s] = 0.0; }
                 }
             }
             double ct;
-            if (z_weno) {
+            bool coded = false;
+            if constexpr (IMM) {
+                if (ot != 5) { ct = zt_top_face_coded(ot, cw, d1[s], d2[s], d3[s], ck[s], ck1[s]); coded = true; }
+            }
+            if (coded) {
+            } else if (z_weno) {
                 // the window is used by a warp-uniform branch per direction (both only in warps that straddle w = 0)
                 ct = ck1[s];
                 if (ml != 0xffffffffu) ct = ck1[s] - zt_inc_q(d4[s], d3[s], d2[s], d1[s], Qd[s], Qc[s], Qb[s], K);
@@ -752,7 +794,8 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             } else {
                 ct = zt_top_face_buffer(k + 2, Nz, cw, d1[s], d2[s], d3[s], ck[s], ck1[s]);
             }
-            const double Ft = cw * ct;
+            double Ft = cw * ct;
+            if constexpr (IMM) { if (ot == 7) Ft = 0.0; }
             // ---- own part of the tendency: c du - dF per axis in units of face velocity, forcing, G^- part of the substep ----
             double forcing = fma(kA[s], sA, fma(kB[s], sB, k_own * ck[s]));
             if (relax) forcing = fma(lds(a32 + oM + is) * lds(ARX(s) + 24), fma(lds(ARX(s)), fma(lds(ARX(s) + 8), sA, lds(ARX(s) + 16) * sB), -ck[s]), forcing);
@@ -794,7 +837,8 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             double Gn;
             if (FLATY) Gn = fma(nrdx, Fe, part[s][p]);
             else { const double Fn = lds(A32S(s) + oFY + fb + 8 * 32); Gn = fma(nrdx, Fe, fma(nrdy, Fn, part[s][p])); }
-            const double unew = fma(dtg, Gn, base[s][p]);
+            double unew = fma(dtg, Gn, base[s][p]);
+            if constexpr (IMM) { if (cell_imm[p]) unew = 0.0; }   // mask_immersed_field! (update_lagrangian_filter_state.jl:22-24)
 #if ZT_TMA_STORE
             // out-buffer of this barrier interval: tiles [TY][32] of U_new and G^n per plane and tracer
             {
@@ -939,7 +983,7 @@ static bool zt_foldable(const LfbLayout &L)
 extern "C" int lfb_ztma_supported(const LfbStageParams *P)
 {
     const LfbLayout &L = P->L;
-    if (P->advect != LFB_ADVECTION_WENO5 || P->imm || (P->relax && !P->mask)) return 0;
+    if (P->advect != LFB_ADVECTION_WENO5 || P->dzc || (P->relax && !P->mask)) return 0;     // immersed grids: whole cells only
     const bool fold = zt_foldable(L);
     if (!fold && (L.topo[0] == LFB_FLAT || L.topo[1] == LFB_FLAT || L.topo[2] == LFB_FLAT)) return 0;
     if (L.topo[2] == LFB_PERIODIC && L.N[2] < 2 * L.H[2]) return 0;
@@ -952,10 +996,10 @@ extern "C" int lfb_ztma_supported(const LfbStageParams *P)
 
 extern "C" int lfb_ztma_tile_rows(void) { return ZT_TY; }
 
-template <int NSUB, int TY, bool WALLS, bool FLATY>
+template <int NSUB, int TY, int WALLS, bool FLATY>
 static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
 {
-    using SM = ZtSmem<NSUB, TY>;
+    using SM = ZtSmem<NSUB, TY, WALLS == 2>;
     // the attribute is per device (a process may hold handles on several GPUs)
     static bool configured[64] = {};
     int dev = 0;
@@ -984,7 +1028,7 @@ static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
         const int64_t shift = R.xoff - ZT_HX;
         auto mv = [&](const double *p) { return p ? p + shift : p; };
         SS.U_old = mv(S->U_old); SS.U_new = const_cast<double *>(mv(S->U_new)); SS.G = const_cast<double *>(mv(S->G));
-        SS.scratch = const_cast<double *>(mv(S->scratch)); SS.mask = mv(S->mask);
+        SS.scratch = const_cast<double *>(mv(S->scratch)); SS.mask = mv(S->mask); SS.codes = mv(S->codes);
         for (int a = 0; a < 3; ++a) {
             SS.vel[a] = mv(S->vel[a]);
             SS.pf.s1[a] = mv(S->pf.s1[a]); SS.pf.s2[a] = mv(S->pf.s2[a]); SS.pf.dst[a] = const_cast<double *>(mv(S->pf.dst[a]));
@@ -1009,6 +1053,7 @@ static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
             bad |= zt_make_map(&P.mF2[q], L, SS.var_fused ? SS.var2[q] : SS.var[q], 0, 32, TY, 1, fold_rows);
         }
     if (S->relax) bad |= zt_make_map(&P.mM, L, SS.mask, 0, 32, TY, 1, fold_rows);
+    if (WALLS == 2) bad |= zt_make_map(&P.mK, L, SS.codes, 0, SM::KP, TY + 1, 1, fold_rows);
 #if ZT_TMA_STORE
     for (int r = 0; r < 2; ++r) {
         const int jend = r == 0 ? SS.j1 : SS.jb1;
@@ -1034,10 +1079,14 @@ extern "C" cudaError_t lfb_launch_stage_ztma(const LfbStageParams *P, cudaStream
     if (P->j1 <= P->j0) return cudaSuccess;
     const bool walls = (P->L.topo[0] == LFB_BOUNDED && !P->plain_cols) || (P->L.topo[1] == LFB_BOUNDED && !P->plain_rows) ||
                        P->L.topo[2] == LFB_PERIODIC || P->relax;                     // the general instantiation
-    if (P->fold) {
-        if (walls) return P->single_exp ? zt_launch<1, ZT_TY, true, true>(P, stream) : zt_launch<2, ZT_TY, true, true>(P, stream);
-        return P->single_exp ? zt_launch<1, ZT_TY, false, true>(P, stream) : zt_launch<2, ZT_TY, false, true>(P, stream);
+    if (P->codes) {                                    // immersed grid: general instantiation with face codes
+        if (P->fold) return P->single_exp ? zt_launch<1, ZT_TY, 2, true>(P, stream) : zt_launch<2, ZT_TY, 2, true>(P, stream);
+        return P->single_exp ? zt_launch<1, ZT_TY, 2, false>(P, stream) : zt_launch<2, ZT_TY, 2, false>(P, stream);
     }
-    if (walls) return P->single_exp ? zt_launch<1, ZT_TY, true, false>(P, stream) : zt_launch<2, ZT_TY, true, false>(P, stream);
-    return P->single_exp ? zt_launch<1, ZT_TY, false, false>(P, stream) : zt_launch<2, ZT_TY, false, false>(P, stream);
+    if (P->fold) {
+        if (walls) return P->single_exp ? zt_launch<1, ZT_TY, 1, true>(P, stream) : zt_launch<2, ZT_TY, 1, true>(P, stream);
+        return P->single_exp ? zt_launch<1, ZT_TY, 0, true>(P, stream) : zt_launch<2, ZT_TY, 0, true>(P, stream);
+    }
+    if (walls) return P->single_exp ? zt_launch<1, ZT_TY, 1, false>(P, stream) : zt_launch<2, ZT_TY, 1, false>(P, stream);
+    return P->single_exp ? zt_launch<1, ZT_TY, 0, false>(P, stream) : zt_launch<2, ZT_TY, 0, false>(P, stream);
 }

@@ -123,6 +123,39 @@ def test_immersed_boundary_3d(strict):
     m.close(); o.close()
 
 
+@pytest.mark.parametrize("size,topology,vel_names,N,backward", [
+    ((40, 20, 16), ("Periodic", "Periodic", "Bounded"), ("u", "v", "w"), 2, False),      # a 3-D bump under a periodic ocean
+    ((36, 18, 12), ("Periodic", "Bounded", "Bounded"), ("u", "v", "w"), 1, True),        # channel, single exponential, backward pass
+    ((70, 9, 14), ("Bounded", "Periodic", "Bounded"), ("u", "v", "w"), 4, False),        # walls in x, partial tiles, two coefficient sets
+    ((96, 1, 20), ("Periodic", "Flat", "Bounded"), ("u", "w"), 2, False),                # the lee-wave shape on the folded kernel
+])
+def test_immersed_boundary_on_the_tma_kernel(size, topology, vel_names, N, backward):
+    """Whole-cell immersed grids (GridFittedBottom) on the TMA z-march kernel: the scheme of every face and the immersed
+    flag of every cell travel as one more TMA tile of packed codes (lfb_build_face_codes), fluxes through faces that touch
+    the boundary vanish, cells inside stay zero; against the CPU oracle on the same inputs."""
+    nonflat = [n for n, t in zip(size, topology) if t != "Flat"]
+    g0 = lfb200.RectilinearGrid(size=tuple(nonflat), extent=tuple(float(n) for n in nonflat), topology=topology)
+    y_dep = topology[1] != "Flat"
+    g = lfb200.ImmersedBoundaryGrid(g0, lfb200.GridFittedBottom(_bump(g0, 0.45 * g0.Lz, 0.12 * g0.Lx, g0.origin[0] + 0.4 * g0.Lx, y_dep=y_dep)))
+    flags = g.immersed_flags()
+    H = g.H
+    inner = (slice(H[0], -H[0]), slice(H[1], -H[1]) if H[1] else slice(None), slice(H[2], -H[2]))
+    assert 0 < flags[inner].sum() < 0.35 * flags[inner].size
+    times = [0.0, 0.5, 1.0]
+    fields = make_series(g, times, var_names=("T", "b"), velocity_names=vel_names, T_period=2.0)
+    fp = lfb200.set_offline_BW2_filter_params(N=N, freq_c=2 * np.pi / 2.0)
+    o, m = make_pair(g, ("T", "b"), vel_names, fp, times, fields, kernel="ztma", backward=backward)
+    assert m.kernel_name == "ztma"
+    names = oracle_names(("T", "b"), vel_names, fp)
+    o.init_from_data(); m.init_from_data()
+    for dt in (0.1, 0.1, 0.05, 0.25, 0.2):
+        o.step(dt); m.step(dt)
+    compare_state(o, m, names, TOL_STEP)
+    for name in names[:2]:
+        assert np.all(m.tracer(name)[inner][flags[inner] != 0] == 0.0)
+    m.close(); o.close()
+
+
 def test_offline_pipeline_with_options_vs_oracle():
     """run_offline_Lagrangian_filter end to end (forward + backward pass, combination) with the options beyond the
     defaults: an immersed lee-wave-shaped grid with partial cells (examples/offline_filter_lee_wave.jl:49-53), and AB2 with
