@@ -168,22 +168,30 @@ class ImmersedBoundaryGrid:
             raise ValueError("an immersed bottom needs a non-Flat z axis")
         self.underlying_grid = underlying_grid
         self.immersed_boundary = immersed_boundary
+        self._parent = None
 
     def __getattr__(self, name):
-        if name in ("underlying_grid", "immersed_boundary"):
+        if name in ("underlying_grid", "immersed_boundary", "_parent"):
             raise AttributeError(name)
         return getattr(self.underlying_grid, name)
 
     def slab(self, rank: int, nranks: int) -> "ImmersedBoundaryGrid":
+        """The y-slab of rank `rank`.  Its flags / cell heights are cut out of the GLOBAL arrays, so that the halo rows
+        of a slab hold the neighbour slabs' values (and the periodic images of the global grid at its outer edges)."""
         if nranks == 1:
             return self
-        ib = self.immersed_boundary
-        if isinstance(ib.bottom, np.ndarray):
-            ny = self.underlying_grid.Ny // nranks
-            ib = type(ib).__new__(type(ib))
-            ib.__dict__.update(self.immersed_boundary.__dict__)
-            ib.bottom = np.asarray(self.immersed_boundary.bottom)[:, rank * ny:(rank + 1) * ny]
-        return ImmersedBoundaryGrid(self.underlying_grid.slab(rank, nranks), ib)
+        g = ImmersedBoundaryGrid(self.underlying_grid.slab(rank, nranks), self.immersed_boundary)
+        g._parent = (self, rank, nranks)
+        return g
+
+    def _cut(self, name: str):
+        """`name`() of the global grid, cut down to this slab (None stays None)."""
+        parent, rank, nranks = self._parent
+        a = getattr(parent, name)()
+        if a is None:
+            return None
+        ny, H = parent.underlying_grid.Ny // nranks, parent.underlying_grid.Hy
+        return np.asfortranarray(a[:, rank * ny:(rank + 1) * ny + 2 * H, :])
 
     # ------------------------------------------------------------------ host evaluation
     def bottom_height(self) -> np.ndarray:
@@ -233,6 +241,8 @@ class ImmersedBoundaryGrid:
     def immersed_flags(self) -> np.ndarray:
         """Parent array (centre, halos included) of 0 / 1 flags: 1 inside the immersed boundary.  Periodic halos
         carry the periodic images, the halos of Bounded axes stay 0 (no stencil test reads them)."""
+        if getattr(self, "_parent", None):
+            return self._cut("immersed_flags")
         g, ib = self.underlying_grid, self.immersed_boundary
         zb, zf = self._adjusted_bottom()
         if isinstance(ib, PartialCellBottom):
@@ -247,6 +257,8 @@ class ImmersedBoundaryGrid:
     def cell_heights(self):
         """Parent array of the cell heights dz(i,j,k) for PartialCellBottom (None for whole cells): the lowest wet
         cell of a column reaches from the (capped) bottom to its top face."""
+        if getattr(self, "_parent", None):
+            return self._cut("cell_heights")
         g, ib = self.underlying_grid, self.immersed_boundary
         if not isinstance(ib, PartialCellBottom):
             return None
@@ -263,6 +275,8 @@ class ImmersedBoundaryGrid:
         (post:285-298): z_centre < bottom_height (the stored, i.e. capped / grid-fitted, bottom).  For whole cells
         this is the set of immersed cells; with partial cells it also holds the wet bottom cells whose centre lies
         below the bottom."""
+        if getattr(self, "_parent", None):
+            return self._cut("below_bottom_mask")
         g, ib = self.underlying_grid, self.immersed_boundary
         if not isinstance(ib, PartialCellBottom):
             return self.immersed_flags() != 0

@@ -178,3 +178,30 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
         h = ctypes.c_void_p()
         rc = L.lfb_create(ctypes.byref(d), ctypes.byref(h))
         assert rc == -2 and b"no CPU fallback" in L.lfb_last_error()
+
+
+def test_immersed_grid_host_evaluation():
+    """ImmersedBoundaryGrid on the host: GridFittedBottom marks the cells whose centre lies at or below the bottom,
+    PartialCellBottom the cells whose top face does (with the lowest wet cell capped at the minimum fraction of its
+    height); periodic halos carry the images; a y-slab's arrays are cut out of the global ones."""
+    g0 = lfb200.RectilinearGrid(size=(16, 12, 8), extent=(16.0, 12.0, 8.0), topology=("Periodic", "Periodic", "Bounded"))
+    bottom = lambda x, y: -8 + 3.3 * np.exp(-((x - 6) ** 2 + (y - 1) ** 2) / 8)
+    gf = lfb200.ImmersedBoundaryGrid(g0, lfb200.GridFittedBottom(bottom))
+    gp = lfb200.ImmersedBoundaryGrid(g0, lfb200.PartialCellBottom(bottom, minimum_fractional_cell_height=0.2))
+    assert gf.N == g0.N and gf.spacing == g0.spacing and gf.cell_heights() is None
+    F, P, Hh = gf.immersed_flags(), gp.immersed_flags(), gp.cell_heights()
+    assert F.shape == g0.center_shape() and set(np.unique(F)) == {0.0, 1.0}
+    zc = g0.nodes(2, with_halos=False)
+    x, y = g0.nodes(0, with_halos=False), g0.nodes(1, with_halos=False)
+    zb = bottom(x[:, None], y[None, :])
+    assert np.array_equal(F[3:-3, 3:-3, 3:-3], (zc[None, None, :] <= zb[:, :, None]).astype(float))
+    assert P[3:-3, 3:-3, 3:-3].sum() <= F[3:-3, 3:-3, 3:-3].sum() + 16 * 12       # top-face test: at most one cell per column fewer / more
+    assert np.array_equal(F[:3], F[16:19]) and np.array_equal(F[:, -3:], F[:, 3:6])     # periodic images
+    inner_h = Hh[3:-3, 3:-3, 3:-3]
+    assert inner_h.min() >= 0.2 * 1.0 - 1e-12 and inner_h.max() == 1.0
+    for r in range(3):
+        s = gp.slab(r, 3)
+        assert s.center_shape() == (22, 10, 14)
+        assert np.array_equal(s.immersed_flags(), P[:, 4 * r:4 * r + 10, :])
+        assert np.array_equal(s.cell_heights(), Hh[:, 4 * r:4 * r + 10, :])
+        assert np.array_equal(s.below_bottom_mask(), gp.below_bottom_mask()[:, 4 * r:4 * r + 10, :])
