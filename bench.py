@@ -214,7 +214,20 @@ def run_remap(args, local):
     best = min(times[1:]) if len(times) > 1 else times[0]
     nodes = g.Nx * g.Ny * g.Nz
     inner = outs[0][g.Hx:-g.Hx, g.Hy:-g.Hy, g.Hz:-g.Hz]
-    line = {"metric": "remap nodes/s", "value": nodes / best, "unit": "node/s (one output time, search shared by the fields)",
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_per_node = (3 + 2 * len(fields)) * 8            # read 3 displacement maps once, per field read f and write f_at_mean
+    achieved = nodes * bytes_per_node / best / 1e9
+    line = {"metric": "remap nodes/s", "value": nodes / best,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "algorithmic_bytes_per_node": bytes_per_node,
+                         "note": "the search is FP64-latency bound (17 % FP64 pipe, 31 % issue slots at 8 warps per SM, "
+                                 "profiles/r02_ncu_remap3d_512x512x128.txt), nowhere near the HBM roof: ~2000 candidate "
+                                 "evaluations per node against 104 B of algorithmic traffic"}, "unit": "node/s (one output time, search shared by the fields)",
             "n_gpus": 1, "seconds_per_output_time": best, "fields": len(fields), "grid": list(args.size),
             "nan_fraction": float(np.isnan(inner).mean()), "higher_is_better": True, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"remap to the mean position of {len(fields)} fields on the synthetic 3D "

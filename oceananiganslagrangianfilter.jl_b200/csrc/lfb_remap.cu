@@ -399,12 +399,17 @@ __device__ __forceinline__ void remap3_locate_node(const Remap3Params &P, const 
             if (orient3(a, b, c, qx, qy, qz) < 0) { t = b; b = c; c = t; }
         }
         if (found && pass < 2) {
-            // is the circumsphere empty of the points of the outer shell?
-            const double lim = srad2 * (1.0 - 1e-10);
-            for (int d2 = -r2; d2 <= r2 && found; ++d2)
-                for (int d1 = -r1; d1 <= r1 && found; ++d1) {
+            // Is the circumsphere empty of the points of the outer shell?  Only lattice points whose cell can reach the
+            // sphere need a look: a point at lattice offset d sits within maxdisp cells of q + d h along every axis.
+            const double lim = srad2 * (1.0 - 1e-10), rad = sqrt(srad2);
+            const double h0 = P.ax[0].delta / P.ax[0].rg, h1 = P.ax[1].delta / P.ax[1].rg, h2 = P.ax[2].delta / P.ax[2].rg;
+            const int lo0 = max(-r0, (int)floor((scx - rad - qx) / h0 - P.ax[0].maxdisp)), hi0 = min(r0, (int)ceil((scx + rad - qx) / h0 + P.ax[0].maxdisp));
+            const int lo1 = max(-r1, (int)floor((scy - rad - qy) / h1 - P.ax[1].maxdisp)), hi1 = min(r1, (int)ceil((scy + rad - qy) / h1 + P.ax[1].maxdisp));
+            const int lo2 = max(-r2, (int)floor((scz - rad - qz) / h2 - P.ax[2].maxdisp)), hi2 = min(r2, (int)ceil((scz + rad - qz) / h2 + P.ax[2].maxdisp));
+            for (int d2 = lo2; d2 <= hi2 && found; ++d2)
+                for (int d1 = lo1; d1 <= hi1 && found; ++d1) {
                     const bool inner_row = d2 >= -R2 && d2 <= R2 && d1 >= -R1 && d1 <= R1;
-                    for (int d0 = -r0; d0 <= r0; ++d0) {
+                    for (int d0 = lo0; d0 <= hi0; ++d0) {
                         if (inner_row && d0 >= -R0 && d0 <= R0) { d0 = R0; continue; }      // skip the inner patch
                         if (!src(i0 + d0, i1 + d1, i2 + d2, t)) continue;
                         const double dd = (t.x - scx) * (t.x - scx) + (t.y - scy) * (t.y - scy) + (t.z - scz) * (t.z - scz);
