@@ -229,8 +229,8 @@ int lfb_kept_info(lfb_handle *h, int id, int *is_f32, int *extents3, void **devi
  * no device synchronisation, between time steps); lfb_kept_trim returns the pooled memory to the device */
 int lfb_kept_release(lfb_handle *h, int id);
 int lfb_kept_trim(lfb_handle *h);
-/* put `count` blocks of `bytes` bytes into the pool ahead of time (before a pass), so that no cudaMalloc happens between
- * queued time steps */
+/* make sure the pool holds at least `count` blocks of `bytes` bytes ahead of time (before a pass), so that no cudaMalloc
+ * happens between queued time steps */
 int lfb_kept_reserve(lfb_handle *h, size_t bytes, int count);
 /* COLLECTIVE over the communicator of lfb_comm_init: assemble the GLOBAL parent array of a kept output on rank
  * `root` from every rank's y-slab (interior rows from their owners, outer halo rows from the first / last rank).
@@ -263,6 +263,8 @@ typedef struct lfb_remap_desc {
  * use unified addressing. */
 int lfb_remap_to_mean(const lfb_remap_desc *desc, const double *const *xi, int n_fields, const double *const *fields,
                       double *const *out);
+/* the work arrays of the 3-D remap are kept between calls (one call per output time); this returns them to the device */
+int lfb_remap_release(void);
 
 /* ---- multi-GPU: y-slab decomposition, one process per GPU -------------------------------------
  * With nranks > 1 every call that produces exported arrays or (re)initialises the state exchanges y-halo rows with

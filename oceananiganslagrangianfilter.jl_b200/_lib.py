@@ -34,7 +34,7 @@ EXPORTS = [
     "lfb_iteration", "lfb_get_tracer", "lfb_set_tracer", "lfb_get_tendency", "lfb_step", "lfb_run_until",
     "lfb_output", "lfb_output_f32", "lfb_output_async", "lfb_wait_transfers", "lfb_host_alloc", "lfb_host_free",
     "lfb_combine", "lfb_output_keep", "lfb_kept_combine", "lfb_kept_fetch", "lfb_kept_fetch_async", "lfb_kept_info", "lfb_kept_release", "lfb_kept_trim", "lfb_kept_reserve",
-    "lfb_kept_gather", "lfb_mem_info", "lfb_remap_to_mean", "lfb_comm_unique_id", "lfb_comm_init", "lfb_kernel_launches",
+    "lfb_kept_gather", "lfb_mem_info", "lfb_remap_to_mean", "lfb_remap_release", "lfb_comm_unique_id", "lfb_comm_init", "lfb_kernel_launches",
     "lfb_stage_time_ms", "lfb_timer_start", "lfb_timer_stop", "lfb_kernel_name", "lfb_device_ptr", "lfb_layout",
 ]
 
@@ -100,6 +100,7 @@ def load():
         "lfb_kept_release": (i32, [vp, i32]), "lfb_kept_trim": (i32, [vp]), "lfb_kept_reserve": (i32, [vp, C.c_size_t, i32]), "lfb_kept_gather": (i32, [vp, i32, i32, C.POINTER(i32)]),
         "lfb_mem_info": (i32, [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
         "lfb_remap_to_mean": (i32, [C.POINTER(RemapDesc), C.POINTER(vp), i32, C.POINTER(vp), C.POINTER(vp)]),
+        "lfb_remap_release": (i32, []),
         "lfb_comm_unique_id": (i32, [vp]), "lfb_comm_init": (i32, [vp, vp, i32, i32]),
         "lfb_kernel_launches": (i64, [vp]), "lfb_stage_time_ms": (i32, [vp, i32, C.POINTER(f64), C.POINTER(i64)]),
         "lfb_timer_start": (i32, [vp]), "lfb_timer_stop": (i32, [vp, C.POINTER(f64)]),

@@ -1371,7 +1371,9 @@ extern "C" int lfb_kept_reserve(lfb_handle *h, size_t bytes, int count)
 {
     if (!h || bytes == 0 || count < 0) return fail(LFB_ERR_ARG, "bad argument");
     CU(cudaSetDevice(h->device));
-    for (int q = 0; q < count; ++q) {
+    int have = 0;                                   // "at least `count`": blocks of this size that are pooled already count
+    for (auto &k : h->kept_pool) if (k.bytes == bytes) ++have;
+    for (int q = have; q < count; ++q) {
         lfb_handle::Pooled pl;
         pl.p = nullptr; pl.bytes = bytes; pl.fetched = nullptr;
         cudaError_t err = cudaMalloc(&pl.p, bytes);

@@ -21,6 +21,7 @@
 #include <string.h>
 #include <time.h>
 
+#include <mutex>
 #include <vector>
 
 #include "lfb200.h"
@@ -592,6 +593,54 @@ static int cloud_extent(const lfb_remap_desc *D, const double *d_xi_a, double *d
     return 0;
 }
 
+// Work arrays of the 3-D remap are cached between calls (one call per output time, always the same sizes): allocating and
+// freeing 14 GB per call at 1024 x 1024 x 128 costs more than the edge planes and the field loop together.
+// lfb_remap_release() returns them to the device.
+struct WsBlock { void *p; size_t bytes; int device; };
+static std::vector<WsBlock> g_ws_free, g_ws_used;
+static std::mutex g_ws_lock;
+
+static cudaError_t ws_alloc(void **p, size_t bytes)
+{
+    std::lock_guard<std::mutex> guard(g_ws_lock);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (size_t q = 0; q < g_ws_free.size(); ++q)
+        if (g_ws_free[q].bytes == bytes && g_ws_free[q].device == dev) {
+            *p = g_ws_free[q].p;
+            g_ws_used.push_back(g_ws_free[q]);
+            g_ws_free.erase(g_ws_free.begin() + q);
+            return cudaSuccess;
+        }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess && !g_ws_free.empty()) {           // give the cached blocks back and retry
+        cudaGetLastError();
+        for (auto &b : g_ws_free) cudaFree(b.p);
+        g_ws_free.clear();
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) g_ws_used.push_back({*p, bytes, dev});
+    return e;
+}
+
+static void ws_free(void *p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> guard(g_ws_lock);
+    for (size_t q = 0; q < g_ws_used.size(); ++q)
+        if (g_ws_used[q].p == p) { g_ws_free.push_back(g_ws_used[q]); g_ws_used.erase(g_ws_used.begin() + q); return; }
+    cudaFree(p);
+}
+
+extern "C" int lfb_remap_release(void)
+{
+    std::lock_guard<std::mutex> guard(g_ws_lock);
+    cudaDeviceSynchronize();
+    for (auto &b : g_ws_free) cudaFree(b.p);
+    g_ws_free.clear();
+    return LFB_OK;
+}
+
 // grids with three non-Flat axes: 3-D walk for the bulk, then the reference's edge-plane interpolation on every
 // Bounded axis (a 2-D LinearNDInterpolator over the points of the first / last index plane, normalised by the extents
 // of that cut, post:678-745), halos zero
@@ -616,16 +665,16 @@ static int remap3(const lfb_remap_desc *D, const double *const *xi, int n_fields
     int *d_flag = nullptr;
     const int64_t nodes = (int64_t)D->size[0] * D->size[1] * D->size[2];
     auto cleanup = [&]() {
-        for (int a = 0; a < 3; ++a) cudaFree(d_xi[a]);
-        cudaFree(d_f); cudaFree(d_out); cudaFree(d_w); cudaFree(d_tet); cudaFree(d_flag); cudaFree(d_pw); cudaFree(d_ptri); cudaFree(d_part);
+        for (int a = 0; a < 3; ++a) ws_free(d_xi[a]);
+        ws_free(d_f); ws_free(d_out); ws_free(d_w); ws_free(d_tet); ws_free(d_flag); ws_free(d_pw); ws_free(d_ptri); ws_free(d_part);
     };
 #define RCU3(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); RFAIL(LFB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
     for (int a = 0; a < 3; ++a)
         if (D->has_map[a] && xi[a]) {
-            RCU3(cudaMalloc(&d_xi[a], len * sizeof(double)));
+            RCU3(ws_alloc((void **)&d_xi[a], len * sizeof(double)));
             RCU3(cudaMemcpy(d_xi[a], xi[a], len * sizeof(double), cudaMemcpyDefault));
         }
-    RCU3(cudaMalloc(&d_part, 3 * EXT_BLOCKS * sizeof(double)));
+    RCU3(ws_alloc((void **)&d_part, 3 * EXT_BLOCKS * sizeof(double)));
     for (int a = 0; a < 3; ++a) {
         RemapAxis &A = P.ax[a];
         A.n = D->size[a]; A.H = D->halo[a]; A.periodic = D->topology[a] == LFB_PERIODIC; A.has_map = D->has_map[a] && xi[a];
@@ -634,11 +683,11 @@ static int remap3(const lfb_remap_desc *D, const double *const *xi, int n_fields
         if (ce) { cleanup(); RFAIL(ce == -1 ? LFB_ERR_ARG : LFB_ERR_CUDA, ce == -1 ? "non-finite displacement" : "extent kernel failed"); }
     }
     const double t_ext = now_s();
-    RCU3(cudaMalloc(&d_f, len * sizeof(double)));
-    RCU3(cudaMalloc(&d_out, len * sizeof(double)));
-    RCU3(cudaMalloc(&d_w, 4 * nodes * sizeof(double)));
-    RCU3(cudaMalloc(&d_tet, 4 * nodes * sizeof(int64_t)));
-    RCU3(cudaMalloc(&d_flag, sizeof(int)));
+    RCU3(ws_alloc((void **)&d_f, len * sizeof(double)));
+    RCU3(ws_alloc((void **)&d_out, len * sizeof(double)));
+    RCU3(ws_alloc((void **)&d_w, 4 * nodes * sizeof(double)));
+    RCU3(ws_alloc((void **)&d_tet, 4 * nodes * sizeof(int64_t)));
+    RCU3(ws_alloc((void **)&d_flag, sizeof(int)));
     // patch radius: displacement + the reach of a lattice circumsphere in normalised cells + margin; doubled while the check fails
     double hn[3], diag = 0;
     for (int a = 0; a < 3; ++a) { hn[a] = P.ax[a].delta / P.ax[a].rg; diag += hn[a] * hn[a]; }
@@ -707,8 +756,8 @@ static int remap3(const lfb_remap_desc *D, const double *const *xi, int n_fields
         }
     }
     if (!planes.empty()) {
-        RCU3(cudaMalloc(&d_pw, 3 * plane_nodes * sizeof(double)));
-        RCU3(cudaMalloc(&d_ptri, 3 * plane_nodes * sizeof(int64_t)));
+        RCU3(ws_alloc((void **)&d_pw, 3 * plane_nodes * sizeof(double)));
+        RCU3(ws_alloc((void **)&d_ptri, 3 * plane_nodes * sizeof(int64_t)));
     }
     int axis_of_plane = 0;
     (void)axis_of_plane;

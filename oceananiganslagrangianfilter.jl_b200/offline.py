@@ -369,7 +369,8 @@ def run_offline_Lagrangian_filter(config: OfflineFilterConfig, output_dtype=np.f
         if store is not None and hasattr(store, "close"):
             store.close()
         if own_model:
-            model.close()
+            model.close()                # frees the pooled blocks of the kept outputs too
+        # a model passed in keeps its pool of output blocks for the next run (model.kept_trim() returns the memory)
     if world > 1 and gather_to_root:
         out = D.merge_outputs_on_root(out, rank, world, config.grid)
         if rank != 0:

@@ -234,7 +234,7 @@ class ForwardBackwardCombiner:
         res = {}
         if self.regrid:
             from .remap import remap_kept_to_mean
-            res.update(remap_kept_to_mean(self.config, model, held))
+            res.update(remap_kept_to_mean(self.config, model, held, alloc=self.alloc))
         for name in self.names:
             res[name] = model.kept_fetch(held[name], alloc=self.alloc, wait=False)
             self.deferred.append(held[name])
@@ -248,12 +248,13 @@ class ForwardBackwardCombiner:
             for kid in self.deferred:
                 self.model.kept_release(kid)
             self.deferred = []
-            self.model.kept_trim()
         for k in self.mine:
             for name, arr in self.results[k].items():
                 self.out.fields.setdefault(name, []).append(arr)
         log.info("Combined forward and backward contributions")
         if self.regrid and self.on_device:
+            from .remap import remap_release
+            remap_release()
             log.info("Wrote regridded data to new variables with _at_mean suffix")
         elif self.regrid:
             regrid_to_mean_position(self.config, self.out)
@@ -306,6 +307,8 @@ def regrid_to_mean_position(config, out: FilterOutput, extra_vars_to_regrid: Seq
                                    immersed=_immersed_mask(g))
         for n in names:
             out.fields.setdefault(n + "_at_mean", []).append(res[n + "_at_mean"])
+    from .remap import remap_release
+    remap_release()
     log.info("Wrote regridded data to new variables with _at_mean suffix")
 
 

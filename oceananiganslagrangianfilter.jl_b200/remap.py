@@ -23,7 +23,7 @@ def centre_nodes(N, H, x0, delta):
 
 def remap_to_mean_device(fields: Dict[str, object], xi: Dict[str, object], N, H, topology, origin, delta,
                          npad: int = 5, device: int = 0, radius: int = 0, immersed=None,
-                         pointers: bool = False) -> Dict[str, np.ndarray]:
+                         pointers: bool = False, alloc=None) -> Dict[str, np.ndarray]:
     """fields: {name: parent array with halos}; xi: {"u"/"v"/"w": parent xi array} for the velocities that have maps.
     origin[ax] = first face coordinate, delta[ax] = spacing.  Returns {name + "_at_mean": parent array} with halos
     zeroed (post:748), computed by liblfb200 (two or three non-Flat axes).
@@ -31,7 +31,8 @@ def remap_to_mean_device(fields: Dict[str, object], xi: Dict[str, object], N, H,
     immersed: boolean parent-shaped mask of the cells `_mask_immersed` blanks (post:285-298, 418-421, 508-511): their
     displacement is set to 0 and their value to NaN before the interpolation.
     pointers=True: the values of `fields` / `xi` are raw DEVICE pointers (FP64 parent arrays on `device`, e.g. from
-    lfb_kept_info) instead of host arrays."""
+    lfb_kept_info) instead of host arrays.  alloc(shape, dtype): allocator of the result arrays (default numpy.empty,
+    Fortran order; page-locked memory makes the copies run at the full PCIe rate)."""
     import ctypes as C
     L = _lib.load()
     if immersed is not None:
@@ -60,13 +61,18 @@ def remap_to_mean_device(fields: Dict[str, object], xi: Dict[str, object], N, H,
     xi_ptrs = (C.c_void_p * 3)(*[ptr(xi["uvw"[ax]]) if "uvw"[ax] in xi else None for ax in range(3)])
     names = list(fields.keys())
     f_ptrs = (C.c_void_p * len(names))(*[ptr(fields[n]) for n in names])
-    outs = [np.empty(shape, dtype=np.float64, order="F") for _ in names]
+    outs = [np.empty(shape, dtype=np.float64, order="F") if alloc is None else alloc(shape, np.float64) for _ in names]
     o_ptrs = (C.c_void_p * len(names))(*[o.ctypes.data for o in outs])
     _lib.check(L.lfb_remap_to_mean(C.byref(d), xi_ptrs, len(names), f_ptrs, o_ptrs))
     return {n + "_at_mean": o for n, o in zip(names, outs)}
 
 
-def remap_kept_to_mean(config, model, held: Dict[str, int]) -> Dict[str, np.ndarray]:
+def remap_release():
+    """Return the cached work arrays of the 3-D remap to the device."""
+    _lib.check(_lib.load().lfb_remap_release())
+
+
+def remap_kept_to_mean(config, model, held: Dict[str, int], alloc=None) -> Dict[str, np.ndarray]:
     """regrid_to_mean_position! for ONE output time whose combined fields are kept on the device (ids of GLOBAL
     FP64 parent arrays on this rank): the device remap reads them in place."""
     from .post import _immersed_mask, _regrid_names
@@ -81,8 +87,8 @@ def remap_kept_to_mean(config, model, held: Dict[str, int]) -> Dict[str, np.ndar
         return remap_to_mean_device({n: model.kept_fetch(held[n]) for n in names},
                                     {vel: model.kept_fetch(held["xi_" + vel + label]) for vel in vels},
                                     g.N, g.H, g.topology, g.origin, g.spacing, npad=config.npad,
-                                    device=getattr(config, "device", 0), immersed=mask)
+                                    device=getattr(config, "device", 0), immersed=mask, alloc=alloc)
     ptr = lambda kid: model.kept_info(kid, pointer=True)[2]
     return remap_to_mean_device({n: ptr(held[n]) for n in names}, {vel: ptr(held["xi_" + vel + label]) for vel in vels},
                                 g.N, g.H, g.topology, g.origin, g.spacing, npad=config.npad,
-                                device=getattr(config, "device", 0), pointers=True)
+                                device=getattr(config, "device", 0), pointers=True, alloc=alloc)
