@@ -287,8 +287,14 @@ static int create_impl(lfb_handle *h)
             }
     }
     CU(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&h->d2h, cudaStreamNonBlocking));
+    {
+        // the small layout kernels behind the uploads (copy stream) and the downloads go first: a stage kernel that fills
+        // every SM would otherwise keep the import of the next snapshot waiting until its own blocks are all issued
+        int lo_prio = 0, hi_prio = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        CU(cudaStreamCreateWithPriority(&h->copy, cudaStreamNonBlocking, hi_prio));
+        CU(cudaStreamCreateWithPriority(&h->d2h, cudaStreamNonBlocking, hi_prio));
+    }
     CU(cudaEventCreateWithFlags(&h->ev_tmp, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming));
     CU(cudaEventCreate(&h->ev_t0));
