@@ -181,6 +181,7 @@ class ForwardBackwardCombiner:
         self.results: Dict[int, Dict[str, np.ndarray]] = {}
         self.done = set()
         self.deferred: List[int] = []                     # combined arrays whose asynchronous fetch may be pending
+        self.pending: Dict[int, Dict[str, int]] = {}      # multi-GPU: gathered output times waiting for their remap
 
     def feed(self, tb: float, outputs: Dict[str, object]):
         nb = int(np.argmin(np.abs(self.btimes - tb)))
@@ -231,18 +232,29 @@ class ForwardBackwardCombiner:
                 model.kept_release(self.bwd[nb][name])
         if self.by_time and self.owner[k] != self.rank:
             return
+        if self.world > 1 and self.regrid:
+            # the owner remaps after the pass: a remap here would keep every other rank waiting at its next halo exchange,
+            # and the owners of different output times would remap one after the other instead of side by side
+            self.pending[k] = held
+            return
+        self.results[k] = self._remap_and_fetch(held)
+
+    def _remap_and_fetch(self, held: Dict[str, int]) -> Dict[str, np.ndarray]:
         res = {}
         if self.regrid:
             from .remap import remap_kept_to_mean
-            res.update(remap_kept_to_mean(self.config, model, held, alloc=self.alloc))
+            res.update(remap_kept_to_mean(self.config, self.model, held, alloc=self.alloc))
         for name in self.names:
-            res[name] = model.kept_fetch(held[name], alloc=self.alloc, wait=False)
+            res[name] = self.model.kept_fetch(held[name], alloc=self.alloc, wait=False)
             self.deferred.append(held[name])
-        self.results[k] = res
+        return res
 
     def finish(self) -> FilterOutput:
         if len(self.done) != len(self.ftimes):
             raise RuntimeError("backward outputs missing: not every forward time could be combined")
+        for k in sorted(self.pending):                    # multi-GPU: every owner remaps its output times now, side by side
+            self.results[k] = self._remap_and_fetch(self.pending[k])
+        self.pending = {}
         if self.on_device:
             self.model.wait_transfers()
             for kid in self.deferred:
