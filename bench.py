@@ -393,6 +393,7 @@ def main():
                 return a
 
         n_at_mean = (len(VAR_NAMES) + len(VEL_NAMES)) if args.pipeline_remap else 0     # remapped fields per output time
+        pinned_mark = m.n_pinned
         pool = PinnedPool((n_out + n_at_mean) * n_times, m.center_shape, np.float64)
         # device blocks of the kept pass outputs: taken before the timed region, like the model's own fields
         m.kept_reserve((n_times + 1) * n_out, np.float32)
@@ -419,6 +420,15 @@ def main():
         del out
         if args.pipeline_remap:
             pool.next, pool.bytes = 0, 0
+            if world > 1:
+                # the owners of output times receive GLOBAL arrays: page-locked destinations for those (the slab arrays of
+                # the run above are released first)
+                from lfb200.distributed import owner_of_time
+                m.free_pinned(since=pinned_mark)
+                n_owned = len([k for k in range(n_times) if owner_of_time(k, world) == rank])
+                pool = PinnedPool((n_out + n_at_mean) * n_owned, gglobal.center_shape(), np.float64) if n_owned else pool
+                if not n_owned:
+                    pool.arrays = [np.empty((1, 1, 1))]
             barrier()
             t0 = time.perf_counter()
             out = run_offline_Lagrangian_filter(cfg, save=False, regrid=True, model=m, rank=rank, world=world,

@@ -1402,6 +1402,30 @@ extern "C" int lfb_kept_trim(lfb_handle *h)
 
 // Gather the y-slabs of a kept output on rank `root` (collective over the slab communicator): the interior rows of
 // every rank, the low halo rows of rank 0 and the high halo rows of the last rank -> the GLOBAL parent array.
+// temporary device blocks of the gather, taken from / returned to the pool of the kept outputs: everything the gather does is
+// ordered on the compute stream, so a block may be handed out again while earlier work on it is still queued there
+static void *pool_take(lfb_handle *h, size_t bytes)
+{
+    for (size_t q = 0; q < h->kept_pool.size(); ++q)
+        if (h->kept_pool[q].bytes == bytes) {
+            if (h->kept_pool[q].fetched) { cudaStreamWaitEvent(h->compute, h->kept_pool[q].fetched, 0); cudaEventDestroy(h->kept_pool[q].fetched); }
+            void *p = h->kept_pool[q].p;
+            h->kept_pool.erase(h->kept_pool.begin() + q);
+            return p;
+        }
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+static void pool_give(lfb_handle *h, void *p, size_t bytes)
+{
+    if (!p) return;
+    lfb_handle::Pooled pl;
+    pl.p = p; pl.bytes = bytes; pl.fetched = nullptr;
+    h->kept_pool.push_back(pl);
+}
+
 extern "C" int lfb_kept_gather(lfb_handle *h, int id, int root, int *gid)
 {
     if (!h || !gid) return fail(LFB_ERR_ARG, "null argument");
@@ -1419,30 +1443,36 @@ extern "C" int lfb_kept_gather(lfb_handle *h, int id, int root, int *gid)
     auto rows_of = [&](int r, int *lo, int *hi) { *lo = r == 0 ? 0 : H; *hi = r == R - 1 ? ny + 2 * H : ny + H; };
     int lo, hi;
     rows_of(h->rank, &lo, &hi);
-    // pack my rows: per z plane a contiguous run of (hi - lo) * ex elements
-    void *pack = nullptr;
+    // pack my rows: per z plane a contiguous run of (hi - lo) * ex elements.  No host synchronisation anywhere: the packs,
+    // the NCCL transfers and the unpacks are ordered on the compute stream.
     const size_t my_row_bytes = (size_t)(hi - lo) * ex * item;
-    CU(cudaMalloc(&pack, my_row_bytes * ez));
+    void *pack = pool_take(h, my_row_bytes * ez);
+    if (!pack) return fail(LFB_ERR_CUDA, "device memory exhausted in the gather of slab outputs");
     CU(cudaMemcpy2DAsync(pack, my_row_bytes, (const char *)K.p + (size_t)lo * ex * item, (size_t)ey * ex * item, my_row_bytes, ez,
                          cudaMemcpyDeviceToDevice, h->compute));
     int rc = LFB_OK;
     if (h->rank == root) {
         int ge[3] = {ex, EY, ez};
         rc = kept_new(h, K.is_f32, ge, gid);
-        if (rc) { cudaFree(pack); return rc; }
+        if (rc) { pool_give(h, pack, my_row_bytes * ez); return rc; }
         char *G = (char *)h->kept[*gid].p;
         std::vector<void *> tmp(R, nullptr);
-        ncclResult_t nr = ncclGroupStart();
-        for (int r = 0; r < R && nr == ncclSuccess; ++r) {
+        std::vector<size_t> tmp_bytes(R, 0);
+        for (int r = 0; r < R && !rc; ++r) {
             if (r == root) continue;
             int rlo, rhi;
             rows_of(r, &rlo, &rhi);
-            const size_t bytes = (size_t)(rhi - rlo) * ex * item * ez;
-            if (cudaMalloc(&tmp[r], bytes) != cudaSuccess) { nr = ncclSystemError; break; }
-            nr = ncclRecv(tmp[r], bytes, ncclChar, r, h->comm, h->compute);
+            tmp_bytes[r] = (size_t)(rhi - rlo) * ex * item * ez;
+            tmp[r] = pool_take(h, tmp_bytes[r]);
+            if (!tmp[r]) rc = fail(LFB_ERR_CUDA, "device memory exhausted in the gather of slab outputs");
         }
-        if (nr == ncclSuccess) nr = ncclGroupEnd(); else ncclGroupEnd();
-        if (nr != ncclSuccess) rc = fail(LFB_ERR_COMM, "gather of slab outputs failed: %s", ncclGetErrorString(nr));
+        if (!rc) {
+            ncclResult_t nr = ncclGroupStart();
+            for (int r = 0; r < R && nr == ncclSuccess; ++r)
+                if (r != root) nr = ncclRecv(tmp[r], tmp_bytes[r], ncclChar, r, h->comm, h->compute);
+            if (nr == ncclSuccess) nr = ncclGroupEnd(); else ncclGroupEnd();
+            if (nr != ncclSuccess) rc = fail(LFB_ERR_COMM, "gather of slab outputs failed: %s", ncclGetErrorString(nr));
+        }
         for (int r = 0; r < R && !rc; ++r) {
             int rlo, rhi;
             rows_of(r, &rlo, &rhi);
@@ -1452,14 +1482,12 @@ extern "C" int lfb_kept_gather(lfb_handle *h, int id, int root, int *gid)
                                                cudaMemcpyDeviceToDevice, h->compute);
             if (ce != cudaSuccess) rc = fail(LFB_ERR_CUDA, "cudaMemcpy2DAsync: %s", cudaGetErrorString(ce));
         }
-        cudaStreamSynchronize(h->compute);
-        for (void *t : tmp) if (t) cudaFree(t);
+        for (int r = 0; r < R; ++r) pool_give(h, tmp[r], tmp_bytes[r]);
     } else {
         ncclResult_t nr = ncclSend(pack, my_row_bytes * ez, ncclChar, root, h->comm, h->compute);
         if (nr != ncclSuccess) rc = fail(LFB_ERR_COMM, "gather of slab outputs failed: %s", ncclGetErrorString(nr));
-        cudaStreamSynchronize(h->compute);
     }
-    cudaFree(pack);
+    pool_give(h, pack, my_row_bytes * ez);
     return rc;
 }
 

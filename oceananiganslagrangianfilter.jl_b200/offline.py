@@ -335,6 +335,11 @@ def run_offline_Lagrangian_filter(config: OfflineFilterConfig, output_dtype=np.f
             n_spec = len(_output_specs(model, config))
             model.kept_reserve((n_times + 1) * n_spec, output_dtype)
             model.kept_reserve(2 * n_spec, np.float64)
+            if world > 1 and config.map_to_mean and regrid:
+                # the global arrays of the output times this rank owns (gathered during the backward pass)
+                g = config.grid
+                n_owned = len([k for k in range(n_times) if D.owner_of_time(k, world) == rank])
+                model.kept_reserve(n_owned * n_spec, np.float64, shape=g.center_shape())
         # forward pass
         feeder.begin(+1)
         feeder.ensure(0.0, 0.0)
