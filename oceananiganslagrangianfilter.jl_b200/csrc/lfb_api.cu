@@ -1548,6 +1548,23 @@ extern "C" int lfb_comm_init(lfb_handle *h, const void *id128, int rank, int nra
     CU(cudaMalloc(&h->send_hi, h->halo_elems * sizeof(double)));
     CU(cudaMalloc(&h->recv_lo, h->halo_elems * sizeof(double)));
     CU(cudaMalloc(&h->recv_hi, h->halo_elems * sizeof(double)));
+    if (nranks > 2) {
+        // NCCL sets up a point-to-point connection the first time two ranks talk: the halo exchange only ever connects
+        // neighbours, the gather of the outputs (lfb_kept_gather) any pair.  One tiny all-to-all here moves those set-ups
+        // (tens of milliseconds each) out of the first pipeline run.
+        double *w = nullptr;
+        CU(cudaMalloc(&w, 2 * (size_t)nranks * sizeof(double)));
+        CU(cudaMemset(w, 0, 2 * (size_t)nranks * sizeof(double)));
+        NC(ncclGroupStart());
+        for (int r = 0; r < nranks; ++r) {
+            if (r == rank) continue;
+            NC(ncclSend(w + r, 1, ncclDouble, r, h->comm, h->compute));
+            NC(ncclRecv(w + nranks + r, 1, ncclDouble, r, h->comm, h->compute));
+        }
+        NC(ncclGroupEnd());
+        CU(cudaStreamSynchronize(h->compute));
+        cudaFree(w);
+    }
     int rc = select_kernel(h);
     if (rc) return rc;
     if (h->imm_set) {
