@@ -59,6 +59,18 @@
 #define ZT_TMA_STORE 0    // 1: the new state and G^n leave through shared memory and cp.async.bulk.tensor stores (UTMASTG);
                           // measured 2.4 % slower than per-thread STG (profiles/microbench/r02_tma_store_experiment.txt)
 #endif
+#ifndef ZT_PFORM
+#define ZT_PFORM 1        // Z-weight products as P + tau^2 R_s (one FP64 instruction less per face)
+#endif
+#ifndef ZT_UPS
+#define ZT_UPS 1          // upwind stencil addresses as a + s * const (sign mask of the face velocity): 6 integer instructions per face instead of 10
+#endif
+#ifndef ZT_ZSPLIT
+#define ZT_ZSPLIT 1       // z face: separate code for warps whose w is positive in every lane (no dummy value, no select)
+#endif
+#ifndef ZT_OPAQUE
+#define ZT_OPAQUE 2       // 1: the partner tracer's cell address lives in a register instead of being re-selected per plane; 2: the thread's base addresses too
+#endif
 #ifndef ZT_PF
 #define ZT_PF 0           // planes an L2 prefetch (cp.async.bulk.prefetch.tensor) runs ahead; 0 = off: measured slower (6: +2 %, 10: +7 %)
 #endif
@@ -79,6 +91,7 @@ struct LfbZtParams {
     alignas(64) CUtensorMap mSU[2];
     alignas(64) CUtensorMap mSG[2];
     double k133, k13, k16, eps43, rd[3];         // 13/3, 1/3, 1/6, 4/3 eps, area / volume per axis
+    double dtg, dtz;                             // dt gamma, dt zeta of the stage (constant-bank operands: no register, no per-plane product)
     double *scratch;                             // one field: store target of the rows beyond j1 in partial tiles
 };
 
@@ -195,9 +208,16 @@ __device__ __forceinline__ double zt_blend(double g0, double g1, double g2, doub
 {
     const double tau = g0 - g2;
     const double G0 = g0 * g0, G1 = g1 * g1, G2 = g2 * g2;
+#if ZT_PFORM
+    // A_s = (G_s + tau^2) prod_{j != s} G_j = P + tau^2 R_s with R_s = prod_{j != s} G_j, P = G0 G1 G2: one FP64 instruction less
+    const double tt = tau * tau;
+    const double R0 = G1 * G2, R1 = G0 * G2, R2 = G0 * G1, P = G0 * R0;
+    const double A0 = fma(tt, R0, P), A1 = fma(tt, R1, P), A2 = fma(tt, R2, P);
+#else
     const double A0 = fma(tau, tau, G0) * (G1 * G2);
     const double A1 = fma(tau, tau, G1) * (G0 * G2);
     const double A2 = fma(tau, tau, G2) * (G0 * G1);
+#endif
     const double den = fma(3.0, A0, fma(6.0, A1, A2));
     const double num = fma(0.5, A0 * y0, K.k13 * (A2 * y2));
     double r;
@@ -239,6 +259,15 @@ __device__ __forceinline__ bool zt_positive(double q) { return __double2hiint(q)
 template <int S>
 __device__ __forceinline__ double zt_face(unsigned a, double q, const ZtK &K)
 {
+#if ZT_UPS
+    // sign-mask addressing, see zt_face_up
+    const int s = __double2hiint(q) >> 31;
+    {
+        const double n = lds(a - S - s * S), e = lds(a + s * S), o = lds(a - 2 * S - s * (3 * S));
+        const double f = lds(a + S + s * (3 * S)), p = lds(a - 3 * S - s * (5 * S));
+        return n + zt_inc(o - p, n - o, e - n, f - e, K);
+    }
+#endif
     const bool left = zt_positive(q);
     const int step = left ? S : -S;
     const unsigned an = left ? a - S : a;
@@ -249,6 +278,27 @@ __device__ __forceinline__ double zt_face(unsigned a, double q, const ZtK &K)
 
 // The upwind decision of a face, shared by every tracer advected by the same velocity: byte offset of the upwind cell n
 // relative to the cell on the high side of the face, and the signed stride that walks the stencil in upwind order.
+#if ZT_UPS
+// s = 0 where the face velocity is not negative (high word >= 0: upwind cell on the low side), -1 where it is negative.
+// The five loads of the stencil sit at a + s * (k S) + const: one IMAD per load, no select and no register constants.
+// (Differs from q > 0 only for q = +0, where the flux q * face vanishes for either stencil.)
+struct ZtUp { int s; };
+template <int S>
+__device__ __forceinline__ ZtUp zt_up(double q)
+{
+    ZtUp u;
+    u.s = __double2hiint(q) >> 31;
+    return u;
+}
+template <int S>
+__device__ __forceinline__ double zt_face_up(unsigned a, const ZtUp &u, const ZtK &K)
+{
+    const int s = u.s;
+    const double n = lds(a - S - s * S), e = lds(a + s * S), o = lds(a - 2 * S - s * (3 * S));
+    const double f = lds(a + S + s * (3 * S)), p = lds(a - 3 * S - s * (5 * S));
+    return n + zt_inc(o - p, n - o, e - n, f - e, K);
+}
+#else
 struct ZtUp { int an, step; };
 template <int S>
 __device__ __forceinline__ ZtUp zt_up(double q)
@@ -266,6 +316,7 @@ __device__ __forceinline__ double zt_face_up(unsigned a, const ZtUp &u, const Zt
     const double f = lds(an + 2 * u.step), p = lds(an - 2 * u.step);
     return n + zt_inc(o - p, n - o, e - n, f - e, K);
 }
+#endif
 
 // Scheme of the face with 1-based global index m on an axis of N cells: 5 = WENO5, 3 = buffer
 // WENO3, 2 = Centered2, 1 / 0 = lower / upper wall face (the value next to the wall; the wall velocity is zero).
@@ -605,13 +656,25 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     const int t = NS == 2 ? tid : tid % SM::NT, sub0 = NS == 2 ? 0 : tid / SM::NT;
     const int tx = t % ZT_TX, ty = t / ZT_TX;
     // address registers: own cell in the pitch-32 / pitch-40 tiles; the per-tracer tiles sit at constant offsets
+#if ZT_OPAQUE >= 2
+    // (opaque to the compiler, which otherwise re-derives them from threadIdx in every barrier interval)
+    unsigned a32 = sbase + 8u * t, a40 = sbase + 8u * (ty * ZT_CW + tx + ZT_HX);
+    unsigned a32s0 = a32 + sub0 * VT_B, a40s0 = a40 + 3 * ROW_B + sub0 * CTP_B;
+    asm volatile("" : "+r"(a32), "+r"(a40), "+r"(a32s0), "+r"(a40s0));
+#else
     const unsigned a32 = sbase + 8u * t, a40 = sbase + 8u * (ty * ZT_CW + tx + ZT_HX);
     const unsigned a32s0 = a32 + sub0 * VT_B, a40s0 = a40 + 3 * ROW_B + sub0 * CTP_B;
+#endif
 #define A32S(s) (a32s0 + (unsigned)(s) * VT_B)
 #define A40S(s) (a40s0 + (unsigned)(s) * CTP_B)
     // own entry of the x-flux tile of tracer s ([TY][40] with TMA stores, else the tracer-tile geometry)
 #define AFX(s) (ZT_TMA_STORE ? a40 + (unsigned)(sub0 + (s)) * UT_B + oFX : A40S(s) + oFX)
     const int partner_off = (NSUB == 2 && NS == 1) ? (sub0 ? -(int)CTP_B : (int)CTP_B) : 0;
+    // the partner's cell as an address register of its own (opaque to the compiler, which otherwise re-selects it per plane)
+    [[maybe_unused]] unsigned aPart = a40s0 + partner_off;
+#if ZT_OPAQUE
+    asm volatile("" : "+r"(aPart));
+#endif
     // partial tiles at the end of the y range / of x (folded form: the last row of 32 cells may be partial)
     const bool active = j0 + ty < j1 && (FLATY ? 32 * (j0 + ty) + tx < S.fold_nx : i0 + tx < L.N[0]);
     const int64_t plane_b = L.plane * 8;                             // byte stride between planes
@@ -622,12 +685,13 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
     for (int s = 0; s < NS; ++s) pUn[s] = active ? S.U_new + cell0 + (int64_t)(item.tracer_c + sub0 + s) * L.len : P.scratch + cell0;
     const int64_t g_off = active ? (S.G - S.U_new) : 0;              // pG = pUn + g_off
     // offsets of this column's periodic images in the halo (0 = none); y only when the y halo is not owned by a neighbour rank
-    int64_t xwrap = 0, ywrap = 0;
+    // (32-bit element offsets: a plane has fewer than 2^31 elements, lfb_ztma_supported)
+    int xwrap = 0, ywrap = 0;
     if (active) {
         const int i = i0 + tx, j = j0 + ty;
         if (L.fuse_halo[0]) { if (i < L.H[0]) xwrap = L.N[0]; else if (i >= L.N[0] - L.H[0]) xwrap = -L.N[0]; }
         if (L.fuse_halo[1]) {
-            if (j < L.H[1]) ywrap = (int64_t)L.N[1] * L.pitch; else if (j >= L.N[1] - L.H[1]) ywrap = -(int64_t)L.N[1] * L.pitch;
+            if (j < L.H[1]) ywrap = L.N[1] * (int)L.pitch; else if (j >= L.N[1] - L.H[1]) ywrap = -L.N[1] * (int)L.pitch;
         }
     }
     // scheme of the west / south face of this column, and (block-uniform) whether any face of the tile is next to a wall
@@ -689,7 +753,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             sts(ARX(s) + 24, 1.0 / S.relax_timescale);
         }
     }
-    const double dtg = S.dt * S.gamma, dtz = S.dt * S.zeta;
+    const double dtg = P.dtg, dtz = P.dtz;
     const double rdx = P.rd[0], rdy = P.rd[1], rdz = P.rd[2];
     const double nrdx = -rdx, nrdy = -rdy;
 
@@ -788,9 +852,17 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             if (coded) {
             } else if (z_weno) {
                 // the window is used by a warp-uniform branch per direction (both only in warps that straddle w = 0)
+#if ZT_ZSPLIT
+                if (ml == 0xffffffffu) ct = ck[s] + zt_inc_q(d0[s], d1[s], d2[s], d3[s], Qa[s], Qb[s], Qc[s], K);
+                else {
+                    ct = ck1[s] - zt_inc_q(d4[s], d3[s], d2[s], d1[s], Qd[s], Qc[s], Qb[s], K);
+                    if (ml != 0u) { const double ctL = ck[s] + zt_inc_q(d0[s], d1[s], d2[s], d3[s], Qa[s], Qb[s], Qc[s], K); ct = left ? ctL : ct; }
+                }
+#else
                 ct = ck1[s];
                 if (ml != 0xffffffffu) ct = ck1[s] - zt_inc_q(d4[s], d3[s], d2[s], d1[s], Qd[s], Qc[s], Qb[s], K);
                 if (ml != 0u) { const double ctL = ck[s] + zt_inc_q(d0[s], d1[s], d2[s], d3[s], Qa[s], Qb[s], Qc[s], K); ct = left ? ctL : ct; }
+#endif
             } else {
                 ct = zt_top_face_buffer(k + 2, Nz, cw, d1[s], d2[s], d3[s], ck[s], ck1[s]);
             }
@@ -799,7 +871,7 @@ __global__ void __launch_bounds__(ZtSmem<NSUB, TY>::THREADS, 1) lfb_stage_ztma(c
             // ---- own part of the tendency: c du - dF per axis in units of face velocity, forcing, G^- part of the substep ----
             double forcing = fma(kA[s], sA, fma(kB[s], sB, k_own * ck[s]));
             if (relax) forcing = fma(lds(a32 + oM + is) * lds(ARX(s) + 24), fma(lds(ARX(s)), fma(lds(ARX(s) + 8), sA, lds(ARX(s) + 16) * sB), -ck[s]), forcing);
-            if (NSUB == 2) forcing = fma(k_oth[s], NS == 2 ? ckk[1 - s] : lds(aCk + partner_off), forcing);
+            if (NSUB == 2) forcing = fma(k_oth[s], NS == 2 ? ckk[1 - s] : ZT_OPAQUE ? lds(aPart + oCk) : lds(aCk + partner_off), forcing);
             const double az = fma(ck[s], dwz, Fb[s] - Ft);
             part[s][p] = FLATY ? fma(rdx, fma(ck[s], dux, Fw), fma(rdz, az, forcing))
                                : fma(rdx, fma(ck[s], dux, Fw), fma(rdy, fma(ck[s], dvy, Fs), fma(rdz, az, forcing)));
@@ -987,6 +1059,7 @@ extern "C" int lfb_ztma_supported(const LfbStageParams *P)
     const bool fold = zt_foldable(L);
     if (!fold && (L.topo[0] == LFB_FLAT || L.topo[1] == LFB_FLAT || L.topo[2] == LFB_FLAT)) return 0;
     if (L.topo[2] == LFB_PERIODIC && L.N[2] < 2 * L.H[2]) return 0;
+    if (L.plane >= ((int64_t)1 << 31)) return 0;                   // 32-bit offsets of the periodic images within a plane
     if (!(P->vel_present[0] || P->vel_present[1] || P->vel_present[2])) return 0;     // absent components: a zero field
     if (L.N[0] < 8 || (!fold && L.N[1] < 4) || L.N[2] < 8) return 0;
     if (L.H[0] < 3 || (!fold && L.H[1] < 3) || L.H[2] < 3) return 0;
@@ -1066,6 +1139,7 @@ static cudaError_t zt_launch(const LfbStageParams *S, cudaStream_t stream)
     if (bad) return cudaErrorInvalidValue;
     P.k133 = 13.0 / 3.0; P.k13 = 1.0 / 3.0; P.k16 = 1.0 / 6.0; P.eps43 = LFB_WENO_EPS * (4.0 / 3.0);
     for (int a = 0; a < 3; ++a) P.rd[a] = S->area[a] / S->volume;
+    P.dtg = S->dt * S->gamma; P.dtz = S->dt * S->zeta;
     P.scratch = SS.scratch;
     const int ytiles = (SS.j1 - SS.j0 + TY - 1) / TY + (SS.jb1 > SS.jb0 ? (SS.jb1 - SS.jb0 + TY - 1) / TY : 0);
     dim3 grid(S->n_items * ytiles, (!FLATY && S->xt_n > 0) ? S->xt_n : (L.N[0] + ZT_TX - 1) / ZT_TX, 1);
