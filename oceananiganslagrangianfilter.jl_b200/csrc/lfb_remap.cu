@@ -293,20 +293,24 @@ __device__ __forceinline__ void remap3_locate_node(const Remap3Params &P, const 
     };
     bool found = false;
     double wa = 0, wb = 0, wc = 0, wd = 0, scx = 0, scy = 0, scz = 0, srad2 = 0;
-    // Up to three passes over growing patches.  The early ones search an inner patch two cells, then one cell smaller in
-    // every direction (a fraction of the candidates) and then check that no point of the shell around it lies inside the
-    // circumsphere of the tetrahedron found: the Delaunay tetrahedron that contains the node is the unique one with an
-    // empty circumsphere, so a result that passes is the result of the full search.  Otherwise (rare) the next pass
-    // searches the next larger patch, the last one the full patch.
-    // first patch: the cells a vertex of the enclosing tetrahedron normally comes from (displacement + 1 cell); second:
-    // half way to the full patch
+    // Up to four passes over growing patches.  The early ones search an inner patch (a fraction of the candidates) and
+    // then check that no point of the shell around it lies inside the circumsphere of the tetrahedron found: the Delaunay
+    // tetrahedron that contains the node is the unique one with an empty circumsphere, so a result that passes is the
+    // result of the full search.  Otherwise (rare) the next pass searches the next larger patch, the last one the full patch.
+    // second patch: displacement + 1 cell; third: half way to the full patch
     const int f0 = min(r0, (int)ceil(P.ax[0].maxdisp) + 1), f1 = min(r1, (int)ceil(P.ax[1].maxdisp) + 1), f2 = min(r2, (int)ceil(P.ax[2].maxdisp) + 1);
-    for (int pass = 0; pass < 3 && !found; ++pass) {
-        const int R0 = pass == 0 ? f0 : pass == 1 ? (f0 + r0 + 1) / 2 : r0;
-        const int R1 = pass == 0 ? f1 : pass == 1 ? (f1 + r1 + 1) / 2 : r1;
-        const int R2 = pass == 0 ? f2 : pass == 1 ? (f2 + r2 + 1) / 2 : r2;
-        if (pass == 0 && R0 == r0 && R1 == r1 && R2 == r2) continue;                       // nothing smaller to try
-        if (pass == 1 && ((R0 == f0 && R1 == f1 && R2 == f2) || (R0 == r0 && R1 == r1 && R2 == r2))) continue;
+    // innermost patch: the displacement alone (at least one cell).  With displacements below one cell every vertex of the
+    // enclosing tetrahedron is a direct lattice neighbour of the node (27 candidates instead of 125); the emptiness check
+    // over the shell decides, as for every patch but the full one.
+    const int g0 = min(f0, max(1, (int)ceil(P.ax[0].maxdisp))), g1 = min(f1, max(1, (int)ceil(P.ax[1].maxdisp))), g2 = min(f2, max(1, (int)ceil(P.ax[2].maxdisp)));
+    int pR0 = -1, pR1 = -1, pR2 = -1;
+    for (int pass = 0; pass < 4 && !found; ++pass) {
+        const int R0 = pass == 0 ? g0 : pass == 1 ? f0 : pass == 2 ? (f0 + r0 + 1) / 2 : r0;
+        const int R1 = pass == 0 ? g1 : pass == 1 ? f1 : pass == 2 ? (f1 + r1 + 1) / 2 : r1;
+        const int R2 = pass == 0 ? g2 : pass == 1 ? f2 : pass == 2 ? (f2 + r2 + 1) / 2 : r2;
+        if (R0 == pR0 && R1 == pR1 && R2 == pR2) continue;                                 // the same patch as the pass before
+        pR0 = R0; pR1 = R1; pR2 = R2;
+        const bool full_patch = R0 == r0 && R1 == r1 && R2 == r2;
         // a: nearest data point to the node
         double best = INFINITY;
         bool have = false;
@@ -399,7 +403,7 @@ __device__ __forceinline__ void remap3_locate_node(const Remap3Params &P, const 
             else                           { c = d; }          // face (a, b, d)
             if (orient3(a, b, c, qx, qy, qz) < 0) { t = b; b = c; c = t; }
         }
-        if (found && pass < 2) {
+        if (found && !full_patch) {
             // Is the circumsphere empty of the points of the outer shell?  Only lattice points whose cell can reach the
             // sphere need a look: a point at lattice offset d sits within maxdisp cells of q + d h along every axis.
             const double lim = srad2 * (1.0 - 1e-10), rad = sqrt(srad2);
