@@ -228,7 +228,7 @@ def run_remap(args, local):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "algorithmic_bytes_per_node": bytes_per_node,
                          "note": "the search is FP64-latency bound (17 % FP64 pipe, 31 % issue slots at 8 warps per SM, "
-                                 "profiles/r02_ncu_remap3d_512x512x128.txt), nowhere near the HBM roof: ~2000 candidate "
+                                 "profiles/r02_ncu_remap3d_512x512x128.txt), nowhere near the HBM roof: several hundred candidate "
                                  "evaluations per node against 104 B of algorithmic traffic"}, "unit": "node/s (one output time, search shared by the fields)",
             "n_gpus": 1, "seconds_per_output_time": best, "fields": len(fields), "grid": list(args.size),
             "nan_fraction": float(np.isnan(inner).mean()), "higher_is_better": True, "dtype": "f64", "data": "synthetic",
@@ -467,8 +467,8 @@ def main():
                     "traffic": traffic, "kernel": m.kernel_name, "launch_ms": stage_avg_ms, "peak_source": which,
                     "algorithmic_bytes_per_launch": bytes_per_launch,
                     "note": "FP64 WENO5-Z is bound by the warp schedulers' issue port (an FP64 instruction holds it for two "
-                            "cycles) before it is HBM bound: with no other instruction at all the ceiling would be 58 % of "
-                            "the HBM peak; see DESIGN.md section 5"}
+                            "cycles) before it is HBM bound: with no other instruction at all the ceiling would be 61 % of "
+                            "the HBM peak at 1965 MHz and 55 % at the ~1750 MHz the power cap allows; see DESIGN.md section 5"}
         cpu = None
         if not args.no_cpu and world == 1:
             rate, cms, cores = cpu_port_rate(args.cpu_size, 12, 2)
