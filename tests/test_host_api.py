@@ -180,6 +180,17 @@ def test_c_abi_library_loads_and_exports_every_declared_symbol():
         assert rc == -2 and b"no CPU fallback" in L.lfb_last_error()
 
 
+def test_integration_shim_binds_every_declared_symbol():
+    """INTEGRATION.md shows the reference-side binding (Julia ccall stubs): every function of include/lfb200.h has one."""
+    header = open(os.path.join(ROOT, "include", "lfb200.h")).read()
+    declared = sorted(set(re.findall(r"\b(lfb_[a-z0-9_]+)\s*\(", header)) - {"lfb_handle", "lfb_desc"})
+    shim = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    bound = set(re.findall(r"ccall\(\(:(lfb_[a-z0-9_]+), ", shim))
+    missing = [name for name in declared if name not in bound]
+    assert not missing, f"no ccall stub in INTEGRATION.md for {missing}"
+    assert not sorted(bound - set(declared)), "INTEGRATION.md binds symbols the header does not declare"
+
+
 def test_immersed_grid_host_evaluation():
     """ImmersedBoundaryGrid on the host: GridFittedBottom marks the cells whose centre lies at or below the bottom,
     PartialCellBottom the cells whose top face does (with the lowest wet cell capped at the minimum fraction of its
