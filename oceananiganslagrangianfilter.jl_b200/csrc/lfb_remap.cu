@@ -291,6 +291,11 @@ __device__ __forceinline__ void remap3_locate_node(const Remap3Params &P, const 
     auto none = [&]() {
         for (int v = 0; v < 4; ++v) { tet[4 * node + v] = -1; wgt[4 * node + v] = 0.0; }
     };
+    // Nodes on the first / last plane of a Bounded axis take their value from the edge-plane interpolation (post:641-745),
+    // which overwrites whatever is found here -- and they lie outside the hull of the cloud, where the search would
+    // run through every pass up to the full patch before giving up (1.6 % of the nodes, a quarter of the work).
+    if ((!P.ax[0].periodic && (i0 == 0 || i0 == P.ax[0].n - 1)) || (!P.ax[1].periodic && (i1 == 0 || i1 == P.ax[1].n - 1)) ||
+        (!P.ax[2].periodic && (i2 == 0 || i2 == P.ax[2].n - 1))) { none(); return; }
     bool found = false;
     double wa = 0, wb = 0, wc = 0, wd = 0, scx = 0, scy = 0, scz = 0, srad2 = 0;
     // Up to four passes over growing patches.  The early ones search an inner patch (a fraction of the candidates) and
@@ -311,16 +316,22 @@ __device__ __forceinline__ void remap3_locate_node(const Remap3Params &P, const 
         if (R0 == pR0 && R1 == pR1 && R2 == pR2) continue;                                 // the same patch as the pass before
         pR0 = R0; pR1 = R1; pR2 = R2;
         const bool full_patch = R0 == r0 && R1 == r1 && R2 == r2;
-        // a: nearest data point to the node
+        // a: the node's own data point (it lies within its displacement of the node, and its nearest neighbour -- the
+        // Delaunay edge the walk starts from -- is a direct lattice neighbour, inside the innermost patch; starting from
+        // the data point nearest to the node instead made that patch fail on anisotropic grids, where the nearest point
+        // is often a neighbour in x whose own nearest neighbour lies two cells from the node).  Any vertex will do: the
+        // walk ends in the tetrahedron that contains the node.
         double best = INFINITY;
-        bool have = false;
-        for (int d2 = -R2; d2 <= R2; ++d2)
-            for (int d1 = -R1; d1 <= R1; ++d1)
-                for (int d0 = -R0; d0 <= R0; ++d0) {
-                    if (!src(i0 + d0, i1 + d1, i2 + d2, t)) continue;
-                    const double dd = (t.x - qx) * (t.x - qx) + (t.y - qy) * (t.y - qy) + (t.z - qz) * (t.z - qz);
-                    if (dd < best) { best = dd; a = t; have = true; }
-                }
+        bool have = src(i0, i1, i2, a);
+        if (!have) {
+            for (int d2 = -R2; d2 <= R2; ++d2)
+                for (int d1 = -R1; d1 <= R1; ++d1)
+                    for (int d0 = -R0; d0 <= R0; ++d0) {
+                        if (!src(i0 + d0, i1 + d1, i2 + d2, t)) continue;
+                        const double dd = (t.x - qx) * (t.x - qx) + (t.y - qy) * (t.y - qy) + (t.z - qz) * (t.z - qz);
+                        if (dd < best) { best = dd; a = t; have = true; }
+                    }
+        }
         if (!have) continue;
         // b: nearest neighbour of a (a Delaunay edge)
         best = INFINITY; have = false;
@@ -411,16 +422,28 @@ __device__ __forceinline__ void remap3_locate_node(const Remap3Params &P, const 
             const int lo0 = max(-r0, (int)floor((scx - rad - qx) / h0 - P.ax[0].maxdisp)), hi0 = min(r0, (int)ceil((scx + rad - qx) / h0 + P.ax[0].maxdisp));
             const int lo1 = max(-r1, (int)floor((scy - rad - qy) / h1 - P.ax[1].maxdisp)), hi1 = min(r1, (int)ceil((scy + rad - qy) / h1 + P.ax[1].maxdisp));
             const int lo2 = max(-r2, (int)floor((scz - rad - qz) / h2 - P.ax[2].maxdisp)), hi2 = min(r2, (int)ceil((scz + rad - qz) / h2 + P.ax[2].maxdisp));
-            for (int d2 = lo2; d2 <= hi2 && found; ++d2)
+            // ... and of that box only the part of every x row the sphere can reach: a point at lattice offset d lies within
+            // maxdisp cells of q + d h, so a row whose y / z distance to the centre (less that slack) exceeds the radius is
+            // skipped, and the others are cut to the chord of the sphere at that distance (the box alone holds 180 lattice
+            // points per node at 512 x 512 x 128 and 460 at 1024 x 1024 x 128: more than the scans of the search itself)
+            const double m0 = P.ax[0].maxdisp, m1h = P.ax[1].maxdisp * h1, m2h = P.ax[2].maxdisp * h2, wide2 = srad2 * (1.0 + 1e-9);
+            for (int d2 = lo2; d2 <= hi2 && found; ++d2) {
+                const double ez = fabs(qz + d2 * h2 - scz) - m2h, rz2 = wide2 - (ez > 0 ? ez * ez : 0.0);
+                if (rz2 < 0) continue;
                 for (int d1 = lo1; d1 <= hi1 && found; ++d1) {
+                    const double ey = fabs(qy + d1 * h1 - scy) - m1h, w2 = rz2 - (ey > 0 ? ey * ey : 0.0);
+                    if (w2 < 0) continue;
+                    const double w = sqrt(w2);
+                    const int a0 = max(lo0, (int)floor((scx - w - qx) / h0 - m0)), b0 = min(hi0, (int)ceil((scx + w - qx) / h0 + m0));
                     const bool inner_row = d2 >= -R2 && d2 <= R2 && d1 >= -R1 && d1 <= R1;
-                    for (int d0 = lo0; d0 <= hi0; ++d0) {
+                    for (int d0 = a0; d0 <= b0; ++d0) {
                         if (inner_row && d0 >= -R0 && d0 <= R0) { d0 = R0; continue; }      // skip the inner patch
                         if (!src(i0 + d0, i1 + d1, i2 + d2, t)) continue;
                         const double dd = (t.x - scx) * (t.x - scx) + (t.y - scy) * (t.y - scy) + (t.z - scz) * (t.z - scz);
                         if (dd < lim) { found = false; break; }
                     }
                 }
+            }
         }
     }
     if (!found) { none(); return; }
