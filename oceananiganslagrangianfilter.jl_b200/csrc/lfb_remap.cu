@@ -278,9 +278,13 @@ __device__ __forceinline__ double orient3(const Cand3 &a, const Cand3 &b, const 
 // Delaunay tetrahedron containing node (i0, i1, i2) + barycentric weights.  `src(p0, p1, p2, t)` delivers the data point
 // at lattice offset (p0, p1, p2) (false if the reference's cloud does not hold that image): from global memory, or from
 // the patch a block has staged in shared memory.
+// slk[2 a], slk[2 a + 1]: bounds of (position - lattice position) along axis a, in normalised units, over every data point the
+// source can deliver to this node (the staged patch of the block: the displacement maps are smooth, so the local range is
+// a fraction of the global +-maxdisp cells; the global bounds otherwise)
 template <class Src>
 __device__ __forceinline__ void remap3_locate_node(const Remap3Params &P, const Src &src, int i0, int i1, int i2,
-                                                   int64_t *__restrict__ tet, double *__restrict__ wgt, int *__restrict__ too_small)
+                                                   int64_t *__restrict__ tet, double *__restrict__ wgt, int *__restrict__ too_small,
+                                                   const double *slk)
 {
     const int64_t node = ((int64_t)i2 * P.ax[1].n + i1) * P.ax[0].n + i0;
     const double qx = (P.ax[0].origin + P.ax[0].delta * (i0 + 0.5) - P.ax[0].mn) / P.ax[0].rg;
@@ -419,22 +423,23 @@ __device__ __forceinline__ void remap3_locate_node(const Remap3Params &P, const 
             // sphere need a look: a point at lattice offset d sits within maxdisp cells of q + d h along every axis.
             const double lim = srad2 * (1.0 - 1e-10), rad = sqrt(srad2);
             const double h0 = P.ax[0].delta / P.ax[0].rg, h1 = P.ax[1].delta / P.ax[1].rg, h2 = P.ax[2].delta / P.ax[2].rg;
-            const int lo0 = max(-r0, (int)floor((scx - rad - qx) / h0 - P.ax[0].maxdisp)), hi0 = min(r0, (int)ceil((scx + rad - qx) / h0 + P.ax[0].maxdisp));
-            const int lo1 = max(-r1, (int)floor((scy - rad - qy) / h1 - P.ax[1].maxdisp)), hi1 = min(r1, (int)ceil((scy + rad - qy) / h1 + P.ax[1].maxdisp));
-            const int lo2 = max(-r2, (int)floor((scz - rad - qz) / h2 - P.ax[2].maxdisp)), hi2 = min(r2, (int)ceil((scz + rad - qz) / h2 + P.ax[2].maxdisp));
-            // ... and of that box only the part of every x row the sphere can reach: a point at lattice offset d lies within
-            // maxdisp cells of q + d h, so a row whose y / z distance to the centre (less that slack) exceeds the radius is
-            // skipped, and the others are cut to the chord of the sphere at that distance (the box alone holds 180 lattice
-            // points per node at 512 x 512 x 128 and 460 at 1024 x 1024 x 128: more than the scans of the search itself)
-            const double m0 = P.ax[0].maxdisp, m1h = P.ax[1].maxdisp * h1, m2h = P.ax[2].maxdisp * h2, wide2 = srad2 * (1.0 + 1e-9);
+            // a point at lattice offset d sits at q + d h + s with s inside [slk lo, slk hi] along every axis
+            const int lo0 = max(-r0, (int)floor((scx - rad - qx - slk[1]) / h0)), hi0 = min(r0, (int)ceil((scx + rad - qx - slk[0]) / h0));
+            const int lo1 = max(-r1, (int)floor((scy - rad - qy - slk[3]) / h1)), hi1 = min(r1, (int)ceil((scy + rad - qy - slk[2]) / h1));
+            const int lo2 = max(-r2, (int)floor((scz - rad - qz - slk[5]) / h2)), hi2 = min(r2, (int)ceil((scz + rad - qz - slk[4]) / h2));
+            // ... and of that box only the part of every x row the sphere can reach: a row whose y / z distance to the centre
+            // (less the slack) exceeds the radius is skipped, and the others are cut to the chord of the sphere at that
+            // distance (the box alone holds 180 lattice points per node at 512 x 512 x 128 and 460 at 1024 x 1024 x 128: more
+            // than the scans of the search itself)
+            const double wide2 = srad2 * (1.0 + 1e-9);
             for (int d2 = lo2; d2 <= hi2 && found; ++d2) {
-                const double ez = fabs(qz + d2 * h2 - scz) - m2h, rz2 = wide2 - (ez > 0 ? ez * ez : 0.0);
+                const double zc = qz + d2 * h2 - scz, ez = fmax(fmax(zc + slk[4], -(zc + slk[5])), 0.0), rz2 = wide2 - ez * ez;
                 if (rz2 < 0) continue;
                 for (int d1 = lo1; d1 <= hi1 && found; ++d1) {
-                    const double ey = fabs(qy + d1 * h1 - scy) - m1h, w2 = rz2 - (ey > 0 ? ey * ey : 0.0);
+                    const double yc = qy + d1 * h1 - scy, ey = fmax(fmax(yc + slk[2], -(yc + slk[3])), 0.0), w2 = rz2 - ey * ey;
                     if (w2 < 0) continue;
                     const double w = sqrt(w2);
-                    const int a0 = max(lo0, (int)floor((scx - w - qx) / h0 - m0)), b0 = min(hi0, (int)ceil((scx + w - qx) / h0 + m0));
+                    const int a0 = max(lo0, (int)floor((scx - w - qx - slk[1]) / h0)), b0 = min(hi0, (int)ceil((scx + w - qx - slk[0]) / h0));
                     const bool inner_row = d2 >= -R2 && d2 <= R2 && d1 >= -R1 && d1 <= R1;
                     for (int d0 = a0; d0 <= b0; ++d0) {
                         if (inner_row && d0 >= -R0 && d0 <= R0) { d0 = R0; continue; }      // skip the inner patch
@@ -496,7 +501,9 @@ __global__ void lfb_remap3d_locate(const Remap3Params P, const double *__restric
     const int i0 = blockIdx.x * blockDim.x + threadIdx.x, i1 = blockIdx.y, i2 = blockIdx.z;
     if (i0 >= P.ax[0].n) return;
     const Src3Global src = {P, xi0, xi1, xi2};
-    remap3_locate_node(P, src, i0, i1, i2, tet, wgt, too_small);
+    double slk[6];
+    for (int a = 0; a < 3; ++a) { slk[2 * a + 1] = P.ax[a].maxdisp * P.ax[a].delta / P.ax[a].rg * (1.0 + 1e-12); slk[2 * a] = -slk[2 * a + 1]; }
+    remap3_locate_node(P, src, i0, i1, i2, tet, wgt, too_small, slk);
 }
 
 // The same with the patch of a block of 32 x BY nodes staged once in shared memory (normalised positions of every
@@ -517,7 +524,7 @@ struct Src3Shared {
 };
 
 template <int R3_BY>
-__global__ void __launch_bounds__(R3_BX * R3_BY) lfb_remap3d_locate_smem(const Remap3Params P, const double *__restrict__ xi0,
+__global__ void __launch_bounds__(R3_BX * R3_BY, 1) lfb_remap3d_locate_smem(const Remap3Params P, const double *__restrict__ xi0,
                                                                         const double *__restrict__ xi1, const double *__restrict__ xi2,
                                                                         int64_t *__restrict__ tet, double *__restrict__ wgt,
                                                                         int *__restrict__ too_small)
@@ -528,17 +535,43 @@ __global__ void __launch_bounds__(R3_BX * R3_BY) lfb_remap3d_locate_smem(const R
     double *px = r3_smem, *py = px + ne, *pz = py + ne;
     const int n0 = blockIdx.x * R3_BX, n1 = blockIdx.y * R3_BY, i2 = blockIdx.z;
     const int b0 = n0 - r0, b1 = n1 - r1, b2 = i2 - r2;
+    // while staging: the range of (position - lattice position) over the patch, per axis (lo as a maximum of the negated value)
+    double sl[6] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
     for (int e = threadIdx.x; e < ne; e += blockDim.x) {
         const int q0 = e % e0, q1 = (e / e0) % e1, q2 = e / (e0 * e1);
         Cand3 t;
-        if (candidate3(P, xi0, xi1, xi2, b0 + q0, b1 + q1, b2 + q2, t)) { px[e] = t.x; py[e] = t.y; pz[e] = t.z; }
-        else { px[e] = INFINITY; py[e] = 0; pz[e] = 0; }
+        if (candidate3(P, xi0, xi1, xi2, b0 + q0, b1 + q1, b2 + q2, t)) {
+            px[e] = t.x; py[e] = t.y; pz[e] = t.z;
+            const double v[3] = {t.x, t.y, t.z};
+            const int pp[3] = {b0 + q0, b1 + q1, b2 + q2};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double off = v[a] - (P.ax[a].origin + P.ax[a].delta * (pp[a] + 0.5) - P.ax[a].mn) / P.ax[a].rg;
+                sl[2 * a] = fmax(sl[2 * a], -off); sl[2 * a + 1] = fmax(sl[2 * a + 1], off);
+            }
+        } else { px[e] = INFINITY; py[e] = 0; pz[e] = 0; }
+    }
+    __shared__ double r3_slack[R3_BY][6];
+#pragma unroll
+    for (int v = 0; v < 6; ++v) {
+        for (int o = 16; o > 0; o >>= 1) sl[v] = fmax(sl[v], __shfl_xor_sync(0xffffffffu, sl[v], o));
+        if ((threadIdx.x & 31) == 0) r3_slack[threadIdx.x >> 5][v] = sl[v];
     }
     __syncthreads();
     const int i0 = n0 + threadIdx.x % R3_BX, i1 = n1 + threadIdx.x / R3_BX;
     if (i0 >= P.ax[0].n || i1 >= P.ax[1].n) return;
+    double slk[6];
+#pragma unroll
+    for (int v = 0; v < 6; ++v) {
+        double m = r3_slack[0][v];
+        for (int w = 1; w < R3_BY; ++w) m = fmax(m, r3_slack[w][v]);
+        // widened by rounding room; an empty patch (no data point at all) leaves the global bound
+        const double g = P.ax[v / 2].maxdisp * P.ax[v / 2].delta / P.ax[v / 2].rg;
+        m = m > -1e300 ? m + 1e-12 : g;
+        slk[v] = (v & 1) ? m : -m;
+    }
     const Src3Shared src = {px, py, pz, b0, b1, b2, e0, e1};
-    remap3_locate_node(P, src, i0, i1, i2, tet, wgt, too_small);
+    remap3_locate_node(P, src, i0, i1, i2, tet, wgt, too_small, slk);
 }
 
 __global__ void lfb_remap3d_apply(const Remap3Params P, const int64_t *__restrict__ tet, const double *__restrict__ wgt,
