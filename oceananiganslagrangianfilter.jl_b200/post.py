@@ -311,6 +311,12 @@ def regrid_to_mean_position(config, out: FilterOutput, extra_vars_to_regrid: Seq
     if len(g.nonflat_axes) < 2:
         raise ValueError("regridding to the mean position needs at least two non-Flat axes (the reference's "
                          "LinearNDInterpolator does not exist in one dimension either)")
+    if pads_documented_column(g.topology):
+        log.warning("Regridding on a grid with a Bounded axis ahead of a Periodic one %s: the reference pads the wrong "
+                    "coordinate column there (post_processing_utils.jl:523-611: the column index only advances inside the "
+                    "periodic branches); lfb200 pads every Periodic axis's own coordinate, as the reference's comments and "
+                    "documentation describe, so the *_at_mean fields differ from the reference's on this topology "
+                    "(include/lfb200.h, lfb_remap_to_mean)", tuple(g.topology))
     for k in range(len(out.times)):
         xi = {vel: out.fields["xi_" + vel + label][k] for vel in config.velocity_names
               if "xi_" + vel + label in out.fields}
@@ -322,6 +328,13 @@ def regrid_to_mean_position(config, out: FilterOutput, extra_vars_to_regrid: Seq
     from .remap import remap_release
     remap_release()
     log.info("Wrote regridded data to new variables with _at_mean suffix")
+
+
+def pads_documented_column(topology) -> bool:
+    """True where the device remap deliberately departs from the reference: among the non-Flat axes a Bounded one comes
+    before a Periodic one, so the reference's padding loop (post:523-611) would pad the wrong coordinate column."""
+    axes = [t for t in topology if t != "Flat"]
+    return any(t == "Periodic" and "Bounded" in axes[:i] for i, t in enumerate(axes))
 
 
 def _immersed_mask(grid):

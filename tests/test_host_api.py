@@ -191,6 +191,17 @@ def test_integration_shim_binds_every_declared_symbol():
     assert not sorted(bound - set(declared)), "INTEGRATION.md binds symbols the header does not declare"
 
 
+def test_remap_padding_deviation_is_flagged():
+    """The one deliberate deviation of the device remap is announced exactly where it applies."""
+    from lfb200.post import pads_documented_column
+    assert not pads_documented_column(("Periodic", "Flat", "Bounded"))        # every example of the reference
+    assert not pads_documented_column(("Periodic", "Periodic", "Bounded"))
+    assert not pads_documented_column(("Bounded", "Bounded", "Bounded"))
+    assert pads_documented_column(("Bounded", "Periodic", "Bounded"))
+    assert pads_documented_column(("Bounded", "Flat", "Periodic"))
+    assert not pads_documented_column(("Flat", "Periodic", "Bounded"))
+
+
 def test_immersed_grid_host_evaluation():
     """ImmersedBoundaryGrid on the host: GridFittedBottom marks the cells whose centre lies at or below the bottom,
     PartialCellBottom the cells whose top face does (with the lowest wet cell capped at the minimum fraction of its
