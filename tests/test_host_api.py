@@ -227,3 +227,81 @@ def test_immersed_grid_host_evaluation():
         assert np.array_equal(s.immersed_flags(), P[:, 4 * r:4 * r + 10, :])
         assert np.array_equal(s.cell_heights(), Hh[:, 4 * r:4 * r + 10, :])
         assert np.array_equal(s.below_bottom_mask(), gp.below_bottom_mask()[:, 4 * r:4 * r + 10, :])
+
+
+class _FakeModel:
+    """Stands in for LagrangianFilter in the host-logic tests of the snapshot window (no device)."""
+
+    def __init__(self, n_slots, names=("u", "w", "b")):
+        self.n_slots = n_slots
+        self.velocities_present, self.var_names = [n for n in names if n in "uvw"], [n for n in names if n not in "uvw"]
+        self.slots = {}                 # slot -> (pass time, {name: file index})
+        self.uploads, self.direction, self.waits = [], 0, 0
+
+    def set_direction(self, d):
+        self.direction = d
+
+    def set_slot_time(self, slot, t):
+        self.slots[slot] = (t, self.slots[slot][1])
+
+    def invalidate_slot(self, slot):
+        self.slots.pop(slot, None)
+
+    def wait_transfers(self):
+        self.waits += 1
+
+    def upload_snapshot(self, slot, name, arr, t, wait=False):
+        held = self.slots.get(slot, (t, {}))[1] if self.slots.get(slot, (None,))[0] == t else {}
+        held[name] = int(arr[0])
+        self.slots[slot] = (t, held)
+        self.uploads.append((slot, name, int(arr[0]), t))
+
+
+class _FakeSource:
+    def __init__(self, times):
+        self.times = list(times)
+
+    def snapshot(self, name, n):
+        return np.array([n], dtype=np.float32)
+
+
+def test_snapshot_window_resident_and_streamed():
+    """SnapshotFeeder (the reference's FieldTimeSeries InMemory(4) window, utils:211-212; backward pass = the same
+    snapshots re-tagged T_end - t, utils:97-180): resident series are uploaded once and only re-tagged for the
+    backward pass; streamed series keep the snapshots bracketing every step resident and never use more than n_slots."""
+    from lfb200.offline import SnapshotFeeder
+    times = [10.0, 11.0, 12.0, 13.0, 14.0]
+    idx = [0, 1, 2, 3, 4]
+    # all resident
+    m = _FakeModel(n_slots=5)
+    f = SnapshotFeeder(m, _FakeSource(times), idx, times, 10.0, 14.0)
+    f.begin(+1)
+    assert len(m.uploads) == 5 * 3 and m.direction == 1
+    assert [m.slots[s][0] for s in range(5)] == [0.0, 1.0, 2.0, 3.0, 4.0]
+    f.ensure(0.0, 4.0)
+    f.begin(-1)
+    assert len(m.uploads) == 15, "the backward pass must not upload again"
+    assert [m.slots[s][0] for s in range(5)] == [4.0, 3.0, 2.0, 1.0, 0.0] and m.direction == -1
+    assert all(m.slots[s][1] == {"u": s, "w": s, "b": s} for s in range(5))
+    # streamed through two slots, forward then reversed
+    for direction in (+1, -1):
+        m = _FakeModel(n_slots=2)
+        f = SnapshotFeeder(m, _FakeSource(times), idx, times, 10.0, 14.0)
+        f.begin(direction)
+        t = 0.0
+        while t < 4.0 - 1e-12:
+            f.ensure(t, t + 0.25)
+            assert len(m.slots) <= 2
+            tags = sorted(tag for tag, _ in m.slots.values())
+            assert tags[0] <= t + 1e-12 and tags[-1] >= t + 0.25 - 1e-12, (direction, t, tags)
+            for tag, held in m.slots.values():
+                want = int(round(tag)) if direction > 0 else 4 - int(round(tag))     # file index behind a pass time
+                assert held == {"u": want, "w": want, "b": want}
+            t += 0.25
+        assert len(m.uploads) == 5 * 3, "every snapshot travels once per pass"
+    # a step that spans more snapshots than there are slots is refused with a clear message
+    m = _FakeModel(n_slots=2)
+    f = SnapshotFeeder(m, _FakeSource(times), idx, times, 10.0, 14.0)
+    f.begin(+1)
+    with pytest.raises(RuntimeError, match="slots"):
+        f.ensure(0.5, 2.5)
