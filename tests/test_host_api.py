@@ -305,3 +305,66 @@ def test_snapshot_window_resident_and_streamed():
     f.begin(+1)
     with pytest.raises(RuntimeError, match="slots"):
         f.ensure(0.5, 2.5)
+
+
+class _FakeKeptModel:
+    """Device-resident pass outputs as ids of small numpy arrays; counts allocations and releases."""
+
+    def __init__(self):
+        self.store, self.next_id, self.released, self.log = {}, 1, [], []
+
+    def new(self, arr):
+        kid = self.next_id
+        self.next_id += 1
+        self.store[kid] = np.array(arr, dtype=np.float64)
+        return kid
+
+    def kept_combine(self, f, lo, hi, w, sign):
+        b = self.store[lo] if hi is None else (1.0 - w) * self.store[lo] + w * self.store[hi]
+        self.log.append((f, lo, hi, w, sign))
+        return self.new(self.store[f] + sign * b)
+
+    def kept_gather(self, kid, root):
+        return kid
+
+    def kept_release(self, kid):
+        assert kid in self.store, f"released twice or never allocated: {kid}"
+        self.released.append(kid)
+        del self.store[kid]
+
+    def kept_fetch(self, kid, alloc=None, wait=True):
+        return self.store[kid].copy()
+
+    def wait_transfers(self):
+        pass
+
+
+def test_forward_backward_combiner_plan_and_block_bookkeeping():
+    """sum_forward_backward_contributions! (post:45-170) on device-resident outputs: out(t_k) = fwd(t_k) +- bwd(T - t_k)
+    (minus for the mean velocities), every forward time combined as soon as its backward partner is fed, and every
+    device block released exactly once."""
+    from types import SimpleNamespace
+    from lfb200.post import ForwardBackwardCombiner
+    cfg = SimpleNamespace(label="", advection="WENO", velocity_names=("u",), compute_mean_velocities=True, T=4.0,
+                          var_names_to_filter=("b",), map_to_mean=True)
+    names = ["b_Lagrangian_filtered", "xi_u", "u_Lagrangian_filtered"]
+    m = _FakeKeptModel()
+    times = [0.0, 1.0, 2.0, 3.0, 4.0]
+    val = lambda pas, t, q: np.array([100.0 * pas + 10.0 * t + q, 1.0])
+    fwd = {t: {n: m.new(val(1, t, q)) for q, n in enumerate(names)} for t in times}
+    c = ForwardBackwardCombiner(cfg, fwd, {t: int(8 * t) for t in times}, m)
+    combined_after = []
+    for tb in times:
+        c.feed(tb, {n: m.new(val(2, tb, q)) for q, n in enumerate(names)})
+        combined_after.append(sorted(c.done))
+    # forward time t_k waits for backward pass time T - t_k: the last forward time is combined first
+    assert combined_after == [[4], [3, 4], [2, 3, 4], [1, 2, 3, 4], [0, 1, 2, 3, 4]]
+    out = c.finish()
+    assert out.times == times and out.iterations == [0, 8, 16, 24, 32]
+    for k, t in enumerate(times):
+        for q, n in enumerate(names):
+            sign = -1.0 if n == "u_Lagrangian_filtered" else 1.0
+            np.testing.assert_array_equal(out.fields[n][k], val(1, t, q) + sign * val(2, 4.0 - t, q))
+    assert not m.store, f"device blocks never released: {sorted(m.store)}"
+    assert len(m.released) == len(set(m.released)) == 3 * (5 + 5 + 5)       # forward, backward and combined blocks
+    assert all(hi is None and w == 0.0 for _, _, hi, w, _ in m.log)         # same aligned steps: no interpolation needed
