@@ -262,17 +262,15 @@ __device__ __forceinline__ double zt_face(unsigned a, double q, const ZtK &K)
 #if ZT_UPS
     // sign-mask addressing, see zt_face_up
     const int s = __double2hiint(q) >> 31;
-    {
-        const double n = lds(a - S - s * S), e = lds(a + s * S), o = lds(a - 2 * S - s * (3 * S));
-        const double f = lds(a + S + s * (3 * S)), p = lds(a - 3 * S - s * (5 * S));
-        return n + zt_inc(o - p, n - o, e - n, f - e, K);
-    }
-#endif
+    const double n = lds(a - S - s * S), e = lds(a + s * S), o = lds(a - 2 * S - s * (3 * S));
+    const double f = lds(a + S + s * (3 * S)), p = lds(a - 3 * S - s * (5 * S));
+#else
     const bool left = zt_positive(q);
     const int step = left ? S : -S;
     const unsigned an = left ? a - S : a;
     const double n = lds(an), e = lds(an + step), o = lds(an - step);
     const double f = lds(an + 2 * step), p = lds(an - 2 * step);
+#endif
     return n + zt_inc(o - p, n - o, e - n, f - e, K);
 }
 
@@ -1059,7 +1057,7 @@ extern "C" int lfb_ztma_supported(const LfbStageParams *P)
     const bool fold = zt_foldable(L);
     if (!fold && (L.topo[0] == LFB_FLAT || L.topo[1] == LFB_FLAT || L.topo[2] == LFB_FLAT)) return 0;
     if (L.topo[2] == LFB_PERIODIC && L.N[2] < 2 * L.H[2]) return 0;
-    if (L.plane >= ((int64_t)1 << 31)) return 0;                   // 32-bit offsets of the periodic images within a plane
+    if (L.plane >= ((int64_t)1 << 30)) return 0;                   // 32-bit offsets of the periodic images within a plane
     if (!(P->vel_present[0] || P->vel_present[1] || P->vel_present[2])) return 0;     // absent components: a zero field
     if (L.N[0] < 8 || (!fold && L.N[1] < 4) || L.N[2] < 8) return 0;
     if (L.H[0] < 3 || (!fold && L.H[1] < 3) || L.H[2] < 3) return 0;
