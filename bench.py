@@ -482,10 +482,10 @@ def main():
                             "the HBM peak at 1965 MHz and 55 % at the ~1750 MHz the power cap allows; see DESIGN.md section 5"}
         cpu = None
         if not args.no_cpu and world == 1:
-            rate, cms, cores = cpu_port_rate(args.cpu_size, 12, 2)
+            rate, cms, cores = cpu_port_rate(args.cpu_size, 24, 2)
             cs = args.cpu_size
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{cs[0]}x{cs[1]}x{cs[2]} sub-grid of the workload, 12 RK3 steps after 2 warm-up, OpenMP with "
+                   "sample": f"{cs[0]}x{cs[1]}x{cs[2]} sub-grid of the workload, 24 RK3 steps after 2 warm-up, OpenMP with "
                              f"omp_get_max_threads() = {cores} ({cms:.0f} ms/step)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
