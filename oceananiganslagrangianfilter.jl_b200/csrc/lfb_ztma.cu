@@ -19,7 +19,7 @@
 //   * upwinding is done on addresses, not values: the five cells of a face stencil are loaded in upwind order
 //     (mirrored shared-memory addressing), so no FP64 select or negation is executed; along z the register
 //     window is used by a warp-uniform branch per direction;
-//   * the arithmetic per face is short (47 FP64 instructions in x / y, 36 in z): smoothness indicators scaled
+//   * the arithmetic per face is short (46 FP64 instructions in x / y, 35 in z): smoothness indicators scaled
 //     by 4/3 with eps folded into the curvature term, the blend written as x1 - (A0 y0 / 2 + A2 y2 / 3) / den
 //     with y = second differences already at hand, a cubic reciprocal refinement folded into the last FMA,
 //     fluxes and divergences in units of face velocity (areas / volume applied once per axis);
